@@ -1,0 +1,168 @@
+/* paillier_b200.h — C ABI of the B200-native batched Paillier hot path.
+ *
+ * Drop-in boundary for ONE path of aerius-labs/paillier-halo2: batched encryption
+ * c = g^m * r^n mod n^2, homomorphic addition c1*c2 mod n^2, their N-ary fold (tally) and the
+ * per-step (q, rem) witness values that PaillierChip::encrypt/add assign through BigUintChip.
+ * The reference has no FFI of its own; each entry point below names the reference interface it
+ * replaces (paths into the reference repository).  The Rust-side binding a maintainer would add
+ * is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all integers are little-endian arrays of uint64_t words ("u64 limbs"); word i has weight
+ *     2^(64 i), the same order PaillierChip::get_biguint folds (src/paillier.rs:22-30);
+ *   - a value of b bits occupies  PB200_WORDS(b) = ceil(b/64) words; unused high bits are zero;
+ *   - batches are unit-major and contiguous: unit u starts at word u * words_per_value;
+ *   - every function returns 0 (PB200_OK) or a negative pb200_status; nothing throws or aborts
+ *     across the ABI (maps to Result<_, Error> on the Rust side, src/paillier.rs:38,68);
+ *   - the caller owns every buffer it passes; the library owns a pb200_key until
+ *     pb200_key_destroy;  a key is bound to one CUDA device and one internal stream; calls on one
+ *     key are serialised by the caller (mirrors &mut Context<F>), different keys may be used from
+ *     different threads;
+ *   - functions with the suffix _dev take DEVICE pointers (resident in the key's device) and
+ *     enqueue on the key's stream without a final synchronise unless stated; the others take HOST
+ *     pointers and return when the result is in the output buffer;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point returns
+ *     PB200_ERR_CUDA.
+ */
+#ifndef PAILLIER_B200_H
+#define PAILLIER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_WORDS(bits) (((bits) + 63) / 64)
+
+typedef enum pb200_status {
+    PB200_OK = 0,
+    PB200_ERR_INVALID_ARG = -1,   /* null pointer, zero sizes, n_bits % limb_bits != 0 (assign_integer's assert) */
+    PB200_ERR_ZERO_MODULUS = -2,  /* n == 0: num-bigint modpow / % panic (src/paillier.rs:89-91,96) */
+    PB200_ERR_EVEN_MODULUS = -3,  /* n even: outside the GPU path's contract (a Paillier n = p*q is odd) */
+    PB200_ERR_RANGE = -4,         /* an input does not fit its declared bit width (range check would fail) */
+    PB200_ERR_UNSUPPORTED = -5,   /* key size larger than the largest compiled engine */
+    PB200_ERR_CUDA = -6,          /* CUDA runtime failure; pb200_last_cuda_error() has the text */
+    PB200_ERR_NOMEM = -7,
+    PB200_ERR_SINK = -8           /* the witness sink callback returned non-zero */
+} pb200_status;
+
+typedef struct pb200_key pb200_key;
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* pb200_strerror(int status);
+const char* pb200_last_cuda_error(void);      /* thread-local text of the last CUDA failure */
+const char* pb200_version(void);
+int pb200_device_count(void);                 /* number of visible CUDA devices, 0 if none */
+/* number of kernel launches issued by this library since load (all threads); bench.py reports it */
+uint64_t pb200_kernel_launches(void);
+
+/* ---- key ------------------------------------------------------------------------------------
+ * Replaces: EncryptionPublicKeyAssigned{n,g} + PaillierChip::construct (src/paillier.rs:6-20) and
+ * the per-call recomputation of n^2 by square+refresh (src/paillier.rs:39-45, :69-75) / n*n
+ * (:88, :95).  n_bits = enc_bits of the reference (bit width n, g, m, r are assigned with,
+ * src/bench.rs:44-60); limb_bits = BigUintChip limb width (64 and 88 in the reference's tests),
+ * only used to format witness limbs.  n and g are PB200_WORDS(n_bits) words each. */
+int pb200_key_create(int device, uint32_t n_bits, uint32_t limb_bits,
+                     const uint64_t* n_le, const uint64_t* g_le, pb200_key** out);
+void pb200_key_destroy(pb200_key* key);
+uint32_t pb200_key_n_bits(const pb200_key* key);
+uint32_t pb200_key_words_in(const pb200_key* key);   /* PB200_WORDS(n_bits)   : n, g, m, r        */
+uint32_t pb200_key_words_out(const pb200_key* key);  /* PB200_WORDS(2*n_bits) : n^2, c, q, rem    */
+int pb200_key_device(const pb200_key* key);
+/* n^2 (words_out words) — value of the Fresh n2 of src/paillier.rs:45 */
+int pb200_key_n2(const pb200_key* key, uint64_t* n2_out);
+/* name of the arithmetic engine selected for this key size, e.g. "block28<8,19>" or "simple64" */
+const char* pb200_key_engine(const pb200_key* key);
+/* choose the engine explicitly: 0 = automatic (fastest available), 1 = simple64 (thread per
+ * ciphertext, always available, used as the on-GPU cross-check), 2 = block28 (warp-role Barrett) */
+int pb200_key_set_engine(pb200_key* key, int engine);
+void* pb200_key_stream(const pb200_key* key);        /* cudaStream_t the key enqueues on */
+int pb200_key_sync(pb200_key* key);                  /* cudaStreamSynchronize on that stream */
+
+/* ---- encrypt --------------------------------------------------------------------------------
+ * Replaces: paillier_enc_native (src/paillier.rs:87-92) for `count` independent (m, r) pairs, and
+ * the VALUE returned by PaillierChip::encrypt (src/paillier.rs:32-60).
+ * m, r: count * words_in words; c_out: count * words_out words, canonical (< n^2).
+ * PB200_ERR_RANGE if any m or r has bits at or above n_bits (host variant only). */
+int pb200_encrypt_batch(pb200_key* key, const uint64_t* m_le, const uint64_t* r_le, size_t count,
+                        uint64_t* c_out_le);
+int pb200_encrypt_batch_dev(pb200_key* key, const uint64_t* d_m_le, const uint64_t* d_r_le,
+                            size_t count, uint64_t* d_c_out_le);
+
+/* ---- add ------------------------------------------------------------------------------------
+ * Replaces: paillier_add_native (src/paillier.rs:94-97) and PaillierChip::add (:62-85) for `count`
+ * pairs.  c_words = words per input ciphertext: words_out for real ciphertexts, words_in for the
+ * half-width values the reference's tests assign (src/paillier.rs:216-221; extend_limbs at :79-80
+ * zero-pads them).  out: count * words_out words.  q_out (nullable): floor(c1*c2 / n^2), the mul_mod
+ * quotient witness, count * words_out words. */
+int pb200_add_batch(pb200_key* key, const uint64_t* c1_le, const uint64_t* c2_le, uint32_t c_words,
+                    size_t count, uint64_t* out_le, uint64_t* q_out_le);
+int pb200_add_batch_dev(pb200_key* key, const uint64_t* d_c1_le, const uint64_t* d_c2_le, uint32_t c_words,
+                        size_t count, uint64_t* d_out_le, uint64_t* d_q_out_le);
+
+/* ---- tally ----------------------------------------------------------------------------------
+ * Replaces: the N-ary fold of paillier_add_native (BASELINE.json config 3).  Product of `count`
+ * ciphertexts (words_out words each) mod n^2 on the key's device; count == 0 gives 1 mod n^2.
+ * The product is commutative and associative, so the result is independent of the tree shape.
+ * _dev: d_c on the key's device, d_partial_out receives one words_out-word value on the device. */
+int pb200_tally(pb200_key* key, const uint64_t* c_le, size_t count, uint64_t* out_le);
+int pb200_tally_dev(pb200_key* key, const uint64_t* d_c_le, size_t count, uint64_t* d_partial_out_le);
+/* combine `n_partials` per-shard partial products (host memory, e.g. gathered from the other
+ * ranks with NCCL all-gather or a host gather) into the final product on the key's device */
+int pb200_tally_combine(pb200_key* key, const uint64_t* partials_le, size_t n_partials, uint64_t* out_le);
+
+/* ---- witness --------------------------------------------------------------------------------
+ * Replaces: the witness generation inside BigUintChip::pow_mod_fixed_exp / mul_mod that
+ * PaillierChip::encrypt drives (src/paillier.rs:51,55,57).  Every mul_mod(a, b, n^2) of the chain
+ * contributes one RECORD = q (words_out words) followed by rem (words_out words) with
+ * q = floor(a*b / n^2), rem = a*b mod n^2.  Chain order per unit:
+ *   g-chain : for bit i of m, low to high:  sqr_i = (g^(2^i))^2 ;  if bit set: mul = acc * g^(2^i)
+ *   r-chain : for bit i of n, low to high:  sqr_i = (r^(2^i))^2 ;  if bit set: mul = acc * r^(2^i)
+ *   final   : gm * rn
+ * The g-chain squarings depend on the key only; they are produced once per key
+ * (pb200_key_g_chain) and are NOT repeated in the per-unit stream.  The per-unit stream therefore
+ * holds, in order: popcount(m) g-chain mul records, bits(n)+popcount(n) r-chain records (sqr and
+ * mul interleaved as above), 1 final record. */
+typedef struct pb200_witness_chunk {
+    size_t first_unit;             /* index of the first unit in this chunk                        */
+    size_t n_units;                /* units in this chunk                                          */
+    uint32_t words_out;            /* words per q / per rem                                        */
+    const uint64_t* offsets;       /* n_units+1 record offsets into `records` (unit u: [off[u], off[u+1])) */
+    const uint64_t* records;       /* records, each 2*words_out words: q then rem                  */
+    const uint32_t* g_mul_counts;  /* n_units: number of g-chain mul records at the head of each unit */
+} pb200_witness_chunk;
+
+/* called on the calling thread, chunk memory is valid only during the call; return 0 to continue */
+typedef int (*pb200_witness_sink_fn)(void* user, const pb200_witness_chunk* chunk);
+
+/* max_chunk_units == 0 lets the library size chunks to its staging buffers */
+int pb200_encrypt_witness_batch(pb200_key* key, const uint64_t* m_le, const uint64_t* r_le, size_t count,
+                                uint64_t* c_out_le /* nullable */, size_t max_chunk_units,
+                                pb200_witness_sink_fn sink, void* user);
+
+/* number of records unit (m) contributes to the per-unit stream: popcount(m) + bits(n) + popcount(n) + 1 */
+uint64_t pb200_witness_records_for(const pb200_key* key, const uint64_t* m_le);
+
+/* 64-bit FNV-1a digests of each unit's record stream (all words, little-endian byte order),
+ * computed on the device without materialising the witness on the host: digest_out[count]. */
+int pb200_encrypt_witness_digest(pb200_key* key, const uint64_t* m_le, const uint64_t* r_le, size_t count,
+                                 uint64_t* c_out_le /* nullable */, uint64_t* digest_out);
+
+/* per-key g-chain squarings: record i (i < n_bits) = (q, rem) of (g^(2^i) mod n^2)^2 mod n^2.
+ * out: n_bits * 2 * words_out words. */
+int pb200_key_g_chain(pb200_key* key, uint64_t* records_out);
+
+/* ---- limb formatting (K5) ------------------------------------------------------------------
+ * Replaces: decompose_biguint inside BigUintChip::assign_integer for limb_bits != 64
+ * (src/paillier.rs:187 uses 88).  Pure bit repack, host-side convenience over a device kernel:
+ * values of `value_bits` bits (PB200_WORDS words each) -> value_bits/limb_bits limbs, each limb
+ * stored in 2 words (low, high) so that 64 < limb_bits <= 128 fits. */
+int pb200_repack_limbs(pb200_key* key, const uint64_t* values_le, size_t count, uint32_t value_bits,
+                       uint32_t limb_bits, uint64_t* limbs_out /* count * (value_bits/limb_bits) * 2 words */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAILLIER_B200_H */

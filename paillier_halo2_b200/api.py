@@ -1,0 +1,252 @@
+"""Host-side mirror of the reference's interface for the Paillier hot path, over the C ABI.
+
+The reference exposes this path as two pure functions and one chip
+(`paillier_enc_native`, `paillier_add_native`, `PaillierChip::{construct, encrypt, add}`;
+src/paillier.rs:87-97, :11-85).  The batched equivalents keep the names and argument meaning:
+
+    key = PaillierKey(n, g, enc_bits, limb_bits)          # EncryptionPublicKeyAssigned + construct
+    cs  = key.paillier_enc_native(ms, rs)                 # src/paillier.rs:87-92, per (m, r) pair
+    ss  = key.paillier_add_native(c1s, c2s)               # src/paillier.rs:94-97, per pair
+    t   = key.tally(cs)                                   # N-ary fold of paillier_add_native
+
+Every call goes to CUDA through libpaillier_b200.so; nothing here computes a ciphertext on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import Pb200Error, check  # noqa: F401
+
+
+def words(bits: int) -> int:
+    return (bits + 63) // 64
+
+
+def ints_to_words(vals: Sequence[int], nwords: int) -> np.ndarray:
+    """Python ints -> (len, nwords) little-endian uint64 array.  Raises OverflowError if one does not fit."""
+    out = np.empty((len(vals), nwords), dtype="<u8")
+    nbytes = nwords * 8
+    for i, v in enumerate(vals):
+        out[i] = np.frombuffer(int(v).to_bytes(nbytes, "little"), dtype="<u8")
+    return out
+
+
+def words_to_ints(arr: np.ndarray) -> List[int]:
+    arr = np.ascontiguousarray(arr, dtype="<u8")
+    if arr.ndim == 1:
+        arr = arr.reshape(1, -1)
+    return [int.from_bytes(row.tobytes(), "little") for row in arr]
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(_lib.u64p)
+
+
+class PaillierKey:
+    """EncryptionPublicKeyAssigned{n, g} (src/paillier.rs:6-9) bound to one CUDA device."""
+
+    def __init__(self, n: int, g: int, enc_bits: int, limb_bits: int = 64, device: int = 0):
+        self._lib = _lib.load()
+        self.enc_bits = enc_bits
+        self.limb_bits = limb_bits
+        self.n = n
+        self.g = g
+        win = words(enc_bits)
+        try:
+            n_w = ints_to_words([n], win)
+            g_w = ints_to_words([g], win)
+        except OverflowError:
+            raise Pb200Error(_lib.PB200_ERR_RANGE, "PaillierKey")
+        h = C.c_void_p()
+        check(self._lib.pb200_key_create(device, enc_bits, limb_bits, _p(n_w), _p(g_w), C.byref(h)), "pb200_key_create")
+        self._h = h
+        self.words_in = self._lib.pb200_key_words_in(h)
+        self.words_out = self._lib.pb200_key_words_out(h)
+        self.device = device
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.pb200_key_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- properties ---------------------------------------------------------------------------
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def engine(self) -> str:
+        return self._lib.pb200_key_engine(self._h).decode()
+
+    def set_engine(self, engine: int) -> None:
+        check(self._lib.pb200_key_set_engine(self._h, engine), "pb200_key_set_engine")
+
+    def n2(self) -> int:
+        out = np.zeros(self.words_out, dtype="<u8")
+        check(self._lib.pb200_key_n2(self._h, _p(out)), "pb200_key_n2")
+        return words_to_ints(out)[0]
+
+    def sync(self) -> None:
+        check(self._lib.pb200_key_sync(self._h), "pb200_key_sync")
+
+    # -- raw array API (uint64 little-endian words, unit-major) -----------------------------
+    def encrypt_words(self, m_w: np.ndarray, r_w: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        m_w = np.ascontiguousarray(m_w, dtype="<u8")
+        r_w = np.ascontiguousarray(r_w, dtype="<u8")
+        count = m_w.shape[0]
+        assert m_w.shape == (count, self.words_in) and r_w.shape == m_w.shape
+        if out is None:
+            out = np.empty((count, self.words_out), dtype="<u8")
+        check(self._lib.pb200_encrypt_batch(self._h, _p(m_w), _p(r_w), count, _p(out)), "pb200_encrypt_batch")
+        return out
+
+    def add_words(self, c1_w: np.ndarray, c2_w: np.ndarray, want_q: bool = False):
+        c1_w = np.ascontiguousarray(c1_w, dtype="<u8")
+        c2_w = np.ascontiguousarray(c2_w, dtype="<u8")
+        count, cw = c1_w.shape
+        assert c2_w.shape == c1_w.shape
+        out = np.empty((count, self.words_out), dtype="<u8")
+        q = np.empty((count, self.words_out), dtype="<u8") if want_q else None
+        check(self._lib.pb200_add_batch(self._h, _p(c1_w), _p(c2_w), cw, count, _p(out), _p(q) if want_q else None),
+              "pb200_add_batch")
+        return (out, q) if want_q else out
+
+    def tally_words(self, c_w: np.ndarray) -> np.ndarray:
+        c_w = np.ascontiguousarray(c_w, dtype="<u8").reshape(-1, self.words_out)
+        out = np.empty(self.words_out, dtype="<u8")
+        check(self._lib.pb200_tally(self._h, _p(c_w) if c_w.shape[0] else None, c_w.shape[0], _p(out)), "pb200_tally")
+        return out
+
+    def tally_combine_words(self, partials_w: np.ndarray) -> np.ndarray:
+        partials_w = np.ascontiguousarray(partials_w, dtype="<u8").reshape(-1, self.words_out)
+        out = np.empty(self.words_out, dtype="<u8")
+        check(self._lib.pb200_tally_combine(self._h, _p(partials_w), partials_w.shape[0], _p(out)), "pb200_tally_combine")
+        return out
+
+    # -- reference-named API on Python ints ---------------------------------------------------
+    def paillier_enc_native(self, ms: Sequence[int], rs: Sequence[int]) -> List[int]:
+        """Batched src/paillier.rs:87-92 under this key's (n, g)."""
+        try:
+            m_w = ints_to_words(ms, self.words_in)
+            r_w = ints_to_words(rs, self.words_in)
+        except OverflowError:
+            raise Pb200Error(_lib.PB200_ERR_RANGE, "paillier_enc_native")
+        return words_to_ints(self.encrypt_words(m_w, r_w)) if len(ms) else []
+
+    def paillier_add_native(self, c1s: Sequence[int], c2s: Sequence[int], c_bits: Optional[int] = None,
+                            want_q: bool = False):
+        """Batched src/paillier.rs:94-97.  c_bits = width the inputs are assigned with (enc_bits in the
+        reference's tests, 2*enc_bits for real ciphertexts; default 2*enc_bits)."""
+        cw = words(c_bits if c_bits is not None else 2 * self.enc_bits)
+        try:
+            a = ints_to_words(c1s, cw)
+            b = ints_to_words(c2s, cw)
+        except OverflowError:
+            raise Pb200Error(_lib.PB200_ERR_RANGE, "paillier_add_native")
+        if not len(c1s):
+            return ([], []) if want_q else []
+        if want_q:
+            out, q = self.add_words(a, b, True)
+            return words_to_ints(out), words_to_ints(q)
+        return words_to_ints(self.add_words(a, b))
+
+    def tally(self, cs: Sequence[int]) -> int:
+        c_w = ints_to_words(cs, self.words_out) if len(cs) else np.empty((0, self.words_out), dtype="<u8")
+        return words_to_ints(self.tally_words(c_w))[0]
+
+    # -- witness ------------------------------------------------------------------------------
+    def g_chain(self) -> List[Tuple[int, int]]:
+        """Per-key records (q, rem) of the g-chain squarings, i < enc_bits."""
+        out = np.empty((self.enc_bits, 2, self.words_out), dtype="<u8")
+        check(self._lib.pb200_key_g_chain(self._h, _p(out)), "pb200_key_g_chain")
+        return [(words_to_ints(out[i, 0])[0], words_to_ints(out[i, 1])[0]) for i in range(self.enc_bits)]
+
+    def encrypt_witness(self, ms: Sequence[int], rs: Sequence[int], max_chunk_units: int = 0,
+                        on_chunk: Optional[Callable] = None):
+        """Returns (ciphertexts, per-unit list of (q, rem) records, per-unit g-chain mul counts).
+        With `on_chunk`, chunks are handed to the callback as numpy views and not accumulated."""
+        m_w = ints_to_words(ms, self.words_in)
+        r_w = ints_to_words(rs, self.words_in)
+        count = len(ms)
+        c_out = np.empty((count, self.words_out), dtype="<u8")
+        units: List[List[Tuple[int, int]]] = []
+        gcounts: List[int] = []
+        wo = self.words_out
+
+        def sink(_user, chp):
+            ch = chp.contents
+            nu = ch.n_units
+            offs = np.ctypeslib.as_array(ch.offsets, shape=(nu + 1,))
+            total = int(offs[nu])
+            recs = np.ctypeslib.as_array(ch.records, shape=(total, 2, wo))
+            gc = np.ctypeslib.as_array(ch.g_mul_counts, shape=(nu,))
+            if on_chunk is not None:
+                return int(on_chunk(ch.first_unit, offs, recs, gc) or 0)
+            for u in range(nu):
+                rr = recs[int(offs[u]):int(offs[u + 1])]
+                units.append([(int.from_bytes(x[0].tobytes(), "little"), int.from_bytes(x[1].tobytes(), "little")) for x in rr])
+                gcounts.append(int(gc[u]))
+            return 0
+
+        cb = _lib.SINK_FN(sink)
+        check(self._lib.pb200_encrypt_witness_batch(self._h, _p(m_w), _p(r_w), count, _p(c_out), max_chunk_units, cb, None),
+              "pb200_encrypt_witness_batch")
+        return words_to_ints(c_out) if count else [], units, gcounts
+
+    def encrypt_witness_digest(self, ms: Sequence[int], rs: Sequence[int]):
+        m_w = ints_to_words(ms, self.words_in)
+        r_w = ints_to_words(rs, self.words_in)
+        count = len(ms)
+        c_out = np.empty((count, self.words_out), dtype="<u8")
+        dig = np.empty(count, dtype="<u8")
+        check(self._lib.pb200_encrypt_witness_digest(self._h, _p(m_w), _p(r_w), count, _p(c_out), _p(dig)),
+              "pb200_encrypt_witness_digest")
+        return (words_to_ints(c_out) if count else []), [int(d) for d in dig]
+
+    def witness_records_for(self, m: int) -> int:
+        return int(self._lib.pb200_witness_records_for(self._h, _p(ints_to_words([m], self.words_in))))
+
+    def repack_limbs(self, vals: Sequence[int], value_bits: int, limb_bits: int) -> List[List[int]]:
+        """decompose_biguint for limb_bits != 64 (K5): returns value_bits/limb_bits limbs per value."""
+        v_w = ints_to_words(vals, words(value_bits))
+        nl = value_bits // limb_bits
+        out = np.empty((len(vals), nl, 2), dtype="<u8")
+        check(self._lib.pb200_repack_limbs(self._h, _p(v_w), len(vals), value_bits, limb_bits, _p(out)), "pb200_repack_limbs")
+        return [[int(out[i, j, 0]) | (int(out[i, j, 1]) << 64) for j in range(nl)] for i in range(len(vals))]
+
+
+MASK64 = (1 << 64) - 1
+DIGEST_INIT = 0xCBF29CE484222325
+DIGEST_PRIME = 0x100000001B3
+DIGEST_C = 0x9E3779B97F4A7C15
+
+
+def witness_digest(records: Iterable[Tuple[int, int]], words_out: int) -> int:
+    """Host restatement of the device digest (include/paillier_b200.h): per record
+    H = sum_j w_j * C^(j+1) mod 2^64 over the 2*words_out words (q then rem); D = (D ^ H) * PRIME."""
+    d = DIGEST_INIT
+    for q, rem in records:
+        h = 0
+        c = DIGEST_C
+        for v in (q, rem):
+            for j in range(words_out):
+                h = (h + ((v >> (64 * j)) & MASK64) * c) & MASK64
+                c = (c * DIGEST_C) & MASK64
+        d = ((d ^ h) * DIGEST_PRIME) & MASK64
+    return d

@@ -1,0 +1,374 @@
+// capi.cu — the C ABI declared in include/paillier_b200.h.
+//
+// Host-side glue only: validation (the reference's range checks / panics mapped to status codes),
+// per-key constant setup, staging copies and engine dispatch.  All arithmetic per ciphertext runs in
+// CUDA kernels (block28_kernels.cu, simple64_kernels.cu); there is no CPU fallback.
+#include "../../include/paillier_b200.h"
+#include "engine.hpp"
+#include <cstring>
+#include <mutex>
+#include <new>
+
+using namespace pb200;
+
+static thread_local std::string t_cuda_error;
+
+static int cuda_fail(cudaError_t e, const char* where) {
+    t_cuda_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return PB200_ERR_CUDA;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+struct DevBuf {  // grow-only device buffer
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct pb200_key {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t n_bits = 0, limb_bits = 0, words_in = 0, words_out = 0;
+    BigInt n, g, n2;
+    SimpleConsts* d_simple = nullptr;
+    u64* d_gchain = nullptr;        // lazy: n_bits records
+    int* d_flags = nullptr;
+    Block28Key* fast = nullptr;
+    std::string fast_why;
+    int engine = 0;                 // 0 auto, 1 simple64, 2 block28
+    DevBuf in_a, in_b, out_a, out_b, scratch, offs;
+    std::string engine_name;
+};
+
+static bool use_fast(const pb200_key* k) { return k->fast && k->engine != 1; }
+
+extern "C" {
+
+const char* pb200_strerror(int s) {
+    switch (s) {
+        case PB200_OK: return "ok";
+        case PB200_ERR_INVALID_ARG: return "invalid argument";
+        case PB200_ERR_ZERO_MODULUS: return "modulus n is zero (num-bigint would panic)";
+        case PB200_ERR_EVEN_MODULUS: return "modulus n is even (GPU path requires odd n)";
+        case PB200_ERR_RANGE: return "input does not fit its declared bit width (range check fails)";
+        case PB200_ERR_UNSUPPORTED: return "key size not supported by any compiled engine";
+        case PB200_ERR_CUDA: return "CUDA failure";
+        case PB200_ERR_NOMEM: return "out of memory";
+        case PB200_ERR_SINK: return "witness sink aborted";
+        default: return "unknown status";
+    }
+}
+const char* pb200_last_cuda_error(void) { return t_cuda_error.c_str(); }
+const char* pb200_version(void) { return "paillier_b200 0.1 (sm_100a)"; }
+int pb200_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+uint64_t pb200_kernel_launches(void) { return g_kernel_launches.load(); }
+
+static bool fits(const uint64_t* v, uint32_t words, uint32_t bits) {
+    for (uint32_t i = 0; i < words; i++) {
+        uint32_t lo = i * 64;
+        if (lo >= bits) { if (v[i]) return false; }
+        else if (bits - lo < 64) { if (v[i] >> (bits - lo)) return false; }
+    }
+    return true;
+}
+
+int pb200_key_create(int device, uint32_t n_bits, uint32_t limb_bits, const uint64_t* n_le, const uint64_t* g_le,
+                     pb200_key** out) {
+    if (!out) return PB200_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!n_le || !g_le || n_bits == 0 || limb_bits == 0 || limb_bits > 128) return PB200_ERR_INVALID_ARG;
+    if (n_bits % limb_bits != 0) return PB200_ERR_INVALID_ARG;  // assign_integer asserts bit_len % limb_bits == 0
+    uint32_t win = PB200_WORDS(n_bits), wout = PB200_WORDS(2 * n_bits);
+    if (wout > PB200_SIMPLE_MAXK) return PB200_ERR_UNSUPPORTED;
+    if (!fits(n_le, win, n_bits) || !fits(g_le, win, n_bits)) return PB200_ERR_RANGE;
+    BigInt n = BigInt::from_u64_le(n_le, win), g = BigInt::from_u64_le(g_le, win);
+    if (n.is_zero()) return PB200_ERR_ZERO_MODULUS;
+    if (!n.is_odd()) return PB200_ERR_EVEN_MODULUS;
+    int ndev = pb200_device_count();
+    if (device < 0 || device >= ndev) { t_cuda_error = "no such CUDA device"; return PB200_ERR_CUDA; }
+    CU(cudaSetDevice(device));
+    pb200_key* k = new (std::nothrow) pb200_key();
+    if (!k) return PB200_ERR_NOMEM;
+    k->device = device; k->n_bits = n_bits; k->limb_bits = limb_bits; k->words_in = win; k->words_out = wout;
+    k->n = n; k->g = g; k->n2 = BigInt::mul(n, n);
+    SimpleConsts* h = new SimpleConsts();
+    memset(h, 0, sizeof(*h));
+    h->k = (int)wout; h->kin = (int)win; h->n_bits = (int)n_bits; h->exp_bits = (int)n.bits();
+    h->s = (int)(64 * wout - k->n2.bits());
+    BigInt Nt = BigInt::shl(k->n2, h->s);
+    BigInt mu = BigInt::div(BigInt::pow2(128 * (size_t)wout), Nt);
+    Nt.to_u64_le(h->Nt, wout); mu.to_u64_le(h->mu, wout + 1);
+    n.to_u64_le(h->n, win); g.to_u64_le(h->g, win);
+    cudaError_t e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&k->d_simple, sizeof(SimpleConsts));
+    if (e == cudaSuccess) e = cudaMalloc(&k->d_flags, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(k->d_simple, h, sizeof(SimpleConsts), cudaMemcpyHostToDevice, k->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(k->d_flags, 0, sizeof(int), k->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(k->stream);
+    delete h;
+    if (e != cudaSuccess) { int rc = cuda_fail(e, "pb200_key_create"); pb200_key_destroy(k); return rc; }
+    cudaError_t fe = cudaSuccess;
+    k->fast = block28_create(n, g, n_bits, device, k->stream, &k->fast_why, &fe);
+    if (fe != cudaSuccess) { int rc = cuda_fail(fe, "block28_create"); pb200_key_destroy(k); return rc; }
+    k->engine_name = k->fast ? block28_name(k->fast) : "simple64";
+    *out = k;
+    return PB200_OK;
+}
+
+void pb200_key_destroy(pb200_key* k) {
+    if (!k) return;
+    cudaSetDevice(k->device);
+    if (k->stream) cudaStreamSynchronize(k->stream);
+    if (k->fast) block28_destroy(k->fast);
+    if (k->d_simple) cudaFree(k->d_simple);
+    if (k->d_gchain) cudaFree(k->d_gchain);
+    if (k->d_flags) cudaFree(k->d_flags);
+    k->in_a.release(); k->in_b.release(); k->out_a.release(); k->out_b.release(); k->scratch.release(); k->offs.release();
+    if (k->stream) cudaStreamDestroy(k->stream);
+    delete k;
+}
+uint32_t pb200_key_n_bits(const pb200_key* k) { return k ? k->n_bits : 0; }
+uint32_t pb200_key_words_in(const pb200_key* k) { return k ? k->words_in : 0; }
+uint32_t pb200_key_words_out(const pb200_key* k) { return k ? k->words_out : 0; }
+int pb200_key_device(const pb200_key* k) { return k ? k->device : -1; }
+int pb200_key_n2(const pb200_key* k, uint64_t* out) {
+    if (!k || !out) return PB200_ERR_INVALID_ARG;
+    k->n2.to_u64_le(out, k->words_out);
+    return PB200_OK;
+}
+const char* pb200_key_engine(const pb200_key* k) {
+    if (!k) return "";
+    return use_fast(k) ? k->engine_name.c_str() : "simple64";
+}
+int pb200_key_set_engine(pb200_key* k, int engine) {
+    if (!k || engine < 0 || engine > 2) return PB200_ERR_INVALID_ARG;
+    if (engine == 2 && !k->fast) return PB200_ERR_UNSUPPORTED;
+    k->engine = engine;
+    return PB200_OK;
+}
+void* pb200_key_stream(const pb200_key* k) { return k ? (void*)k->stream : nullptr; }
+int pb200_key_sync(pb200_key* k) {
+    if (!k) return PB200_ERR_INVALID_ARG;
+    CU(cudaSetDevice(k->device));
+    CU(cudaStreamSynchronize(k->stream));
+    return PB200_OK;
+}
+
+// reads and clears the device-side range flag
+static int take_flags(pb200_key* k) {
+    int f = 0;
+    CU(cudaMemcpyAsync(&f, k->d_flags, sizeof(int), cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    if (f) { CU(cudaMemsetAsync(k->d_flags, 0, sizeof(int), k->stream)); return PB200_ERR_RANGE; }
+    return PB200_OK;
+}
+
+static int ensure_gchain(pb200_key* k) {
+    if (k->d_gchain) return PB200_OK;
+    CU(cudaMalloc(&k->d_gchain, (size_t)k->n_bits * 2 * k->words_out * sizeof(u64)));
+    CU(simple_gchain(k->d_simple, k->d_gchain, (int)k->n_bits, k->stream));
+    return PB200_OK;
+}
+
+// ---- encrypt --------------------------------------------------------------------------------
+int pb200_encrypt_batch_dev(pb200_key* k, const uint64_t* d_m, const uint64_t* d_r, size_t count, uint64_t* d_c) {
+    if (!k || (count && (!d_m || !d_r || !d_c))) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    CU(cudaSetDevice(k->device));
+    if (use_fast(k)) { CU(block28_encrypt(k->fast, (const u64*)d_m, (const u64*)d_r, count, (u64*)d_c, k->stream)); return PB200_OK; }
+    int rc = ensure_gchain(k); if (rc) return rc;
+    CU(simple_encrypt(k->d_simple, k->d_gchain, (const u64*)d_m, (const u64*)d_r, count, (u64*)d_c, nullptr, nullptr,
+                      nullptr, k->d_flags, k->stream));
+    return PB200_OK;
+}
+
+static int check_inputs(const pb200_key* k, const uint64_t* v, size_t count) {
+    for (size_t u = 0; u < count; u++) if (!fits(v + u * k->words_in, k->words_in, k->n_bits)) return PB200_ERR_RANGE;
+    return PB200_OK;
+}
+
+int pb200_encrypt_batch(pb200_key* k, const uint64_t* m, const uint64_t* r, size_t count, uint64_t* c_out) {
+    if (!k || (count && (!m || !r || !c_out))) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    if (k->n_bits % 64) { int rc = check_inputs(k, m, count); if (rc) return rc; rc = check_inputs(k, r, count); if (rc) return rc; }
+    CU(cudaSetDevice(k->device));
+    size_t bin = count * k->words_in * sizeof(u64), bout = count * k->words_out * sizeof(u64);
+    CU(k->in_a.reserve(bin)); CU(k->in_b.reserve(bin)); CU(k->out_a.reserve(bout));
+    CU(cudaMemcpyAsync(k->in_a.p, m, bin, cudaMemcpyHostToDevice, k->stream));
+    CU(cudaMemcpyAsync(k->in_b.p, r, bin, cudaMemcpyHostToDevice, k->stream));
+    int rc = pb200_encrypt_batch_dev(k, (const uint64_t*)k->in_a.p, (const uint64_t*)k->in_b.p, count, (uint64_t*)k->out_a.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    return use_fast(k) ? PB200_OK : take_flags(k);
+}
+
+// ---- add ------------------------------------------------------------------------------------
+int pb200_add_batch_dev(pb200_key* k, const uint64_t* d_c1, const uint64_t* d_c2, uint32_t c_words, size_t count,
+                        uint64_t* d_out, uint64_t* d_q) {
+    if (!k || (count && (!d_c1 || !d_c2 || !d_out)) || c_words == 0 || c_words > k->words_out) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    CU(cudaSetDevice(k->device));
+    CU(simple_add(k->d_simple, (const u64*)d_c1, (const u64*)d_c2, (int)c_words, count, (u64*)d_out, (u64*)d_q, k->d_flags, k->stream));
+    return PB200_OK;
+}
+int pb200_add_batch(pb200_key* k, const uint64_t* c1, const uint64_t* c2, uint32_t c_words, size_t count, uint64_t* out,
+                    uint64_t* q_out) {
+    if (!k || (count && (!c1 || !c2 || !out)) || c_words == 0 || c_words > k->words_out) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    CU(cudaSetDevice(k->device));
+    size_t bin = count * c_words * sizeof(u64), bout = count * k->words_out * sizeof(u64);
+    CU(k->in_a.reserve(bin)); CU(k->in_b.reserve(bin)); CU(k->out_a.reserve(bout));
+    if (q_out) CU(k->out_b.reserve(bout));
+    CU(cudaMemcpyAsync(k->in_a.p, c1, bin, cudaMemcpyHostToDevice, k->stream));
+    CU(cudaMemcpyAsync(k->in_b.p, c2, bin, cudaMemcpyHostToDevice, k->stream));
+    int rc = pb200_add_batch_dev(k, (const uint64_t*)k->in_a.p, (const uint64_t*)k->in_b.p, c_words, count,
+                                 (uint64_t*)k->out_a.p, q_out ? (uint64_t*)k->out_b.p : nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
+    if (q_out) CU(cudaMemcpyAsync(q_out, k->out_b.p, bout, cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    return take_flags(k);
+}
+
+// ---- tally ----------------------------------------------------------------------------------
+int pb200_tally_dev(pb200_key* k, const uint64_t* d_c, size_t count, uint64_t* d_out) {
+    if (!k || !d_out || (count && !d_c)) return PB200_ERR_INVALID_ARG;
+    CU(cudaSetDevice(k->device));
+    if (use_fast(k) && count) { CU(block28_tally(k->fast, (const u64*)d_c, count, (u64*)d_out, k->stream)); return PB200_OK; }
+    CU(k->scratch.reserve(simple_tally_scratch_words((int)k->words_out) * sizeof(u64)));
+    CU(simple_tally(k->d_simple, (int)k->words_out, (const u64*)d_c, count, (u64*)d_out, (u64*)k->scratch.p, k->d_flags, k->stream));
+    return PB200_OK;
+}
+int pb200_tally(pb200_key* k, const uint64_t* c, size_t count, uint64_t* out) {
+    if (!k || !out || (count && !c)) return PB200_ERR_INVALID_ARG;
+    CU(cudaSetDevice(k->device));
+    size_t bin = count * k->words_out * sizeof(u64), bout = k->words_out * sizeof(u64);
+    CU(k->in_a.reserve(bin ? bin : 8)); CU(k->out_b.reserve(bout));
+    if (bin) CU(cudaMemcpyAsync(k->in_a.p, c, bin, cudaMemcpyHostToDevice, k->stream));
+    int rc = pb200_tally_dev(k, (const uint64_t*)k->in_a.p, count, (uint64_t*)k->out_b.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, k->out_b.p, bout, cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    return take_flags(k);
+}
+int pb200_tally_combine(pb200_key* k, const uint64_t* partials, size_t n_partials, uint64_t* out) {
+    // the combine of G <= 8 shard partials is the same fold; use the exact simple engine for it
+    if (!k || !out || (n_partials && !partials)) return PB200_ERR_INVALID_ARG;
+    int saved = k->engine; k->engine = 1;
+    int rc = pb200_tally(k, partials, n_partials, out);
+    k->engine = saved;
+    return rc;
+}
+
+// ---- witness --------------------------------------------------------------------------------
+static uint64_t popcount_words(const uint64_t* v, uint32_t words) {
+    uint64_t c = 0; for (uint32_t i = 0; i < words; i++) c += (uint64_t)__builtin_popcountll(v[i]); return c;
+}
+uint64_t pb200_witness_records_for(const pb200_key* k, const uint64_t* m) {
+    if (!k || !m) return 0;
+    uint64_t pn = 0; for (size_t i = 0; i < k->n.w.size(); i++) pn += (uint64_t)__builtin_popcount(k->n.w[i]);
+    return popcount_words(m, k->words_in) + k->n.bits() + pn + 1;
+}
+
+int pb200_key_g_chain(pb200_key* k, uint64_t* records_out) {
+    if (!k || !records_out) return PB200_ERR_INVALID_ARG;
+    CU(cudaSetDevice(k->device));
+    int rc = ensure_gchain(k); if (rc) return rc;
+    CU(cudaMemcpyAsync(records_out, k->d_gchain, (size_t)k->n_bits * 2 * k->words_out * sizeof(u64), cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    return take_flags(k);
+}
+
+int pb200_encrypt_witness_batch(pb200_key* k, const uint64_t* m, const uint64_t* r, size_t count, uint64_t* c_out,
+                                size_t max_chunk_units, pb200_witness_sink_fn sink, void* user) {
+    if (!k || !sink || (count && (!m || !r))) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    int rc = check_inputs(k, m, count); if (rc) return rc;
+    rc = check_inputs(k, r, count); if (rc) return rc;
+    CU(cudaSetDevice(k->device));
+    rc = ensure_gchain(k); if (rc) return rc;
+    const size_t rec_words = 2 * (size_t)k->words_out;
+    uint64_t fixed = pb200_witness_records_for(k, m) - popcount_words(m, k->words_in);  // bits(n)+popcount(n)+1
+    size_t max_unit_records = (size_t)fixed + k->n_bits;
+    const size_t budget = (size_t)256 << 20;  // bytes of staged records per chunk
+    size_t auto_units = budget / (max_unit_records * rec_words * sizeof(u64));
+    if (auto_units < 1) auto_units = 1;
+    size_t chunk_units = max_chunk_units ? max_chunk_units : auto_units;
+    std::vector<uint64_t> offsets, host_records;
+    std::vector<uint32_t> gcounts;
+    for (size_t first = 0; first < count; first += chunk_units) {
+        size_t nu = count - first < chunk_units ? count - first : chunk_units;
+        offsets.assign(nu + 1, 0); gcounts.assign(nu, 0);
+        for (size_t u = 0; u < nu; u++) {
+            uint64_t pc = popcount_words(m + (first + u) * k->words_in, k->words_in);
+            gcounts[u] = (uint32_t)pc;
+            offsets[u + 1] = offsets[u] + pc + fixed;
+        }
+        size_t total_records = (size_t)offsets[nu];
+        size_t bin = nu * k->words_in * sizeof(u64), bout = nu * k->words_out * sizeof(u64);
+        CU(k->in_a.reserve(bin)); CU(k->in_b.reserve(bin)); CU(k->out_a.reserve(bout));
+        CU(k->offs.reserve((nu + 1) * sizeof(u64)));
+        CU(k->scratch.reserve(total_records * rec_words * sizeof(u64)));
+        CU(cudaMemcpyAsync(k->in_a.p, m + first * k->words_in, bin, cudaMemcpyHostToDevice, k->stream));
+        CU(cudaMemcpyAsync(k->in_b.p, r + first * k->words_in, bin, cudaMemcpyHostToDevice, k->stream));
+        CU(cudaMemcpyAsync(k->offs.p, offsets.data(), (nu + 1) * sizeof(u64), cudaMemcpyHostToDevice, k->stream));
+        CU(simple_encrypt(k->d_simple, k->d_gchain, (const u64*)k->in_a.p, (const u64*)k->in_b.p, nu, (u64*)k->out_a.p,
+                          (u64*)k->scratch.p, (const u64*)k->offs.p, nullptr, k->d_flags, k->stream));
+        host_records.resize(total_records * rec_words);
+        CU(cudaMemcpyAsync(host_records.data(), k->scratch.p, total_records * rec_words * sizeof(u64), cudaMemcpyDeviceToHost, k->stream));
+        if (c_out) CU(cudaMemcpyAsync(c_out + first * k->words_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
+        CU(cudaStreamSynchronize(k->stream));
+        rc = take_flags(k); if (rc) return rc;
+        pb200_witness_chunk ch;
+        ch.first_unit = first; ch.n_units = nu; ch.words_out = k->words_out;
+        ch.offsets = offsets.data(); ch.records = host_records.data(); ch.g_mul_counts = gcounts.data();
+        if (sink(user, &ch) != 0) return PB200_ERR_SINK;
+    }
+    return PB200_OK;
+}
+
+int pb200_encrypt_witness_digest(pb200_key* k, const uint64_t* m, const uint64_t* r, size_t count, uint64_t* c_out,
+                                 uint64_t* digest_out) {
+    if (!k || !digest_out || (count && (!m || !r))) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    int rc = check_inputs(k, m, count); if (rc) return rc;
+    rc = check_inputs(k, r, count); if (rc) return rc;
+    CU(cudaSetDevice(k->device));
+    rc = ensure_gchain(k); if (rc) return rc;
+    size_t bin = count * k->words_in * sizeof(u64), bout = count * k->words_out * sizeof(u64);
+    CU(k->in_a.reserve(bin)); CU(k->in_b.reserve(bin)); CU(k->out_a.reserve(bout)); CU(k->out_b.reserve(count * sizeof(u64)));
+    CU(cudaMemcpyAsync(k->in_a.p, m, bin, cudaMemcpyHostToDevice, k->stream));
+    CU(cudaMemcpyAsync(k->in_b.p, r, bin, cudaMemcpyHostToDevice, k->stream));
+    CU(simple_encrypt(k->d_simple, k->d_gchain, (const u64*)k->in_a.p, (const u64*)k->in_b.p, count, (u64*)k->out_a.p,
+                      nullptr, nullptr, (u64*)k->out_b.p, k->d_flags, k->stream));
+    CU(cudaMemcpyAsync(digest_out, k->out_b.p, count * sizeof(u64), cudaMemcpyDeviceToHost, k->stream));
+    if (c_out) CU(cudaMemcpyAsync(c_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    return take_flags(k);
+}
+
+// ---- limb formatting ------------------------------------------------------------------------
+int pb200_repack_limbs(pb200_key* k, const uint64_t* values, size_t count, uint32_t value_bits, uint32_t limb_bits,
+                       uint64_t* limbs_out) {
+    if (!k || !values || !limbs_out || limb_bits == 0 || limb_bits > 128 || value_bits % limb_bits) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    CU(cudaSetDevice(k->device));
+    uint32_t wpv = PB200_WORDS(value_bits), nl = value_bits / limb_bits;
+    size_t bin = count * wpv * sizeof(u64), bout = count * nl * 2 * sizeof(u64);
+    CU(k->in_a.reserve(bin)); CU(k->out_a.reserve(bout));
+    CU(cudaMemcpyAsync(k->in_a.p, values, bin, cudaMemcpyHostToDevice, k->stream));
+    CU(repack_limbs((const u64*)k->in_a.p, count, (int)wpv, (int)value_bits, (int)limb_bits, (u64*)k->out_a.p, k->stream));
+    CU(cudaMemcpyAsync(limbs_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    return PB200_OK;
+}
+
+}  // extern "C"

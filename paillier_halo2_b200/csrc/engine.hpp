@@ -1,0 +1,41 @@
+// engine.hpp — internal interfaces between the C ABI (capi.cu) and the CUDA engines.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "host_bigint.hpp"
+#include "simple64.cuh"
+
+namespace pb200 {
+
+extern std::atomic<uint64_t> g_kernel_launches;
+inline void count_launch(uint64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- simple64 engine launchers (simple64_kernels.cu) ---------------------------------------
+// All pointers are device pointers; work is enqueued on `st`.
+cudaError_t simple_gchain(const SimpleConsts* dK, u64* d_gchain /* n_bits * 2k */, int n_bits, cudaStream_t st);
+cudaError_t simple_encrypt(const SimpleConsts* dK, const u64* d_gchain, const u64* d_m, const u64* d_r, size_t count,
+                           u64* d_c /*nullable*/, u64* d_records /*nullable*/, const u64* d_offsets /*nullable*/,
+                           u64* d_digest /*nullable*/, int* d_flags, cudaStream_t st);
+cudaError_t simple_add(const SimpleConsts* dK, const u64* d_c1, const u64* d_c2, int c_words, size_t count,
+                       u64* d_out, u64* d_q /*nullable*/, int* d_flags, cudaStream_t st);
+// product of `count` values (k words each) -> d_out (k words); d_scratch: at least simple_tally_scratch_words(k) words
+size_t simple_tally_scratch_words(int k);
+cudaError_t simple_tally(const SimpleConsts* dK, int k, const u64* d_c, size_t count, u64* d_out, u64* d_scratch,
+                         int* d_flags, cudaStream_t st);
+cudaError_t repack_limbs(const u64* d_vals, size_t count, int words_per_value, int value_bits, int limb_bits,
+                         u64* d_out, cudaStream_t st);
+
+// ---- block28 engine (block28_kernels.cu) ----------------------------------------------------
+struct Block28Key;  // opaque per-key state of the fast engine
+// returns nullptr (and leaves *why) when no compiled configuration covers the key size
+Block28Key* block28_create(const BigInt& n, const BigInt& g, uint32_t n_bits, int device, cudaStream_t st,
+                           std::string* why, cudaError_t* cuda_err);
+void block28_destroy(Block28Key*);
+const char* block28_name(const Block28Key*);
+cudaError_t block28_encrypt(Block28Key*, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st);
+cudaError_t block28_tally(Block28Key*, const u64* d_c, size_t count, u64* d_out, cudaStream_t st);
+
+}  // namespace pb200
