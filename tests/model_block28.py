@@ -1,0 +1,198 @@
+"""Limb-exact Python model of the block28 CUDA engine (paillier_halo2_b200/csrc/block28.cuh).
+
+Not the oracle: this file models OUR kernel's arithmetic (radix-2^28 signed digits, G x BL block
+products, lazy Barrett with truncated high product) so its bounds can be fuzzed on the CPU.  Every
+64-bit accumulator is range-checked against the signed 64-bit limits the kernel relies on.
+"""
+from __future__ import annotations
+
+W = 28
+M = 1 << W
+H = 1 << (W - 1)
+I64 = 1 << 63
+
+
+def sgxt(v: int) -> int:
+    """centered residue mod 2^28 in [-2^27, 2^27)"""
+    return ((v + H) & (M - 1)) - H
+
+
+class Params:
+    def __init__(self, G: int, BL: int, margin: int = 10):
+        self.G, self.BL = G, BL
+        self.L = G * BL
+        self.beta = 14 * (2 * self.L - 1)          # 2*beta = s1 + s2 = 28(2L-1)
+        self.kN = self.beta - margin               # bit length of the normalised modulus Nt
+        self.margin = margin
+
+    def key(self, N: int):
+        assert N % 2 == 1 and N.bit_length() <= self.kN
+        sh = self.kN - N.bit_length()
+        Nt = N << sh
+        mu = (1 << (2 * self.beta)) // Nt
+        assert mu.bit_length() <= W * self.L - 1
+        return sh, Nt, mu
+
+
+def to_digits(v: int, L: int):
+    """exact integer -> L strict centered digits (value must fit)"""
+    out = []
+    for _ in range(L):
+        d = sgxt(v)
+        out.append(d)
+        v = (v - d) >> W
+    assert v == 0, "value does not fit"
+    return out
+
+
+def from_digits(d):
+    return sum(x << (W * i) for i, x in enumerate(d))
+
+
+def block(d, b, BL):
+    return d[b * BL:(b + 1) * BL]
+
+
+def antidiag(P, A, B, pairs, mode_of=None):
+    """D = sum over block pairs (i,j) of A_i * B_j (column sums, 2BL-1 signed 64-bit accumulators)."""
+    BL = P.BL
+    acc = [0] * (2 * BL - 1)
+    for (i, j, mode, dbl) in pairs:
+        a, b = block(A, i, BL), block(B, j, BL)
+        for x in range(BL):
+            for y in range(BL):
+                if mode == "F" or (mode == "LT" and x + y <= BL - 1) or (mode == "UTG" and x + y >= BL - 2):
+                    acc[x + y] += (2 if dbl else 1) * a[x] * b[y]
+                elif mode == "SQ":
+                    if x == y:
+                        acc[x + y] += a[x] * b[y]
+                    elif x < y:
+                        acc[x + y] += 2 * a[x] * b[y]
+    for c in acc:
+        assert -I64 < c < I64, "64-bit accumulator overflow"
+    return acc
+
+
+def normalize_D(P, acc):
+    """ripple the 2BL-1 column sums into 2BL digits: strict except the last, which absorbs the carry"""
+    out = []
+    carry = 0
+    for c in acc:
+        t = c + carry
+        assert -I64 < t < I64
+        d = sgxt(t)
+        out.append(d)
+        carry = (t - d) >> W
+    out.append(carry)            # digit 2BL-1: loose
+    assert abs(carry) < (1 << 31), "top digit of D does not fit int32"
+    return out
+
+
+def sched_full(G):
+    """role t -> [(d, [(i, j)])]: cyclic antidiagonals t and t+G of a full product"""
+    out = []
+    for t in range(G):
+        lo = [(i, t - i) for i in range(0, t + 1)]
+        hi = [(i, t + G - i) for i in range(t + 1, G)]
+        out.append([(t, lo), (t + G, hi)])
+    return out
+
+
+def product(P, A, B, nblocks_out, which, sqr=False):
+    """X blocks [0, nblocks_out) of A*B.  which: "full" | "high" (blocks >= G exact up to the guard) | "low" (blocks < G)"""
+    G, BL = P.G, P.BL
+    X = [0] * (nblocks_out * BL)
+    for d in range(2 * G - 1):
+        pairs = []
+        for i in range(G):
+            j = d - i
+            if not (0 <= j < G):
+                continue
+            if which == "full":
+                if sqr:
+                    if i < j:
+                        pairs.append((i, j, "F", True))
+                    elif i == j:
+                        pairs.append((i, j, "SQ", False))
+                else:
+                    pairs.append((i, j, "F", False))
+            elif which == "high":
+                if d >= G:
+                    pairs.append((i, j, "F", False))
+                elif d == G - 1:
+                    pairs.append((i, j, "UTG", False))
+            elif which == "low":
+                if d < G - 1:
+                    pairs.append((i, j, "F", False))
+                elif d == G - 1:
+                    pairs.append((i, j, "LT", False))
+        if not pairs:
+            continue
+        D = normalize_D(P, antidiag(P, A, B, pairs))
+        for k in range(2 * BL):
+            pos = d * BL + k
+            if pos < len(X):
+                X[pos] += D[k]
+            else:
+                assert which == "low" or D[k] == 0 or pos >= len(X)
+    return X
+
+
+def ripple_blocks(P, X, nblocks):
+    """per-block ripple: strict digits, block-top keeps the carry (loose)"""
+    BL = P.BL
+    out = list(X)
+    for b in range(nblocks):
+        carry = 0
+        for k in range(BL):
+            t = out[b * BL + k] + carry
+            if k < BL - 1:
+                d = sgxt(t)
+                out[b * BL + k] = d
+                carry = (t - d) >> W
+            else:
+                out[b * BL + k] = t
+                assert abs(t) < (1 << 31)
+    return out
+
+
+def mulmod(P, keyc, A, B, sqr=False):
+    """lazy Barrett: returns R (L digits, strict with loose block tops), R == A*B (mod Nt), |R| < 2^beta"""
+    sh, Nt, mu = keyc
+    G, BL, L = P.G, P.BL, P.L
+    X = product(P, A, B, 2 * G, "full", sqr)                     # 2L digits, loose (sum of two D digits)
+    # q1 = X digits [L-1, 2L-1), with digit 2L-1 folded into 2L-2
+    q1 = X[L - 1:2 * L - 1]
+    q1[L - 1] += X[2 * L - 1] << W
+    assert abs(q1[L - 1]) < (1 << 31)
+    mu_d = keyc_digits(P, keyc)[1]
+    Y = product(P, q1, mu_d, 2 * G, "high")
+    qh = Y[L:2 * L]                                              # q-hat digits (loose)
+    Nt_d = keyc_digits(P, keyc)[0]
+    Pl = product(P, qh, Nt_d, G, "low")
+    R = [X[i] - Pl[i] for i in range(L)]
+    R = ripple_blocks(P, R, G)
+    R[L - 1] = sgxt(R[L - 1])                                    # drop multiples of 2^(28L)
+    return R
+
+
+_cache = {}
+
+
+def keyc_digits(P, keyc):
+    k = (P.L, keyc[1])
+    if k not in _cache:
+        _cache[k] = (to_digits(keyc[1], P.L), to_digits(keyc[2], P.L))
+    return _cache[k]
+
+
+def canonical(P, keyc, R, N):
+    """final step: (R * 2^sh mod Nt) >> sh  ==  R mod N"""
+    sh, Nt, mu = keyc
+    two_sh = to_digits(1 << sh, P.L)
+    Y = mulmod(P, keyc, R, two_sh)
+    v = from_digits(Y)
+    assert abs(v) < (1 << P.beta)
+    v %= Nt
+    assert v % (1 << sh) == 0
+    return v >> sh

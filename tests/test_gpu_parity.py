@@ -1,0 +1,156 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the committed golden vectors and
+the CPU oracle on seeded inputs.  Bit-exact (integer work): no tolerance anywhere."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle.paillier_oracle import encrypt_steps, paillier_add_native, paillier_enc_native, pow_chain_steps, tally_native
+from paillier_halo2_b200 import _lib, workload
+from paillier_halo2_b200.api import PaillierKey, Pb200Error, ints_to_words, witness_digest, words_to_ints
+from util import h, kat
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = [1, 2]  # simple64, block28 (skipped per key when block28 does not cover the size)
+
+
+def _key(n, g, n_bits, limb_bits, engine):
+    key = PaillierKey(n, g, n_bits, limb_bits)
+    try:
+        key.set_engine(engine)
+    except Pb200Error as e:
+        key.close()
+        if e.status == _lib.PB200_ERR_UNSUPPORTED:
+            pytest.skip("block28 engine does not cover this key size")
+        raise
+    return key
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_golden_encrypt(built_lib, engine):
+    groups = {}
+    for case in kat()["enc"]:
+        groups.setdefault((case["n"], case["g"], case["n_bits"], case["limb_bits"]), []).append(case)
+    checked = 0
+    for (n, g, n_bits, limb_bits), cases in groups.items():
+        try:
+            key = PaillierKey(h(n), h(g), n_bits, limb_bits)
+            key.set_engine(engine)
+        except Pb200Error as e:
+            if e.status == _lib.PB200_ERR_UNSUPPORTED:
+                continue
+            raise
+        with key:
+            got = key.paillier_enc_native([h(c["m"]) for c in cases], [h(c["r"]) for c in cases])
+            for c, v in zip(cases, got):
+                assert v == h(c["c"]), (c["tag"], n_bits, key.engine)
+            checked += len(cases)
+    if checked == 0:
+        pytest.skip("engine not available for any golden key size")
+
+
+def test_golden_add_with_quotient(built_lib):
+    for case in kat()["add"]:
+        with PaillierKey(h(case["n"]), 2, case["n_bits"], case["limb_bits"]) as key:
+            res, q = key.paillier_add_native([h(case["c1"])], [h(case["c2"])], c_bits=case["c_bits"], want_q=True)
+            assert res == [h(case["res"])] and q == [h(case["q"])]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_golden_tally(built_lib, engine):
+    for case in kat()["tally"]:
+        try:
+            key = PaillierKey(h(case["n"]), 2, case["n_bits"], 88 if case["n_bits"] == 264 else 64)
+            key.set_engine(engine)
+        except Pb200Error as e:
+            if e.status == _lib.PB200_ERR_UNSUPPORTED:
+                continue
+            raise
+        with key:
+            cs = [h(c) for c in case["cs"]]
+            assert key.tally(cs) == h(case["res"])
+            assert key.tally(cs[:1]) == cs[0] % (h(case["n"]) ** 2)
+            assert key.tally([]) == 1 % (h(case["n"]) ** 2)
+
+
+def test_golden_witness_records_and_digests(built_lib):
+    for case in kat()["witness"]:
+        n, g, n_bits = h(case["n"]), h(case["g"]), case["n_bits"]
+        with PaillierKey(n, g, n_bits, case["limb_bits"]) as key:
+            wo = key.words_out
+            ms = [h(u["m"]) for u in case["units"]]
+            rs = [h(u["r"]) for u in case["units"]]
+            cs, units, gcounts = key.encrypt_witness(ms, rs, max_chunk_units=2)  # ragged chunks: 2,2,1
+            cs2, digests = key.encrypt_witness_digest(ms, rs)
+            assert cs == cs2 == [h(u["c"]) for u in case["units"]]
+            for u, recs, gc, d in zip(case["units"], units, gcounts, digests):
+                assert len(recs) == u["n_records"] == key.witness_records_for(h(u["m"]))
+                assert gc == u["g_mul_count"]
+                assert d == h(u["digest"]) == witness_digest(recs, wo)
+                if "records" in u:
+                    assert [[hex(q), hex(rem)] for q, rem in recs] == u["records"]
+                else:
+                    assert [hex(x) for x in recs[0]] == u["first"] and [hex(x) for x in recs[-1]] == u["last"]
+            gch = key.g_chain()
+            assert witness_digest(gch, wo) == h(case["g_chain_digest"])
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("n_bits,count", [(1024, 70), (2048, 45)])
+def test_seeded_batch_vs_oracle(built_lib, engine, n_bits, count):
+    key_d = workload.load_key(n_bits)
+    n, g = key_d["n"], key_d["g_rand"]
+    m_w, r_w = workload.units(n_bits, count)
+    ms, rs = words_to_ints(m_w), words_to_ints(r_w)
+    with _key(n, g, n_bits, 64, engine) as key:
+        got = words_to_ints(key.encrypt_words(m_w, r_w))
+    assert got == [paillier_enc_native(n, g, m, r) for m, r in zip(ms, rs)]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_paillier_algebra_on_gpu(built_lib, engine):
+    """encode -> homomorphic tally -> decode round trip with the fixture primes (size-independent property)."""
+    n_bits = 1024
+    kd = workload.load_key(n_bits)
+    n, p, q = kd["n"], kd["p"], kd["q"]
+    n2, lam = n * n, (kd["p"] - 1) * (kd["q"] - 1)
+    mu = pow((pow(n + 1, lam, n2) - 1) // n, -1, n)
+    dec = lambda c: (pow(c, lam, n2) - 1) // n * mu % n
+    m_w, r_w = workload.units(n_bits, 33)
+    ms = words_to_ints(m_w)
+    with _key(n, n + 1, n_bits, 64, engine) as key:
+        c_w = key.encrypt_words(m_w, r_w)
+        cs = words_to_ints(c_w)
+        assert [dec(c) for c in cs[:5]] == ms[:5]
+        assert dec(words_to_ints(key.tally_words(c_w))[0]) == sum(ms) % n
+        s = key.paillier_add_native(cs[:16], cs[16:32])
+        assert [dec(x) for x in s[:3]] == [(ms[i] + ms[16 + i]) % n for i in range(3)]
+
+
+def test_empty_and_error_paths(built_lib):
+    with PaillierKey(0xF123456789ABCDEF0123456789ABCDEF | 1, 7, 128, 64) as key:
+        assert key.paillier_enc_native([], []) == []
+        assert key.paillier_add_native([], []) == []
+        n2 = key.n2()
+        assert n2 == key.n ** 2
+        with pytest.raises(Pb200Error) as e:   # q would not fit 2*enc_bits: the range check on q fails
+            with PaillierKey(3, 2, 128, 64) as small:
+                small.paillier_add_native([(1 << 256) - 1], [(1 << 256) - 1])
+        assert e.value.status == _lib.PB200_ERR_RANGE
+    with pytest.raises(Pb200Error) as e:
+        PaillierKey(10, 3, 128, 64)
+    assert e.value.status == _lib.PB200_ERR_EVEN_MODULUS
+    with PaillierKey(0x1FFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFF, 5, 264, 88) as key:
+        with pytest.raises(Pb200Error) as e:   # m has bits above enc_bits = 264
+            key.encrypt_words(np.full((1, 5), 2**64 - 1, dtype="<u8"), np.ones((1, 5), dtype="<u8"))
+        assert e.value.status == _lib.PB200_ERR_RANGE
+
+
+def test_repack_limbs_88(built_lib):
+    rng = random.Random(5)
+    vals = [rng.getrandbits(528) for _ in range(9)] + [0, (1 << 528) - 1]
+    with PaillierKey(0x1FFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFF, 5, 264, 88) as key:
+        got = key.repack_limbs(vals, 528, 88)
+    from oracle.paillier_oracle import decompose
+    assert got == [decompose(v, 6, 88) for v in vals]
