@@ -1,0 +1,323 @@
+// block28.cuh — "block28" engine: warp-role block products in radix 2^28 with lazy Barrett.
+//
+// Why this shape (measured on B200, profiles/imad_peak_r01.json): IMAD.WIDE without carry runs at
+// 63.5 MAC/clk/SM; the carry-chained IMAD.WIDE.X form of 32-bit-limb arithmetic runs at 31.3.  So the
+// hot loop uses signed 28-bit digits and plain 64-bit column accumulators (mad.wide.s32, no carry
+// flags): up to 304 products of |d| <= 2^27 fit a signed 64-bit column.
+//
+// Layout.  One CTA = G warps x 32 lanes.  A LANE owns one ciphertext; a WARP owns a ROLE.  A number is
+// L = G*BL digits = G blocks of BL digits; in shared memory a block is CH = ceil(BL/4) int4 chunks,
+// stored [block][chunk][lane] so a warp's access is 512 contiguous bytes (conflict-free) and every
+// lane sees only its own ciphertext.  Per-key constants (mu, Nt) are stored once per CTA and read as
+// broadcasts.
+//
+// mulmod(V, B):  all arithmetic modulo Nt = n^2 << sh (a multiple of n^2, bit length beta - MARGIN)
+//   A  T  = V * B                 (2G blocks)  role t sums the block pairs of anti-diagonals t and t+G
+//   B  Q  = hi(q1 * mu)           (G blocks)   q1 = T digits [L-1, 2L-1);  anti-diagonals >= G-1
+//   C  V' = lo(T) - lo(Q * Nt)    (G blocks)   anti-diagonals <= G-1;  V' == V*B (mod Nt), |V'| < 2^beta
+// with 2*beta = 28(2L-1).  Values stay lazily reduced (signed, |v| < 2^beta) along the whole chain;
+// one exact canonicalisation happens per output (finalize).  Each anti-diagonal sum D (2BL-1 columns)
+// is rippled to 2BL strict digits + a spill digit in registers, then merged in three barrier-separated
+// steps: Lo digits -> block d (store), Hi digits -> block d+1 (add + per-block ripple), carry + spill
+// -> digit 0 of block d+2.  tests/model_block28.py is the limb-exact Python model of this file.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pb200 {
+namespace b28 {
+
+constexpr int W = 28;
+constexpr int MARGIN = 10;
+
+template <int G_, int BL_>
+struct Cfg {
+    static constexpr int G = G_, BL = BL_, L = G_ * BL_;
+    static constexpr int CH = (BL_ + 3) / 4;            // int4 chunks per block
+    static constexpr int BLK4 = CH * 32;                // int4 per block per CTA (32 lanes)
+    static constexpr int VAL4 = G_ * BLK4;              // int4 per L-digit value per CTA
+    static constexpr int NCOL = 2 * BL_ - 1;
+    static constexpr int BETA = 14 * (2 * L - 1);
+    static constexpr int KN = BETA - MARGIN;            // bit length of Nt
+    static constexpr int THREADS = 32 * G_;
+    static constexpr int ENTRY4 = G_ * CH;              // int4 per value in global tables (one lane)
+    // shared memory: V, B, Q (L digits each), T (2L digits), constants mu, Nt, two_sh
+    static constexpr int SMEM_INT4 = 5 * VAL4 + 3 * ENTRY4;
+    static constexpr size_t SMEM_BYTES = (size_t)SMEM_INT4 * 16;
+};
+
+__device__ __forceinline__ int sgxt28(int x) {
+    int r; asm("bfe.s32 %0, %1, 0, 28;" : "=r"(r) : "r"(x)); return r;
+}
+__device__ __forceinline__ void madw(long long& acc, int a, int b) {
+    asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b));
+}
+
+enum Mode { M_FULL = 0, M_LT = 1, M_UTG = 2, M_SQ = 3 };
+
+template <int BL, int MODE>
+__device__ __forceinline__ constexpr bool include_xy(int x, int y) {
+    return MODE == M_FULL ? true : MODE == M_LT ? (x + y <= BL - 1) : MODE == M_UTG ? (x + y >= BL - 2) : (x <= y);
+}
+
+// load one block (BL digits) of a per-lane buffer into registers.  p points at chunk 0 of the block for this lane.
+template <class C>
+__device__ __forceinline__ void load_block(int (&a)[C::CH * 4], const int4* p, int stride) {
+#pragma unroll
+    for (int c = 0; c < C::CH; c++) {
+        int4 v = p[c * stride];
+        a[4 * c] = v.x; a[4 * c + 1] = v.y; a[4 * c + 2] = v.z; a[4 * c + 3] = v.w;
+    }
+}
+template <class C>
+__device__ __forceinline__ void store_block(int4* p, const int (&a)[C::CH * 4]) {
+#pragma unroll
+    for (int c = 0; c < C::CH; c++) p[c * 32] = make_int4(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+}
+
+// acc[x+y] += a[x] * b[y] over the (x, y) of MODE; b streamed from shared memory chunk by chunk.
+// DBL doubles every product (off-diagonal block pairs of a squaring); M_SQ doubles x<y and keeps x==y.
+template <class C, int MODE, bool DBL>
+__device__ __forceinline__ void mac_block(long long (&acc)[C::NCOL], const int (&a)[C::CH * 4], const int4* bp, int bstride) {
+    constexpr int BL = C::BL;
+#pragma unroll
+    for (int c = 0; c < C::CH; c++) {
+        int4 bv = bp[c * bstride];
+        int b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int y = 4 * c + e;
+            if (y < BL) {
+                int by = b4[e];
+                int by2 = by + by;
+#pragma unroll
+                for (int x = 0; x < BL; x++) {
+                    if (include_xy<BL, MODE>(x, y)) {
+                        if (MODE == M_SQ) madw(acc[x + y], a[x], x == y ? by : by2);
+                        else madw(acc[x + y], a[x], DBL ? by2 : by);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ripple 2BL-1 column sums into 2BL strict digits + spill.  lo[] <- digits [0,BL), hi[] <- [BL,2BL), returns spill
+template <class C>
+__device__ __forceinline__ int normalize(const long long (&acc)[C::NCOL], int (&lo)[C::CH * 4], int (&hi)[C::CH * 4]) {
+    constexpr int BL = C::BL;
+    long long carry = 0;
+#pragma unroll
+    for (int k = 0; k < C::NCOL; k++) {
+        long long t = acc[k] + carry;
+        int d = sgxt28((int)t);
+        carry = (t - d) >> W;
+        if (k < BL) lo[k] = d; else hi[k - BL] = d;
+    }
+    int c32 = (int)carry;            // |carry| < 2^35 before the last digit; after sgxt the rest is tiny
+    int d = sgxt28(c32);
+    hi[BL - 1] = d;
+    int spill = (int)((carry - d) >> W);
+#pragma unroll
+    for (int k = BL; k < C::CH * 4; k++) { lo[k] = 0; hi[k] = 0; }
+    return spill;
+}
+
+template <class C>
+__device__ __forceinline__ void zero_acc(long long (&acc)[C::NCOL]) {
+#pragma unroll
+    for (int k = 0; k < C::NCOL; k++) acc[k] = 0;
+}
+
+// dst block <- ripple(src block + sign*h), returns the carry out of the block.  p_src/p_dst: chunk 0 for this lane.
+template <class C>
+__device__ __forceinline__ int add_ripple_block(int4* p_dst, const int4* p_src, const int (&h)[C::CH * 4], int sign) {
+    constexpr int BL = C::BL;
+    int a[C::CH * 4];
+    load_block<C>(a, p_src, 32);
+    int carry = 0;
+#pragma unroll
+    for (int k = 0; k < BL; k++) {
+        int t = a[k] + sign * h[k] + carry;
+        int d = sgxt28(t);
+        carry = (t - d) >> W;
+        a[k] = d;
+    }
+#pragma unroll
+    for (int k = BL; k < C::CH * 4; k++) a[k] = 0;
+    store_block<C>(p_dst, a);
+    return carry;
+}
+
+// One anti-diagonal result waiting for its barrier-separated merge steps.
+template <class C>
+struct Pending {
+    int hi[C::CH * 4];
+    int spill;
+    int carry;
+    int blk;      // output block index of the Lo part; -1 = nothing pending
+};
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory view of one CTA
+template <class C>
+struct Smem {
+    int4* V; int4* B; int4* Q; int4* T; const int4* mu; const int4* Nt; const int4* two_sh;   // V must stay first
+    __device__ __forceinline__ Smem(int4* base) {
+        V = base; B = V + C::VAL4; Q = B + C::VAL4; T = Q + C::VAL4;
+        int4* k = T + 2 * C::VAL4;
+        mu = k; Nt = k + C::ENTRY4; two_sh = k + 2 * C::ENTRY4;
+    }
+};
+
+template <class C>
+__device__ __forceinline__ int4* blk_ptr(int4* buf, int blk, int lane) { return buf + blk * C::BLK4 + lane; }
+template <class C>
+__device__ __forceinline__ const int4* blk_ptr(const int4* buf, int blk, int lane) { return buf + blk * C::BLK4 + lane; }
+
+// ---- generic phase executor ---------------------------------------------------------------------
+// One non-inlined function runs all three phases of a mulmod; everything that differs between phases and
+// roles is a warp-uniform runtime value, so the unrolled block-product bodies exist once per job slot.
+enum Phase { PH_MUL = 0, PH_SQR = 1, PH_HIGH = 2, PH_LOW = 3 };
+
+// load block i of q1 = T digits [L-1, 2L-1): digit 0 from the top of T block G+i-1, the rest from block G+i
+template <class C>
+__device__ __forceinline__ void load_q1_block(int (&a)[C::CH * 4], const int4* T, int i, int lane) {
+    constexpr int G = C::G, BL = C::BL;
+    int t[C::CH * 4];
+    load_block<C>(t, blk_ptr<C>(T, G + i, lane), 32);
+    const int* below = (const int*)blk_ptr<C>(T, G + i - 1, lane);
+    a[0] = below[((BL - 1) / 4) * 32 * 4 + ((BL - 1) % 4)];
+#pragma unroll
+    for (int k = 1; k < BL; k++) a[k] = t[k - 1];
+    if (i == G - 1) a[BL - 1] += t[BL - 1] << W;       // fold digit 2L-1 (|.| <= 1) into digit 2L-2
+#pragma unroll
+    for (int k = BL; k < C::CH * 4; k++) a[k] = 0;
+}
+
+// One anti-diagonal job: accumulate its block pairs, ripple, write the Lo digits; Hi digits + spill stay in registers.
+template <class C>
+__device__ __forceinline__ void run_job(Pending<C>& pend, int ph, int d, int i_lo, int i_hi, int mode,
+                                        const int4* abuf, const int4* bbase, int bblk, int bchunk,
+                                        int4* lo_dst, int lo_blk, int lo_op, int lane) {
+    long long acc[C::NCOL];
+    zero_acc<C>(acc);
+    for (int i = i_lo; i <= i_hi; i++) {
+        int a[C::CH * 4];
+        if (ph == PH_HIGH) load_q1_block<C>(a, abuf, i, lane);
+        else load_block<C>(a, blk_ptr<C>(abuf, i, lane), 32);
+        const int4* bp = bbase + (d - i) * bblk;
+        int m = mode;
+        if (ph == PH_SQR) {
+            if (2 * i == d) m = M_SQ;
+            else {
+#pragma unroll
+                for (int k = 0; k < C::BL; k++) a[k] += a[k];      // off-diagonal pair counted twice
+            }
+        }
+        switch (m) {
+            case M_FULL: mac_block<C, M_FULL, false>(acc, a, bp, bchunk); break;
+            case M_LT:   mac_block<C, M_LT, false>(acc, a, bp, bchunk); break;
+            case M_UTG:  mac_block<C, M_UTG, false>(acc, a, bp, bchunk); break;
+            default:     mac_block<C, M_SQ, false>(acc, a, bp, bchunk); break;
+        }
+    }
+    int lo[C::CH * 4];
+    pend.spill = normalize<C>(acc, lo, pend.hi);
+    pend.carry = 0;
+    if (lo_op == 1) {                    // plain store of the Lo digits
+        store_block<C>(blk_ptr<C>(lo_dst, lo_blk, lane), lo);
+    } else if (lo_op == 2) {             // subtract from the block in place (phase C)
+        int4* p = blk_ptr<C>(lo_dst, lo_blk, lane);
+        int t[C::CH * 4];
+        load_block<C>(t, p, 32);
+#pragma unroll
+        for (int k = 0; k < C::BL; k++) t[k] -= lo[k];
+        store_block<C>(p, t);
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void store_zero_block(int4* buf, int blk, int lane) {
+    int z[C::CH * 4];
+#pragma unroll
+    for (int k = 0; k < C::CH * 4; k++) z[k] = 0;
+    store_block<C>(blk_ptr<C>(buf, blk, lane), z);
+}
+
+// ph = PH_MUL / PH_SQR : T  = V * Y          (Y = V for PH_SQR)
+// ph = PH_HIGH         : Q  = digits [L,2L) of q1(T) * mu
+// ph = PH_LOW          : V  = lo_L(T) - lo_L(Q * Nt), rippled
+template <class C>
+__device__ __noinline__ void run_phase(int4* smem_base, const int4* Y, int ph) {
+    constexpr int G = C::G;
+    Smem<C> S(smem_base);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    Pending<C> p0, p1;
+    p0.blk = -1; p1.blk = -1;
+    // hi_dst/hi_src: buffers of the step-2 read-modify-write; nblk: number of blocks of the result; sign of the Hi part
+    int4* hi_dst; const int4* hi_src; int nblk, sign;
+    if (ph <= PH_SQR) {
+        const int4* Yb = ph == PH_SQR ? S.V : Y;
+        {   // anti-diagonal role: pairs i = 0..role
+            int d = role;
+            int i_hi = ph == PH_SQR ? d / 2 : d;
+            run_job<C>(p0, ph, d, 0, i_hi, M_FULL, S.V, Yb + lane, C::BLK4, 32, S.T, d, 1, lane);
+            p0.blk = d;
+        }
+        if (role < G - 1) {   // anti-diagonal role+G: pairs i = role+1..G-1
+            int d = role + G;
+            int i_hi = ph == PH_SQR ? d / 2 : G - 1;
+            run_job<C>(p1, ph, d, d - G + 1, i_hi, M_FULL, S.V, Yb + lane, C::BLK4, 32, S.T, d, 1, lane);
+            p1.blk = d;
+        } else {
+            store_zero_block<C>(S.T, 2 * G - 1, lane);      // block 2G-1 has no Lo contribution
+        }
+        hi_dst = S.T; hi_src = S.T; nblk = 2 * G; sign = 1;
+    } else if (ph == PH_HIGH) {
+        if (role < G - 1) {
+            int d = role + G;
+            run_job<C>(p0, ph, d, d - G + 1, G - 1, M_FULL, S.T, S.mu, C::CH, 1, S.Q, d - G, 1, lane);
+            p0.blk = d - G;
+        } else {          // anti-diagonal G-1: only the columns at and above the guard; its Lo part lies below digit L
+            run_job<C>(p0, ph, G - 1, 0, G - 1, M_UTG, S.T, S.mu, C::CH, 1, S.Q, 0, 0, lane);
+            p0.blk = -1;
+            store_zero_block<C>(S.Q, G - 1, lane);          // Q block G-1 has no Lo contribution
+        }
+        hi_dst = S.Q; hi_src = S.Q; nblk = G; sign = 1;
+    } else {
+        int d = role;
+        run_job<C>(p0, ph, d, 0, d, role < G - 1 ? M_FULL : M_LT, S.Q, S.Nt, C::CH, 1, S.T, d, 2, lane);
+        p0.blk = d;
+        if (role == G - 1) {       // no Hi below digit L: this role ripples block 0 instead (adds zero)
+#pragma unroll
+            for (int k = 0; k < C::CH * 4; k++) p0.hi[k] = 0;
+            p0.spill = 0; p0.blk = -1;
+        }
+        hi_dst = S.V; hi_src = S.T; nblk = G; sign = -1;
+    }
+    __syncthreads();
+    // step 2: Hi digits into block blk+1 with a per-block ripple (phase C also moves the block from T to V)
+    const bool has0 = (ph == PH_HIGH || ph == PH_LOW) ? (p0.blk + 1 <= nblk - 1) : true;
+    if (has0 && p0.blk + 1 <= nblk - 1)
+        p0.carry = add_ripple_block<C>(blk_ptr<C>(hi_dst, p0.blk + 1, lane), blk_ptr<C>(hi_src, p0.blk + 1, lane), p0.hi, sign);
+    if (p1.blk >= 0 && p1.blk + 1 <= nblk - 1)
+        p1.carry = add_ripple_block<C>(blk_ptr<C>(hi_dst, p1.blk + 1, lane), blk_ptr<C>(hi_src, p1.blk + 1, lane), p1.hi, sign);
+    __syncthreads();
+    // step 3: carry of that ripple + the spill digit into digit 0 of block blk+2
+    if (p0.blk + 2 <= nblk - 1) *(int*)blk_ptr<C>(hi_dst, p0.blk + 2, lane) += p0.carry + sign * p0.spill;
+    if (p1.blk >= 0 && p1.blk + 2 <= nblk - 1) *(int*)blk_ptr<C>(hi_dst, p1.blk + 2, lane) += p1.carry + sign * p1.spill;
+    __syncthreads();
+}
+
+// V <- V * Y mod Nt (lazy).  SQR: Y ignored, V <- V^2.
+template <class C, bool SQR>
+__device__ __forceinline__ void mulmod(Smem<C>& S, const int4* Y, int role, int lane) {
+    int4* base = S.V;
+    run_phase<C>(base, Y, SQR ? PH_SQR : PH_MUL);
+    run_phase<C>(base, nullptr, PH_HIGH);
+    run_phase<C>(base, nullptr, PH_LOW);
+}
+
+}  // namespace b28
+}  // namespace pb200

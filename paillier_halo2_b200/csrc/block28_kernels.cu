@@ -1,12 +1,460 @@
-// block28_kernels.cu — placeholder until the block28 engine lands (next commit).
+// block28_kernels.cu — kernels and host driver of the block28 engine (device arithmetic in block28.cuh).
+//
+// Replaces, for `count` independent units: g.modpow(m, n2), r.modpow(n, n2) and the final product of
+// paillier_enc_native (/root/reference/src/paillier.rs:87-92), and the fold of paillier_add_native
+// (:94-97).  Chain per unit (all modulo Nt, a multiple of n^2):
+//   r^n : left-to-right sliding window (w = 5) over the per-key exponent n; the 16 odd powers of r live in
+//         a per-CTA global scratch table (L2-resident), the window schedule is computed once per key;
+//   g^m : fixed-base comb, 8-bit windows: product of TG[i][byte_i(m)], TG[i][d] = g^(d * 2^(8i)) mod Nt
+//         built once per key by this engine (k_gtable_*);
+//   c   : gm * rn, then one exact canonicalisation (finalize) and the shift back from Nt to n^2.
 #include "engine.hpp"
+#include "block28.cuh"
+#include <vector>
+
 namespace pb200 {
-struct Block28Key { int dummy; };
-Block28Key* block28_create(const BigInt&, const BigInt&, uint32_t, int, cudaStream_t, std::string* why, cudaError_t* e) {
-    if (why) *why = "block28 engine not built"; if (e) *e = cudaSuccess; return nullptr;
+using namespace b28;
+
+constexpr int WIN = 5;                 // sliding window of the r-chain
+constexpr int TABN = 1 << (WIN - 1);   // odd powers r^1, r^3, ..., r^(2*TABN-1)
+constexpr int SCRATCH_ENTRIES = TABN + 2;   // + r^2 (table build) + rn (kept while g^m is computed)
+
+struct B28Dev {            // per-key device-side descriptor (same for every configuration)
+    const int4* consts;    // mu, Nt, two_sh : 3 * ENTRY4 int4
+    const int2* ops;       // r-chain schedule: (number of squarings, table index or -1)
+    int n_ops;
+    int first_idx;         // table index the chain starts from
+    const int4* tg;        // comb table: [window][256][ENTRY4]
+    int n_windows;
+    int words_in, words_out;
+    int sh;                // Nt = n2 << sh
+    unsigned nt_top;       // floor(Nt / 2^(28(L-2)))
+    int g_is_one_table;    // unused
+};
+
+// ---- device helpers --------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ int& digit_ref(int4* buf, int p, int lane) {
+    int blk = p / C::BL, k = p % C::BL;
+    return ((int*)(buf + blk * C::BLK4 + (k >> 2) * 32 + lane))[k & 3];
 }
-void block28_destroy(Block28Key*) {}
-const char* block28_name(const Block28Key*) { return "block28"; }
-cudaError_t block28_encrypt(Block28Key*, const u64*, const u64*, size_t, u64*, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t block28_tally(Block28Key*, const u64*, size_t, u64*, cudaStream_t) { return cudaErrorNotSupported; }
+
+// per-lane buffer <- strict digits of the unsigned integer in src[0..nwords) (u64 little-endian)
+template <class C>
+__device__ __forceinline__ void load_value(int4* buf, const u64* src, int nwords, int role, int lane) {
+    int a[C::CH * 4];
+    int carry = 0;
+#pragma unroll
+    for (int k = 0; k < C::BL; k++) {
+        int bit = W * (role * C::BL + k);
+        int wi = bit >> 6, sh = bit & 63;
+        u64 lo = wi < nwords ? src[wi] : 0, hi = wi + 1 < nwords ? src[wi + 1] : 0;
+        u64 v = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+        int t = (int)(v & ((1u << W) - 1)) + carry;
+        int d = sgxt28(t);
+        carry = (t - d) >> W;
+        a[k] = d;
+    }
+#pragma unroll
+    for (int k = C::BL; k < C::CH * 4; k++) a[k] = 0;
+    store_block<C>(blk_ptr<C>(buf, role, lane), a);
+    __syncthreads();
+    if (role + 1 < C::G) *(int*)blk_ptr<C>(buf, role + 1, lane) += carry;
+    __syncthreads();
 }
+
+template <class C>
+__device__ __forceinline__ void set_one(int4* buf, int role, int lane) {
+    int a[C::CH * 4];
+#pragma unroll
+    for (int k = 0; k < C::CH * 4; k++) a[k] = 0;
+    if (role == 0) a[0] = 1;
+    store_block<C>(blk_ptr<C>(buf, role, lane), a);
+    __syncthreads();
+}
+
+// smem per-lane value <-> global [entry][blk][chunk][lane] (coalesced)
+template <class C>
+__device__ __forceinline__ void copy_to_global(int4* g, const int4* buf, int role, int lane) {
+#pragma unroll
+    for (int c = 0; c < C::CH; c++) g[(role * C::CH + c) * 32 + lane] = buf[(role * C::CH + c) * 32 + lane];
+}
+template <class C>
+__device__ __forceinline__ void copy_from_global(int4* buf, const int4* g, int role, int lane) {
+#pragma unroll
+    for (int c = 0; c < C::CH; c++) buf[(role * C::CH + c) * 32 + lane] = g[(role * C::CH + c) * 32 + lane];
+    __syncthreads();
+}
+// smem per-lane value <- one table entry per lane ([blk][chunk] int4, gathered)
+template <class C>
+__device__ __forceinline__ void gather_entry(int4* buf, const int4* entry, int role, int lane) {
+#pragma unroll
+    for (int c = 0; c < C::CH; c++) buf[(role * C::CH + c) * 32 + lane] = __ldg(entry + role * C::CH + c);
+    __syncthreads();
+}
+template <class C>
+__device__ __forceinline__ void scatter_entry(int4* entry, const int4* buf, int role, int lane) {
+#pragma unroll
+    for (int c = 0; c < C::CH; c++) entry[role * C::CH + c] = buf[(role * C::CH + c) * 32 + lane];
+}
+
+template <class C>
+__device__ __forceinline__ void load_consts(int4* smem_base, const B28Dev& K) {
+    int4* k = smem_base + 5 * C::VAL4;
+    for (int i = threadIdx.x; i < 3 * C::ENTRY4; i += C::THREADS) k[i] = K.consts[i];
+    __syncthreads();
+}
+
+// V <- V * (constant in shared memory, ENTRY4 int4, broadcast)
+template <class C>
+__device__ __forceinline__ void mulmod_const(Smem<C>& S, const int4* cst, int role, int lane) {
+    // expand the constant into the per-lane B buffer (keeps phase_product on one code path)
+#pragma unroll
+    for (int c = 0; c < C::CH; c++) S.B[(role * C::CH + c) * 32 + lane] = cst[role * C::CH + c];
+    __syncthreads();
+    mulmod<C, false>(S, S.B, role, lane);
+}
+
+// Exact canonicalisation of the lazy value in V (one thread per lane, role 0): out = ((V * 2^sh) mod Nt) >> sh,
+// written as words_out u64 words.  V must already have been multiplied by two_sh.
+template <class C>
+__device__ void canonical_out(int4* V, const int4* NtC, const B28Dev& K, u64* out, int lane) {
+    constexpr int L = C::L;
+    const int* nt = (const int*)NtC;
+    auto NT = [&](int p) { return nt[(p / C::BL) * C::CH * 4 + (p % C::BL)]; };
+    auto D = [&](int p) -> int& { return digit_ref<C>(V, p, lane); };
+    // full ripple to strict centred digits
+    int carry = 0;
+    for (int p = 0; p < L; p++) { int t = D(p) + carry; int d = sgxt28(t); carry = (t - d) >> W; D(p) = d; }
+    // quotient estimate from the two top digits
+    long long vt = ((long long)D(L - 1) << W) + D(L - 2);
+    long long q = vt / (long long)K.nt_top;
+    if (vt < 0 && vt % (long long)K.nt_top) q -= 1;           // floor division
+    // v -= q * Nt, then fix up into [0, Nt)
+    long long c64 = 0;
+    for (int p = 0; p < L; p++) {
+        long long t = (long long)D(p) - q * (long long)NT(p) + c64;
+        int d = sgxt28((int)t); c64 = (t - d) >> W; D(p) = d;
+    }
+    for (int it = 0; it < 6; it++) {
+        int top = 0;
+        for (int p = L - 1; p >= 0; p--) { top = D(p); if (top) break; }
+        int dir;
+        if (top < 0) dir = 1;                                  // negative: add Nt
+        else {
+            // v >= Nt ?  compare via sign of v - Nt
+            int cc = 0, last = 0; bool nonzero = false;
+            for (int p = 0; p < L; p++) { int t = D(p) - NT(p) + cc; int d = sgxt28(t); cc = (t - d) >> W; if (d) { last = d; nonzero = true; } }
+            dir = (!nonzero || last > 0) ? -1 : 0;             // v - Nt >= 0: subtract
+        }
+        if (dir == 0) break;
+        int cc = 0;
+        for (int p = 0; p < L; p++) { int t = D(p) + dir * NT(p) + cc; int d = sgxt28(t); cc = (t - d) >> W; D(p) = d; }
+    }
+    // unsigned digits (value is now in [0, Nt))
+    carry = 0;
+    for (int p = 0; p < L; p++) { int t = D(p) + carry; D(p) = t & ((1 << W) - 1); carry = t >> W; }
+    // shift right by sh and pack into 64-bit words
+    for (int j = 0; j < K.words_out; j++) {
+        u64 w = 0;
+        int bit0 = 64 * j + K.sh;
+        int p0 = bit0 / W;
+        for (int p = p0; p < p0 + 4 && p < L; p++) {
+            int off = W * p - bit0;                           // position of digit p relative to the word
+            u64 d = (u64)(unsigned)D(p);
+            if (off >= 64) break;
+            w |= off >= 0 ? d << off : d >> (-off);
+        }
+        out[j] = w;
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void finalize(Smem<C>& S, const B28Dev& K, u64* out, bool active, int role, int lane) {
+    mulmod_const<C>(S, S.two_sh, role, lane);
+    if (role == 0 && active) canonical_out<C>(S.V, S.Nt, K, out, lane);
+    __syncthreads();
+}
+
+// ---- kernels ---------------------------------------------------------------------------------
+// comb table, stage 1: bases[i] = g^(2^(8i)) mod Nt, i < n_windows (one CTA; every lane computes the same value)
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1) k_gtable_bases(B28Dev K, const u64* g_words, int4* bases) {
+    extern __shared__ int4 smem[];
+    Smem<C> S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    load_consts<C>(smem, K);
+    load_value<C>(S.V, g_words, K.words_in, role, lane);
+    for (int i = 0; i < K.n_windows; i++) {
+        if (lane == 0) scatter_entry<C>(bases + (size_t)i * C::ENTRY4, S.V, role, lane);
+        __syncthreads();
+        if (i + 1 < K.n_windows)
+            for (int s = 0; s < 8; s++) mulmod<C, true>(S, nullptr, role, lane);
+    }
+}
+// comb table, stage 2: lane = window; TG[i][d] = bases[i]^d, d < 256
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1) k_gtable_fill(B28Dev K, const int4* bases, int4* tg) {
+    extern __shared__ int4 smem[];
+    Smem<C> S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    load_consts<C>(smem, K);
+    int win = blockIdx.x * 32 + lane;
+    bool active = win < K.n_windows;
+    if (!active) win = K.n_windows - 1;
+    int4* row = tg + (size_t)win * 256 * C::ENTRY4;
+    set_one<C>(S.V, role, lane);
+    if (active) scatter_entry<C>(row, S.V, role, lane);
+    gather_entry<C>(S.V, bases + (size_t)win * C::ENTRY4, role, lane);
+    gather_entry<C>(S.B, bases + (size_t)win * C::ENTRY4, role, lane);
+    for (int d = 1; d < 256; d++) {
+        if (active) scatter_entry<C>(row + (size_t)d * C::ENTRY4, S.V, role, lane);
+        __syncthreads();
+        if (d + 1 < 256) mulmod<C, false>(S, S.B, role, lane);
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 2) k_encrypt(B28Dev K, const u64* __restrict__ m, const u64* __restrict__ r,
+                                                            size_t count, u64* __restrict__ c_out, int4* scratch) {
+    extern __shared__ int4 smem[];
+    Smem<C> S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    load_consts<C>(smem, K);
+    size_t unit = (size_t)blockIdx.x * 32 + lane;
+    const bool active = unit < count;
+    if (!active) unit = count - 1;
+    int4* tab = scratch + (size_t)blockIdx.x * SCRATCH_ENTRIES * C::VAL4;
+    // ---- r^n: odd powers table, then the per-key window schedule
+    load_value<C>(S.V, r + unit * K.words_in, K.words_in, role, lane);
+    copy_to_global<C>(tab, S.V, role, lane);                                   // tab[0] = r
+    mulmod<C, true>(S, nullptr, role, lane);                                   // r^2
+    copy_to_global<C>(tab + (size_t)TABN * C::VAL4, S.V, role, lane);
+    __syncthreads();
+    copy_from_global<C>(S.V, tab, role, lane);
+    for (int j = 1; j < TABN; j++) {
+        copy_from_global<C>(S.B, tab + (size_t)TABN * C::VAL4, role, lane);
+        mulmod<C, false>(S, S.B, role, lane);                                  // r^(2j+1)
+        copy_to_global<C>(tab + (size_t)j * C::VAL4, S.V, role, lane);
+    }
+    __syncthreads();
+    copy_from_global<C>(S.V, tab + (size_t)K.first_idx * C::VAL4, role, lane);
+    for (int o = 0; o < K.n_ops; o++) {
+        int2 op = K.ops[o];
+        for (int s = 0; s < op.x; s++) mulmod<C, true>(S, nullptr, role, lane);
+        if (op.y >= 0) {
+            copy_from_global<C>(S.B, tab + (size_t)op.y * C::VAL4, role, lane);
+            mulmod<C, false>(S, S.B, role, lane);
+        }
+    }
+    copy_to_global<C>(tab + (size_t)(TABN + 1) * C::VAL4, S.V, role, lane);    // rn
+    __syncthreads();
+    // ---- g^m: comb over the bytes of m
+    const u64* mw = m + unit * K.words_in;
+    {
+        int d0 = (int)(mw[0] & 255);
+        gather_entry<C>(S.V, K.tg + (size_t)d0 * C::ENTRY4, role, lane);
+    }
+    for (int i = 1; i < K.n_windows; i++) {
+        int d = (int)((mw[i >> 3] >> (8 * (i & 7))) & 255);
+        gather_entry<C>(S.B, K.tg + ((size_t)i * 256 + d) * C::ENTRY4, role, lane);
+        mulmod<C, false>(S, S.B, role, lane);
+    }
+    // ---- c = gm * rn, canonical
+    copy_from_global<C>(S.B, tab + (size_t)(TABN + 1) * C::VAL4, role, lane);
+    mulmod<C, false>(S, S.B, role, lane);
+    finalize<C>(S, K, c_out + unit * K.words_out, active, role, lane);
+}
+
+// out[b] = product of the inputs assigned to CTA b (lane l of CTA b folds units b*32+l, +stride, ...), canonical
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 2) k_tally(B28Dev K, const u64* __restrict__ c, size_t count, u64* __restrict__ out) {
+    extern __shared__ int4 smem[];
+    Smem<C> S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    load_consts<C>(smem, K);
+    const size_t stride = (size_t)gridDim.x * 32;
+    size_t first = (size_t)blockIdx.x * 32 + lane;
+    size_t max_iters = (count + stride - 1) / stride;
+    set_one<C>(S.V, role, lane);
+    for (size_t it = 0; it < max_iters; it++) {
+        size_t u = first + it * stride;
+        const bool have = u < count;
+        load_value<C>(S.B, c + (have ? u : count - 1) * K.words_out, K.words_out, role, lane);
+        if (!have) {                                   // lanes without an input multiply by one
+            int a[C::CH * 4];
+#pragma unroll
+            for (int k = 0; k < C::CH * 4; k++) a[k] = 0;
+            if (role == 0) a[0] = 1;
+            store_block<C>(blk_ptr<C>(S.B, role, lane), a);
+        }
+        __syncthreads();
+        mulmod<C, false>(S, S.B, role, lane);
+    }
+    // fold the 32 lanes: B[lane] = V[lane ^ off]
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int ch = 0; ch < C::CH; ch++) S.B[(role * C::CH + ch) * 32 + lane] = S.V[(role * C::CH + ch) * 32 + (lane ^ off)];
+        __syncthreads();
+        mulmod<C, false>(S, S.B, role, lane);
+    }
+    finalize<C>(S, K, out + (size_t)blockIdx.x * K.words_out, lane == 0, role, lane);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+struct Block28Key {
+    int G = 0, BL = 0;
+    std::string name;
+    B28Dev dev{};
+    int4* d_consts = nullptr; int2* d_ops = nullptr; int4* d_tg = nullptr; u64* d_gwords = nullptr;
+    int4* d_scratch = nullptr; size_t scratch_ctas = 0;
+    u64* d_partials = nullptr; size_t partials_cap = 0;
+    int sms = 148;
+};
+
+template <class C>
+static void to_entry(const BigInt& v, std::vector<int>& out) {   // centred digits in [blk][chunk*4] layout
+    out.assign(C::ENTRY4 * 4, 0);
+    int carry = 0;
+    for (int p = 0; p < C::L; p++) {
+        int t = (int)v.bits_at((size_t)W * p, W) + carry;
+        int d = ((t + (1 << (W - 1))) & ((1 << W) - 1)) - (1 << (W - 1));
+        carry = (t - d) >> W;
+        out[(p / C::BL) * C::CH * 4 + (p % C::BL)] = d;
+    }
+    if (carry != 0 || v.bits() > (size_t)W * C::L - 1) throw std::runtime_error("block28: constant does not fit");
+}
+
+#define CUK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { *cuda_err = e_; block28_destroy(key); return nullptr; } } while (0)
+
+template <class C>
+static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits, int device, cudaStream_t st, cudaError_t* cuda_err) {
+    Block28Key* key = new Block28Key();
+    key->G = C::G; key->BL = C::BL;
+    key->name = "block28<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">";
+    cudaDeviceProp prop;
+    CUK(cudaGetDeviceProperties(&prop, device));
+    key->sms = prop.multiProcessorCount;
+    BigInt n2 = BigInt::mul(n, n);
+    int sh = C::KN - (int)n2.bits();
+    BigInt Nt = BigInt::shl(n2, sh);
+    BigInt mu = BigInt::div(BigInt::pow2(2 * (size_t)C::BETA), Nt);
+    BigInt two_sh = BigInt::pow2(sh);
+    std::vector<int> e_mu, e_nt, e_sh, all;
+    to_entry<C>(mu, e_mu); to_entry<C>(Nt, e_nt); to_entry<C>(two_sh, e_sh);
+    all.insert(all.end(), e_mu.begin(), e_mu.end());
+    all.insert(all.end(), e_nt.begin(), e_nt.end());
+    all.insert(all.end(), e_sh.begin(), e_sh.end());
+    CUK(cudaMalloc(&key->d_consts, all.size() * sizeof(int)));
+    CUK(cudaMemcpyAsync(key->d_consts, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    // sliding-window schedule for the exponent n
+    std::vector<int2> ops;
+    int first_idx = 0;
+    {
+        int i = (int)n.bits() - 1, pending = 0; bool first = true;
+        while (i >= 0) {
+            if (!n.bit(i)) { pending++; i--; continue; }
+            int j = i - WIN + 1; if (j < 0) j = 0;
+            while (!n.bit(j)) j++;
+            int val = 0; for (int b = i; b >= j; b--) val = (val << 1) | (n.bit(b) ? 1 : 0);
+            int len = i - j + 1;
+            if (first) { first_idx = (val - 1) / 2; first = false; }
+            else ops.push_back(make_int2(pending + len, (val - 1) / 2));
+            pending = 0; i = j - 1;
+        }
+        if (pending) ops.push_back(make_int2(pending, -1));
+    }
+    CUK(cudaMalloc(&key->d_ops, (ops.size() + 1) * sizeof(int2)));
+    if (!ops.empty()) CUK(cudaMemcpyAsync(key->d_ops, ops.data(), ops.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    int n_windows = (int)((n_bits + 7) / 8);
+    uint32_t win = (n_bits + 63) / 64;
+    std::vector<u64> gw(win);
+    g.to_u64_le(gw.data(), win);
+    CUK(cudaMalloc(&key->d_gwords, win * sizeof(u64)));
+    CUK(cudaMemcpyAsync(key->d_gwords, gw.data(), win * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CUK(cudaMalloc(&key->d_tg, (size_t)n_windows * 256 * C::ENTRY4 * sizeof(int4)));
+    B28Dev& K = key->dev;
+    K.consts = key->d_consts; K.ops = key->d_ops; K.n_ops = (int)ops.size(); K.first_idx = first_idx;
+    K.tg = key->d_tg; K.n_windows = n_windows; K.words_in = (int)win; K.words_out = (int)((2 * n_bits + 63) / 64);
+    K.sh = sh;
+    K.nt_top = (unsigned)BigInt::shr(Nt, (size_t)W * (C::L - 2)).bits_at(0, 32);
+    // comb table
+    CUK(cudaFuncSetAttribute(k_gtable_bases<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    CUK(cudaFuncSetAttribute(k_gtable_fill<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    CUK(cudaFuncSetAttribute(k_encrypt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    CUK(cudaFuncSetAttribute(k_tally<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    int4* d_bases = nullptr;
+    CUK(cudaMalloc(&d_bases, (size_t)n_windows * C::ENTRY4 * sizeof(int4)));
+    k_gtable_bases<C><<<1, C::THREADS, C::SMEM_BYTES, st>>>(K, key->d_gwords, d_bases); count_launch();
+    k_gtable_fill<C><<<(n_windows + 31) / 32, C::THREADS, C::SMEM_BYTES, st>>>(K, d_bases, key->d_tg); count_launch();
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d_bases);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { *cuda_err = e; block28_destroy(key); return nullptr; }
+    return key;
+}
+
+template <class C>
+static cudaError_t encrypt_cfg(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st) {
+    size_t ctas = (count + 31) / 32;
+    if (ctas > key->scratch_ctas) {
+        if (key->d_scratch) cudaFree(key->d_scratch);
+        key->d_scratch = nullptr; key->scratch_ctas = 0;
+        cudaError_t e = cudaMalloc(&key->d_scratch, ctas * SCRATCH_ENTRIES * C::VAL4 * sizeof(int4));
+        if (e != cudaSuccess) return e;
+        key->scratch_ctas = ctas;
+    }
+    k_encrypt<C><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <class C>
+static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64* d_out, cudaStream_t st) {
+    const int wo = key->dev.words_out;
+    size_t cap = (size_t)2 * key->sms + 8;
+    if (!key->d_partials) {
+        cudaError_t e = cudaMalloc(&key->d_partials, cap * wo * sizeof(u64));
+        if (e != cudaSuccess) return e;
+        key->partials_cap = cap;
+    }
+    size_t ctas = (count + 31) / 32;
+    if (ctas > (size_t)2 * key->sms) ctas = (size_t)2 * key->sms;
+    if (ctas <= 1) {
+        k_tally<C><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out); count_launch();
+        return cudaGetLastError();
+    }
+    k_tally<C><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, key->d_partials); count_launch();
+    k_tally<C><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->d_partials, ctas, d_out); count_launch();
+    return cudaGetLastError();
+}
+
+typedef Cfg<8, 19> Cfg2048;   // L = 152 digits: n^2 up to 4232 bits (|n| <= 2048 and the reference's default sizes)
+
+Block28Key* block28_create(const BigInt& n, const BigInt& g, uint32_t n_bits, int device, cudaStream_t st,
+                           std::string* why, cudaError_t* cuda_err) {
+    *cuda_err = cudaSuccess;
+    if (2 * (size_t)n_bits <= (size_t)Cfg2048::KN - 2 && n_bits % 8 == 0)
+        return create_cfg<Cfg2048>(n, g, n_bits, device, st, cuda_err);
+    if (why) *why = "block28: no compiled configuration covers this key size";
+    return nullptr;
+}
+void block28_destroy(Block28Key* key) {
+    if (!key) return;
+    if (key->d_consts) cudaFree(key->d_consts);
+    if (key->d_ops) cudaFree(key->d_ops);
+    if (key->d_tg) cudaFree(key->d_tg);
+    if (key->d_gwords) cudaFree(key->d_gwords);
+    if (key->d_scratch) cudaFree(key->d_scratch);
+    if (key->d_partials) cudaFree(key->d_partials);
+    delete key;
+}
+const char* block28_name(const Block28Key* key) { return key->name.c_str(); }
+cudaError_t block28_encrypt(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st) {
+    return encrypt_cfg<Cfg2048>(key, d_m, d_r, count, d_c, st);
+}
+cudaError_t block28_tally(Block28Key* key, const u64* d_c, size_t count, u64* d_out, cudaStream_t st) {
+    return tally_cfg<Cfg2048>(key, d_c, count, d_out, st);
+}
+
+}  // namespace pb200

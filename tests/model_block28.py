@@ -74,7 +74,7 @@ def antidiag(P, A, B, pairs, mode_of=None):
 
 
 def normalize_D(P, acc):
-    """ripple the 2BL-1 column sums into 2BL digits: strict except the last, which absorbs the carry"""
+    """ripple the 2BL-1 column sums into 2BL strict digits + one small spill digit (weight 2^(28*2BL))"""
     out = []
     carry = 0
     for c in acc:
@@ -83,8 +83,11 @@ def normalize_D(P, acc):
         d = sgxt(t)
         out.append(d)
         carry = (t - d) >> W
-    out.append(carry)            # digit 2BL-1: loose
-    assert abs(carry) < (1 << 31), "top digit of D does not fit int32"
+    d = sgxt(carry)
+    out.append(d)                 # digit 2BL-1
+    spill = (carry - d) >> W
+    assert abs(spill) <= 4, "spill digit larger than expected"
+    out.append(spill)             # digit 2BL
     return out
 
 
@@ -102,6 +105,7 @@ def product(P, A, B, nblocks_out, which, sqr=False):
     """X blocks [0, nblocks_out) of A*B.  which: "full" | "high" (blocks >= G exact up to the guard) | "low" (blocks < G)"""
     G, BL = P.G, P.BL
     X = [0] * (nblocks_out * BL)
+    Ds = {}
     for d in range(2 * G - 1):
         pairs = []
         for i in range(G):
@@ -129,12 +133,27 @@ def product(P, A, B, nblocks_out, which, sqr=False):
         if not pairs:
             continue
         D = normalize_D(P, antidiag(P, A, B, pairs))
-        for k in range(2 * BL):
-            pos = d * BL + k
-            if pos < len(X):
-                X[pos] += D[k]
-            else:
-                assert which == "low" or D[k] == 0 or pos >= len(X)
+        Ds[d] = D
+    # step 1: Lo parts (plain stores); step 2: Hi parts added with a per-block ripple; step 3: deposits
+    nb = nblocks_out
+    for d, D in Ds.items():
+        if d < nb:
+            for k in range(BL):
+                X[d * BL + k] += D[k]
+    carries = {}
+    for d, D in Ds.items():
+        if d + 1 < nb:
+            carry = 0
+            for k in range(BL):
+                t = X[(d + 1) * BL + k] + D[BL + k] + carry
+                assert abs(t) < (1 << 31)
+                dd = sgxt(t)
+                X[(d + 1) * BL + k] = dd
+                carry = (t - dd) >> W
+            carries[d] = carry
+    for d, D in Ds.items():
+        if d + 2 < nb:
+            X[(d + 2) * BL] += carries.get(d, 0) + D[2 * BL]
     return X
 
 
@@ -171,9 +190,18 @@ def mulmod(P, keyc, A, B, sqr=False):
     Nt_d = keyc_digits(P, keyc)[0]
     Pl = product(P, qh, Nt_d, G, "low")
     R = [X[i] - Pl[i] for i in range(L)]
-    R = ripple_blocks(P, R, G)
-    R[L - 1] = sgxt(R[L - 1])                                    # drop multiples of 2^(28L)
-    return R
+    out = [0] * L
+    for b in range(G):                                           # per-block ripple, carry deposited into the next block
+        carry = 0
+        for k in range(BL):
+            t = R[b * BL + k] + carry
+            assert abs(t) < (1 << 31)
+            dd = sgxt(t)
+            out[b * BL + k] = dd
+            carry = (t - dd) >> W
+        if b + 1 < G:
+            R[(b + 1) * BL] += carry                             # (the kernel does this after a barrier)
+    return out                                                   # carry out of the top block dropped: mod 2^(28L)
 
 
 _cache = {}
