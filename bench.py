@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — Paillier enc/s at |n|=2048 on N B200s (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm   (N>1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU path on the host cores
+
+A step is one pass of the hot path over one batch: encrypt 2^16 independent (m, r) pairs under one
+2048-bit key (BASELINE.json configs[1]; SURVEY.md §8d inputs: seeded Paillier key, random g in
+[2, 2^|n|), full-width Philox m, r).  `value` times the device-resident call (inputs already in HBM) with
+CUDA events on the stream the kernel is launched on; `e2e` times the host-buffer C-ABI call
+(pb200_encrypt_batch: pinned host -> device, kernel, device -> host) by wall clock around the blocking call.
+Multi-GPU: units are independent, so each rank encrypts its own 2^16 units (weak scaling, no data-path
+collective); the time is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BITS = 2048
+UNITS = 1 << 16
+METRIC = "paillier_enc_per_s_n2048"
+UNIT = "enc/s"
+
+
+def mac_counts(n_bits: int):
+    """Algorithmic 32x32->64 MACs per modular multiplication / squaring over n^2:
+    W_mul = 2*L32^2 + L32, W_sqr = (L32^2 + L32)/2 + L32^2 + L32, L32 = 2|n|/32."""
+    l32 = 2 * n_bits // 32
+    return 2 * l32 * l32 + l32, (l32 * l32 + l32) // 2 + l32 * l32 + l32
+
+
+def imad_peak():
+    """P_imad: measured mad.wide MAC/s of this pool's B200 (profiles/imad_peak_r01.json, written by
+    csrc/microbench/imad_peak.cu).  MEASURED_PEAKS.json carries no integer-pipe peak."""
+    path = os.path.join(ROOT, "profiles", "imad_peak_r01.json")
+    try:
+        d = json.load(open(path))
+        return max(r["mac_per_s"] for r in d["results"] if r["variant"].startswith("wide_indep")), "profiles/imad_peak_r01.json"
+    except Exception:
+        return 148 * 64 * 1.965e9, "nominal 148 SM x 64 IMAD/clk x 1.965 GHz"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(threads: int, units: int, key: dict):
+    """The CPU restatement (oracle/paillier_cpu.cpp: OpenSSL BIGNUM port of src/paillier.rs:87-92) on the
+    first `units` units of the same workload, `threads` worker threads.  Returns (enc/s, seconds)."""
+    from oracle import cpu_ref
+    from paillier_halo2_b200 import workload
+
+    m_w, r_w = workload.units(N_BITS, units)
+    t0 = time.perf_counter()
+    cpu_ref.enc_batch(key["n"], key["g_rand"], N_BITS // 64, m_w, r_w, threads=threads)
+    dt = time.perf_counter() - t0
+    return units / dt, dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm (OpenSSL port; the Rust original cannot be built
+    here) with every host thread, on bounded samples of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_ref
+    from paillier_halo2_b200 import workload
+
+    key = workload.load_key(N_BITS)
+    threads = cpu_ref.hardware_threads()
+    sample = max(64, min(UNITS, 96 * threads))          # ~3 s of CPU work per step at ~35 enc/s/thread
+    m_w, r_w = workload.units(N_BITS, sample)
+    for _ in range(args.warmup):
+        cpu_ref.enc_batch(key["n"], key["g_rand"], N_BITS // 64, m_w[: max(threads, 8)], r_w[: max(threads, 8)], threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_ref.enc_batch(key["n"], key["g_rand"], N_BITS // 64, m_w, r_w, threads=threads)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 (OpenSSL BIGNUM)", "data": "synthetic",
+        "config": {"workload": f"batched encrypt |n|={N_BITS}, bounded sample of {sample} units/step of the 2^16-unit batch, random g",
+                   "key": "seeded p*q (SURVEY.md 8d)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} units x {args.steps} steps, OpenSSL BN_mod_exp x2 + BN_mod_mul per unit"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--units", type=int, default=UNITS, help="units per GPU per step (default: the BASELINE config, 2^16)")
+    ap.add_argument("--g", default="rand", choices=["rand", "std"], help="rand: random g (headline); std: g = n+1")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--engine", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from paillier_halo2_b200 import PaillierKey, _lib, workload
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the Paillier hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    kd = workload.load_key(N_BITS)
+    g = kd["g_rand"] if args.g == "rand" else kd["g_std"]
+    units = args.units
+    key = PaillierKey(kd["n"], g, N_BITS, 64, device=local_rank)
+    if args.engine:
+        key.set_engine(args.engine)
+    n_sqr, n_mul = key.chain_counts()
+    w_mul, w_sqr = mac_counts(N_BITS)
+    a_enc = n_sqr * w_sqr + n_mul * w_mul
+
+    # this rank's units: rank r takes the r-th 2^16-unit slice of the Philox stream
+    m_w, r_w = workload.units(N_BITS, units, seed_offset=1000 * rank)
+    m_pin = torch.from_numpy(m_w.view(np.int64)).pin_memory()
+    r_pin = torch.from_numpy(r_w.view(np.int64)).pin_memory()
+    c_pin = torch.empty((units, key.words_out), dtype=torch.int64).pin_memory()
+    d_m = m_pin.cuda(non_blocking=False)
+    d_r = r_pin.cuda(non_blocking=False)
+    d_c = torch.empty((units, key.words_out), dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+    stream = torch.cuda.ExternalStream(key.stream, device=torch.device("cuda", local_rank))
+
+    def step_dev():
+        key.encrypt_dev(d_m.data_ptr(), d_r.data_ptr(), units, d_c.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        step_dev()
+    key.sync()
+
+    # ---- timed: K steps, device-resident inputs, CUDA events on the launching stream, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    launches0 = lib.pb200_kernel_launches()
+    barrier()
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_dev()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.pb200_kernel_launches() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * units * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: the host-buffer C-ABI call, pinned host memory, H2D + kernel + D2H inside the timed region
+    import ctypes as C
+    hp = [C.cast(t_.data_ptr(), _lib.u64p) for t_ in (m_pin, r_pin, c_pin)]
+
+    def step_host():
+        _lib.check(lib.pb200_encrypt_batch(key.handle, hp[0], hp[1], units, hp[2]), "pb200_encrypt_batch")
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * units * args.steps / e2e_s
+
+    # parity spot check of the last step's output against the CPU port (a checker, never the thing measured)
+    parity = None
+    if rank == 0:
+        from oracle import cpu_ref
+        idx = [0, 1, units // 2, units - 1]
+        want = cpu_ref.enc_batch(kd["n"], g, N_BITS // 64, m_w[idx], r_w[idx], threads=4)
+        got_dev = d_c.cpu().numpy().view(np.uint64)[idx]
+        got_host = c_pin.numpy().view(np.uint64)[idx]
+        parity = bool((want == got_dev).all() and (want == got_host).all())
+
+    if rank == 0:
+        peak, peak_src = imad_peak()
+        kernel_s = dev_ms * 1e-3 / args.steps            # one launch per step per rank
+        achieved = units * a_enc / kernel_s
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64 accumulators over signed 28-bit digits (IMAD.WIDE)", "data": "synthetic",
+            "config": {"workload": f"batched encrypt |n|={N_BITS} (4096-bit n^2), {units} units per GPU per step, "
+                                   f"{'random g' if args.g == 'rand' else 'g = n+1'}, full-width m and r (BASELINE.json configs[1])",
+                       "engine": key.engine, "l2": "flushed between timed steps (256 MiB write)",
+                       "chain": {"mod_sqr": n_sqr, "mod_mul": n_mul, "mac_per_enc": a_enc}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(m_pin.numel() * 8 + r_pin.numel() * 8),
+                    "d2h_bytes_per_step": int(c_pin.numel() * 8)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "parity_spot_check": parity,
+            "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC/s (32x32->64 multiply-accumulate)",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "integer-multiply pipe bound; algorithmic MACs = units x (mod_sqr x W_sqr + mod_mul x W_mul), "
+                                 "W for 32-bit limbs over the 4096-bit n^2 (SURVEY.md 8d); HBM and tensor pipes are idle by design"},
+        }
+        if not args.no_cpu and world >= 1:
+            from oracle import cpu_ref
+            threads = cpu_ref.hardware_threads()
+            sample = max(64, min(units, 256 * threads))
+            v, dt = cpu_baseline(threads, sample, kd)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"first {sample} units of the same batch, {dt:.1f} s, OpenSSL BIGNUM port of src/paillier.rs:87-92"}
+        print(json.dumps(line), flush=True)
+    key.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

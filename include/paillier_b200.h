@@ -79,6 +79,9 @@ const char* pb200_key_engine(const pb200_key* key);
  * ciphertext, always available, used as the on-GPU cross-check), 2 = block28 (warp-role Barrett) */
 int pb200_key_set_engine(pb200_key* key, int engine);
 void* pb200_key_stream(const pb200_key* key);        /* cudaStream_t the key enqueues on */
+/* modular squarings and multiplications the selected engine executes per encryption (the chain the
+ * roofline's algorithmic work is counted on; excludes the engine's internal canonicalisation) */
+int pb200_key_chain_counts(const pb200_key* key, uint64_t* n_sqr, uint64_t* n_mul);
 int pb200_key_sync(pb200_key* key);                  /* cudaStreamSynchronize on that stream */
 
 /* ---- encrypt --------------------------------------------------------------------------------
@@ -145,8 +148,10 @@ int pb200_encrypt_witness_batch(pb200_key* key, const uint64_t* m_le, const uint
 /* number of records unit (m) contributes to the per-unit stream: popcount(m) + bits(n) + popcount(n) + 1 */
 uint64_t pb200_witness_records_for(const pb200_key* key, const uint64_t* m_le);
 
-/* 64-bit FNV-1a digests of each unit's record stream (all words, little-endian byte order),
- * computed on the device without materialising the witness on the host: digest_out[count]. */
+/* 64-bit digest of each unit's record stream, computed on the device without materialising the
+ * witness on the host: digest_out[count].  Per record H = sum_j w_j * C^(j+1) mod 2^64 over its
+ * 2*words_out words (q then rem), C = 0x9E3779B97F4A7C15; per unit D = 0xcbf29ce484222325, then
+ * D = (D ^ H) * 0x100000001b3 mod 2^64 for each record in stream order. */
 int pb200_encrypt_witness_digest(pb200_key* key, const uint64_t* m_le, const uint64_t* r_le, size_t count,
                                  uint64_t* c_out_le /* nullable */, uint64_t* digest_out);
 

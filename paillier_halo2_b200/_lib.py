@@ -56,6 +56,7 @@ SYMBOLS = {
     "pb200_key_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
     "pb200_key_stream": (C.c_void_p, [C.c_void_p]),
     "pb200_key_sync": (C.c_int, [C.c_void_p]),
+    "pb200_key_chain_counts": (C.c_int, [C.c_void_p, u64p, u64p]),
     "pb200_encrypt_batch": (C.c_int, [C.c_void_p, u64p, u64p, C.c_size_t, u64p]),
     "pb200_encrypt_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "pb200_add_batch": (C.c_int, [C.c_void_p, u64p, u64p, C.c_uint32, C.c_size_t, u64p, u64p]),

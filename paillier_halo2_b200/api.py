@@ -102,6 +102,23 @@ class PaillierKey:
         check(self._lib.pb200_key_n2(self._h, _p(out)), "pb200_key_n2")
         return words_to_ints(out)[0]
 
+    def chain_counts(self):
+        """(modular squarings, modular multiplications) the selected engine executes per encryption."""
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self._lib.pb200_key_chain_counts(self._h, C.byref(a), C.byref(b)), "pb200_key_chain_counts")
+        return int(a.value), int(b.value)
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.pb200_key_stream(self._h) or 0)
+
+    def encrypt_dev(self, d_m: int, d_r: int, count: int, d_c: int) -> None:
+        """Device-pointer variant (pb200_encrypt_batch_dev): enqueues on the key's stream, no synchronise."""
+        check(self._lib.pb200_encrypt_batch_dev(self._h, d_m, d_r, count, d_c), "pb200_encrypt_batch_dev")
+
+    def tally_dev(self, d_c: int, count: int, d_out: int) -> None:
+        check(self._lib.pb200_tally_dev(self._h, d_c, count, d_out), "pb200_tally_dev")
+
     def sync(self) -> None:
         check(self._lib.pb200_key_sync(self._h), "pb200_key_sync")
 

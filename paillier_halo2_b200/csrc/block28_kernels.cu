@@ -310,6 +310,7 @@ struct Block28Key {
     int4* d_scratch = nullptr; size_t scratch_ctas = 0;
     u64* d_partials = nullptr; size_t partials_cap = 0;
     int sms = 148;
+    uint64_t n_sqr = 0, n_mul = 0;   // modular squarings / multiplications per encryption
 };
 
 template <class C>
@@ -364,6 +365,8 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
         }
         if (pending) ops.push_back(make_int2(pending, -1));
     }
+    key->n_sqr = 1; key->n_mul = (TABN - 1) + (uint64_t)((n_bits + 7) / 8 - 1) + 1;   // r^2; table; comb; gm*rn
+    for (auto& o : ops) { key->n_sqr += (uint64_t)o.x; if (o.y >= 0) key->n_mul += 1; }
     CUK(cudaMalloc(&key->d_ops, (ops.size() + 1) * sizeof(int2)));
     if (!ops.empty()) CUK(cudaMemcpyAsync(key->d_ops, ops.data(), ops.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
     int n_windows = (int)((n_bits + 7) / 8);
@@ -450,6 +453,7 @@ void block28_destroy(Block28Key* key) {
     delete key;
 }
 const char* block28_name(const Block28Key* key) { return key->name.c_str(); }
+void block28_chain_counts(const Block28Key* key, uint64_t* n_sqr, uint64_t* n_mul) { *n_sqr = key->n_sqr; *n_mul = key->n_mul; }
 cudaError_t block28_encrypt(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st) {
     return encrypt_cfg<Cfg2048>(key, d_m, d_r, count, d_c, st);
 }

@@ -154,6 +154,14 @@ int pb200_key_set_engine(pb200_key* k, int engine) {
     return PB200_OK;
 }
 void* pb200_key_stream(const pb200_key* k) { return k ? (void*)k->stream : nullptr; }
+int pb200_key_chain_counts(const pb200_key* k, uint64_t* n_sqr, uint64_t* n_mul) {
+    if (!k || !n_sqr || !n_mul) return PB200_ERR_INVALID_ARG;
+    if (use_fast(k)) { block28_chain_counts(k->fast, n_sqr, n_mul); return PB200_OK; }
+    // simple64 runs the reference's LSB-first chain: bits(n) squarings; popcount(n) + ~popcount(m) + 1 multiplications
+    uint64_t pn = 0; for (size_t i = 0; i < k->n.w.size(); i++) pn += (uint64_t)__builtin_popcount(k->n.w[i]);
+    *n_sqr = k->n.bits(); *n_mul = pn + k->n_bits / 2 + 1;
+    return PB200_OK;
+}
 int pb200_key_sync(pb200_key* k) {
     if (!k) return PB200_ERR_INVALID_ARG;
     CU(cudaSetDevice(k->device));
