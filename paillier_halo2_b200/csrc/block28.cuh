@@ -197,29 +197,25 @@ __device__ __forceinline__ void load_q1_block(int (&a)[C::CH * 4], const int4* T
 
 // One anti-diagonal job: accumulate its block pairs, ripple, write the Lo digits; Hi digits + spill stay in registers.
 template <class C>
-__device__ __forceinline__ void run_job(Pending<C>& pend, int ph, int d, int i_lo, int i_hi, int mode,
+__device__ __forceinline__ void run_job(Pending<C>& pend, int ph, int d, int i_lo, int i_hi,
                                         const int4* abuf, const int4* bbase, int bblk, int bchunk,
                                         int4* lo_dst, int lo_blk, int lo_op, int lane) {
     long long acc[C::NCOL];
     zero_acc<C>(acc);
+#pragma unroll 1
     for (int i = i_lo; i <= i_hi; i++) {
         int a[C::CH * 4];
         if (ph == PH_HIGH) load_q1_block<C>(a, abuf, i, lane);
         else load_block<C>(a, blk_ptr<C>(abuf, i, lane), 32);
         const int4* bp = bbase + (d - i) * bblk;
-        int m = mode;
-        if (ph == PH_SQR) {
-            if (2 * i == d) m = M_SQ;
-            else {
+        if (ph == PH_SQR && 2 * i == d) {
+            mac_block<C, M_SQ, false>(acc, a, bp, bchunk);
+        } else {
+            if (ph == PH_SQR) {
 #pragma unroll
                 for (int k = 0; k < C::BL; k++) a[k] += a[k];      // off-diagonal pair counted twice
             }
-        }
-        switch (m) {
-            case M_FULL: mac_block<C, M_FULL, false>(acc, a, bp, bchunk); break;
-            case M_LT:   mac_block<C, M_LT, false>(acc, a, bp, bchunk); break;
-            case M_UTG:  mac_block<C, M_UTG, false>(acc, a, bp, bchunk); break;
-            default:     mac_block<C, M_SQ, false>(acc, a, bp, bchunk); break;
+            mac_block<C, M_FULL, false>(acc, a, bp, bchunk);
         }
     }
     int lo[C::CH * 4];
@@ -245,6 +241,14 @@ __device__ __forceinline__ void store_zero_block(int4* buf, int blk, int lane) {
     store_block<C>(blk_ptr<C>(buf, blk, lane), z);
 }
 
+// Which anti-diagonal a warp works on in the truncated phases.  Jobs sorted by size (G, G-1, .., 1 block
+// pairs); warps w and w + G/2 .. share a scheduler (warp id mod 4), so big jobs are paired with small ones
+// per scheduler in each phase, and each warp's sizes over phases B and C add up to G + 1.
+template <class C>
+__device__ __forceinline__ int job_rank(int warp) {     // 0 = largest job
+    return warp < C::G / 2 ? warp : (C::G - 1) - (warp - C::G / 2);
+}
+
 // ph = PH_MUL / PH_SQR : T  = V * Y          (Y = V for PH_SQR)
 // ph = PH_HIGH         : Q  = digits [L,2L) of q1(T) * mu
 // ph = PH_LOW          : V  = lo_L(T) - lo_L(Q * Nt), rippled
@@ -252,61 +256,68 @@ template <class C>
 __device__ __noinline__ void run_phase(int4* smem_base, const int4* Y, int ph) {
     constexpr int G = C::G;
     Smem<C> S(smem_base);
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    Pending<C> p0, p1;
-    p0.blk = -1; p1.blk = -1;
-    // hi_dst/hi_src: buffers of the step-2 read-modify-write; nblk: number of blocks of the result; sign of the Hi part
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Pending<C> pend;
+    pend.blk = -1;
+    int blk0 = -1, spill0 = 0;                      // first job of a two-job phase (its Hi digits are stashed in Q)
+    int4* stash = S.Q + threadIdx.x;                // [chunk][thread], free during phase A
     int4* hi_dst; const int4* hi_src; int nblk, sign;
     if (ph <= PH_SQR) {
-        const int4* Yb = ph == PH_SQR ? S.V : Y;
-        {   // anti-diagonal role: pairs i = 0..role
-            int d = role;
-            int i_hi = ph == PH_SQR ? d / 2 : d;
-            run_job<C>(p0, ph, d, 0, i_hi, M_FULL, S.V, Yb + lane, C::BLK4, 32, S.T, d, 1, lane);
-            p0.blk = d;
+        const int4* Yb = (ph == PH_SQR ? S.V : Y) + lane;
+        const int njobs = warp < G - 1 ? 2 : 1;
+#pragma unroll 1
+        for (int half = 0; half < njobs; half++) {
+            const int d = warp + half * G;          // anti-diagonals warp and warp+G
+            const int i_lo = half ? d - G + 1 : 0;
+            const int i_hi = ph == PH_SQR ? d / 2 : (half ? G - 1 : d);
+            run_job<C>(pend, ph, d, i_lo, i_hi, S.V, Yb, C::BLK4, 32, S.T, d, 1, lane);
+            pend.blk = d;
+            if (half == 0 && njobs == 2) {
+#pragma unroll
+                for (int c = 0; c < C::CH; c++)
+                    stash[c * C::THREADS] = make_int4(pend.hi[4 * c], pend.hi[4 * c + 1], pend.hi[4 * c + 2], pend.hi[4 * c + 3]);
+                blk0 = d; spill0 = pend.spill;
+            }
         }
-        if (role < G - 1) {   // anti-diagonal role+G: pairs i = role+1..G-1
-            int d = role + G;
-            int i_hi = ph == PH_SQR ? d / 2 : G - 1;
-            run_job<C>(p1, ph, d, d - G + 1, i_hi, M_FULL, S.V, Yb + lane, C::BLK4, 32, S.T, d, 1, lane);
-            p1.blk = d;
-        } else {
-            store_zero_block<C>(S.T, 2 * G - 1, lane);      // block 2G-1 has no Lo contribution
-        }
+        if (warp == G - 1) store_zero_block<C>(S.T, 2 * G - 1, lane);      // block 2G-1 has no Lo contribution
         hi_dst = S.T; hi_src = S.T; nblk = 2 * G; sign = 1;
     } else if (ph == PH_HIGH) {
-        if (role < G - 1) {
-            int d = role + G;
-            run_job<C>(p0, ph, d, d - G + 1, G - 1, M_FULL, S.T, S.mu, C::CH, 1, S.Q, d - G, 1, lane);
-            p0.blk = d - G;
-        } else {          // anti-diagonal G-1: only the columns at and above the guard; its Lo part lies below digit L
-            run_job<C>(p0, ph, G - 1, 0, G - 1, M_UTG, S.T, S.mu, C::CH, 1, S.Q, 0, 0, lane);
-            p0.blk = -1;
-            store_zero_block<C>(S.Q, G - 1, lane);          // Q block G-1 has no Lo contribution
+        const int d = G - 1 + job_rank<C>(warp);    // anti-diagonals G-1 .. 2G-2 (G .. 1 block pairs)
+        if (d >= G) {
+            run_job<C>(pend, ph, d, d - G + 1, G - 1, S.T, S.mu, C::CH, 1, S.Q, d - G, 1, lane);
+            pend.blk = d - G;
+        } else {      // anti-diagonal G-1: its Lo part lies below digit L (it only feeds carries upward)
+            run_job<C>(pend, ph, d, 0, G - 1, S.T, S.mu, C::CH, 1, S.Q, 0, 0, lane);
+            pend.blk = -1;
+            store_zero_block<C>(S.Q, G - 1, lane);  // Q block G-1 has no Lo contribution
         }
         hi_dst = S.Q; hi_src = S.Q; nblk = G; sign = 1;
     } else {
-        int d = role;
-        run_job<C>(p0, ph, d, 0, d, role < G - 1 ? M_FULL : M_LT, S.Q, S.Nt, C::CH, 1, S.T, d, 2, lane);
-        p0.blk = d;
-        if (role == G - 1) {       // no Hi below digit L: this role ripples block 0 instead (adds zero)
+        const int d = job_rank<C>(warp);            // anti-diagonals 0 .. G-1 (1 .. G block pairs), reversed pairing
+        const int dd = G - 1 - d;
+        run_job<C>(pend, ph, dd, 0, dd, S.Q, S.Nt, C::CH, 1, S.T, dd, 2, lane);
+        pend.blk = dd;
+        if (dd == G - 1) {         // no Hi below digit L: this warp ripples block 0 instead (adds zero)
 #pragma unroll
-            for (int k = 0; k < C::CH * 4; k++) p0.hi[k] = 0;
-            p0.spill = 0; p0.blk = -1;
+            for (int k = 0; k < C::CH * 4; k++) pend.hi[k] = 0;
+            pend.spill = 0; pend.blk = -1;
         }
         hi_dst = S.V; hi_src = S.T; nblk = G; sign = -1;
     }
     __syncthreads();
     // step 2: Hi digits into block blk+1 with a per-block ripple (phase C also moves the block from T to V)
-    const bool has0 = (ph == PH_HIGH || ph == PH_LOW) ? (p0.blk + 1 <= nblk - 1) : true;
-    if (has0 && p0.blk + 1 <= nblk - 1)
-        p0.carry = add_ripple_block<C>(blk_ptr<C>(hi_dst, p0.blk + 1, lane), blk_ptr<C>(hi_src, p0.blk + 1, lane), p0.hi, sign);
-    if (p1.blk >= 0 && p1.blk + 1 <= nblk - 1)
-        p1.carry = add_ripple_block<C>(blk_ptr<C>(hi_dst, p1.blk + 1, lane), blk_ptr<C>(hi_src, p1.blk + 1, lane), p1.hi, sign);
+    int carry0 = 0;
+    if (blk0 >= 0) {
+        int h0[C::CH * 4];
+        load_block<C>(h0, stash, C::THREADS);
+        carry0 = add_ripple_block<C>(blk_ptr<C>(hi_dst, blk0 + 1, lane), blk_ptr<C>(hi_src, blk0 + 1, lane), h0, sign);
+    }
+    if (pend.blk + 1 <= nblk - 1)
+        pend.carry = add_ripple_block<C>(blk_ptr<C>(hi_dst, pend.blk + 1, lane), blk_ptr<C>(hi_src, pend.blk + 1, lane), pend.hi, sign);
     __syncthreads();
     // step 3: carry of that ripple + the spill digit into digit 0 of block blk+2
-    if (p0.blk + 2 <= nblk - 1) *(int*)blk_ptr<C>(hi_dst, p0.blk + 2, lane) += p0.carry + sign * p0.spill;
-    if (p1.blk >= 0 && p1.blk + 2 <= nblk - 1) *(int*)blk_ptr<C>(hi_dst, p1.blk + 2, lane) += p1.carry + sign * p1.spill;
+    if (blk0 >= 0 && blk0 + 2 <= nblk - 1) *(int*)blk_ptr<C>(hi_dst, blk0 + 2, lane) += carry0 + sign * spill0;
+    if (pend.blk + 2 <= nblk - 1) *(int*)blk_ptr<C>(hi_dst, pend.blk + 2, lane) += pend.carry + sign * pend.spill;
     __syncthreads();
 }
 
