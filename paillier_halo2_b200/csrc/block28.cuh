@@ -261,48 +261,53 @@ __device__ __noinline__ void run_phase(int4* smem_base, const int4* Y, int ph) {
     pend.blk = -1;
     int blk0 = -1, spill0 = 0;                      // first job of a two-job phase (its Hi digits are stashed in Q)
     int4* stash = S.Q + threadIdx.x;                // [chunk][thread], free during phase A
-    int4* hi_dst; const int4* hi_src; int nblk, sign;
+    // per-phase parameters (all warp-uniform); run_job has ONE call site so its unrolled bodies exist once
+    int njobs = 1, nblk = G, sign = 1, bblk = C::CH, bchunk = 1, lo_op = 1;
+    const int4* abuf = S.V; const int4* bbase = S.mu; int4* lo_dst = S.Q;
+    int4* hi_dst = S.Q; const int4* hi_src = S.Q;
+    int d_first = 0;
     if (ph <= PH_SQR) {
-        const int4* Yb = (ph == PH_SQR ? S.V : Y) + lane;
-        const int njobs = warp < G - 1 ? 2 : 1;
-#pragma unroll 1
-        for (int half = 0; half < njobs; half++) {
-            const int d = warp + half * G;          // anti-diagonals warp and warp+G
-            const int i_lo = half ? d - G + 1 : 0;
-            const int i_hi = ph == PH_SQR ? d / 2 : (half ? G - 1 : d);
-            run_job<C>(pend, ph, d, i_lo, i_hi, S.V, Yb, C::BLK4, 32, S.T, d, 1, lane);
-            pend.blk = d;
-            if (half == 0 && njobs == 2) {
-#pragma unroll
-                for (int c = 0; c < C::CH; c++)
-                    stash[c * C::THREADS] = make_int4(pend.hi[4 * c], pend.hi[4 * c + 1], pend.hi[4 * c + 2], pend.hi[4 * c + 3]);
-                blk0 = d; spill0 = pend.spill;
-            }
-        }
-        if (warp == G - 1) store_zero_block<C>(S.T, 2 * G - 1, lane);      // block 2G-1 has no Lo contribution
-        hi_dst = S.T; hi_src = S.T; nblk = 2 * G; sign = 1;
+        njobs = warp < G - 1 ? 2 : 1;
+        abuf = S.V; bbase = (ph == PH_SQR ? S.V : Y) + lane; bblk = C::BLK4; bchunk = 32;
+        lo_dst = S.T; hi_dst = S.T; hi_src = S.T; nblk = 2 * G; d_first = warp;
     } else if (ph == PH_HIGH) {
-        const int d = G - 1 + job_rank<C>(warp);    // anti-diagonals G-1 .. 2G-2 (G .. 1 block pairs)
-        if (d >= G) {
-            run_job<C>(pend, ph, d, d - G + 1, G - 1, S.T, S.mu, C::CH, 1, S.Q, d - G, 1, lane);
-            pend.blk = d - G;
-        } else {      // anti-diagonal G-1: its Lo part lies below digit L (it only feeds carries upward)
-            run_job<C>(pend, ph, d, 0, G - 1, S.T, S.mu, C::CH, 1, S.Q, 0, 0, lane);
-            pend.blk = -1;
-            store_zero_block<C>(S.Q, G - 1, lane);  // Q block G-1 has no Lo contribution
-        }
-        hi_dst = S.Q; hi_src = S.Q; nblk = G; sign = 1;
+        abuf = S.T; bbase = S.mu; d_first = G - 1 + job_rank<C>(warp);      // anti-diagonals G-1 .. 2G-2
     } else {
-        const int d = job_rank<C>(warp);            // anti-diagonals 0 .. G-1 (1 .. G block pairs), reversed pairing
-        const int dd = G - 1 - d;
-        run_job<C>(pend, ph, dd, 0, dd, S.Q, S.Nt, C::CH, 1, S.T, dd, 2, lane);
-        pend.blk = dd;
-        if (dd == G - 1) {         // no Hi below digit L: this warp ripples block 0 instead (adds zero)
-#pragma unroll
-            for (int k = 0; k < C::CH * 4; k++) pend.hi[k] = 0;
-            pend.spill = 0; pend.blk = -1;
+        abuf = S.Q; bbase = S.Nt; lo_dst = S.T; lo_op = 2; d_first = G - 1 - job_rank<C>(warp);   // G-1 .. 0, reversed pairing
+        hi_dst = S.V; hi_src = S.T; sign = -1;
+    }
+#pragma unroll 1
+    for (int half = 0; half < njobs; half++) {
+        const int d = d_first + half * G;
+        int i_lo, i_hi, lo_blk, op = lo_op;
+        if (ph <= PH_SQR) {
+            i_lo = half ? d - G + 1 : 0;
+            i_hi = ph == PH_SQR ? d / 2 : (half ? G - 1 : d);
+            lo_blk = d;
+        } else if (ph == PH_HIGH) {
+            i_lo = d >= G ? d - G + 1 : 0; i_hi = G - 1;
+            lo_blk = d - G;
+            if (d < G) { op = 0; lo_blk = 0; }      // anti-diagonal G-1: its Lo part lies below digit L
+        } else {
+            i_lo = 0; i_hi = d; lo_blk = d;
         }
-        hi_dst = S.V; hi_src = S.T; nblk = G; sign = -1;
+        run_job<C>(pend, ph, d, i_lo, i_hi, abuf, bbase, bblk, bchunk, lo_dst, lo_blk, op, lane);
+        pend.blk = (ph == PH_HIGH && d < G) ? -1 : lo_blk;
+        if (half == 0 && njobs == 2) {
+#pragma unroll
+            for (int c = 0; c < C::CH; c++)
+                stash[c * C::THREADS] = make_int4(pend.hi[4 * c], pend.hi[4 * c + 1], pend.hi[4 * c + 2], pend.hi[4 * c + 3]);
+            blk0 = d; spill0 = pend.spill;
+        }
+    }
+    if (ph <= PH_SQR) {
+        if (warp == G - 1) store_zero_block<C>(S.T, 2 * G - 1, lane);       // block 2G-1 has no Lo contribution
+    } else if (ph == PH_HIGH) {
+        if (pend.blk < 0) store_zero_block<C>(S.Q, G - 1, lane);            // Q block G-1 has no Lo contribution
+    } else if (pend.blk == G - 1) {    // no Hi below digit L: this warp ripples block 0 instead (adds zero)
+#pragma unroll
+        for (int k = 0; k < C::CH * 4; k++) pend.hi[k] = 0;
+        pend.spill = 0; pend.blk = -1;
     }
     __syncthreads();
     // step 2: Hi digits into block blk+1 with a per-block ripple (phase C also moves the block from T to V)
