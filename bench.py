@@ -39,14 +39,15 @@ def mac_counts(n_bits: int):
 
 
 def imad_peak():
-    """P_imad: measured mad.wide MAC/s of this pool's B200 (profiles/imad_peak_r01.json, written by
-    csrc/microbench/imad_peak.cu).  MEASURED_PEAKS.json carries no integer-pipe peak."""
-    path = os.path.join(ROOT, "profiles", "imad_peak_r01.json")
+    """P_imad: measured rate of 32x32->64 multiplies (SASS IMAD.WIDE) on this pool's B200, from
+    profiles/imad_peak2_r01.json (csrc/microbench/imad_peak2.cu, variant imadw_only: 31.9 per clk per SM,
+    half the 32-bit IMAD rate).  MEASURED_PEAKS.json carries no integer-pipe peak."""
+    path = os.path.join(ROOT, "profiles", "imad_peak2_r01.json")
     try:
         d = json.load(open(path))
-        return max(r["mac_per_s"] for r in d["results"] if r["variant"].startswith("wide_indep")), "profiles/imad_peak_r01.json"
+        return max(r["op_per_s"] for r in d["results"] if r["variant"] == "imadw_only"), "profiles/imad_peak2_r01.json (IMAD.WIDE, measured)"
     except Exception:
-        return 148 * 64 * 1.965e9, "nominal 148 SM x 64 IMAD/clk x 1.965 GHz"
+        return 148 * 32 * 1.965e9, "nominal 148 SM x 32 IMAD.WIDE/clk x 1.965 GHz"
 
 
 class ClockSampler:
@@ -151,7 +152,11 @@ def main():
     ap.add_argument("--g", default="rand", choices=["rand", "std"], help="rand: random g (headline); std: g = n+1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--engine", type=int, default=0)
+    ap.add_argument("--n-bits", type=int, default=2048, help="key size |n| (default 2048, the BASELINE metric; others are the sweep)")
     args = ap.parse_args()
+    global N_BITS, METRIC
+    N_BITS = args.n_bits
+    METRIC = f"paillier_enc_per_s_n{N_BITS}"
     if args.impl == "reference":
         return run_reference(args)
 

@@ -44,6 +44,9 @@ struct Cfg {
     // shared memory: V, B, Q (L digits each), T (2L digits), constants mu, Nt, two_sh
     static constexpr int SMEM_INT4 = 5 * VAL4 + 3 * ENTRY4;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_INT4 * 16;
+    // resident CTAs per SM the kernels are compiled for (shared memory and 64K registers / 128 per thread)
+    static constexpr int BY_SMEM = (int)((227 * 1024) / SMEM_BYTES), BY_REGS = 512 / THREADS;
+    static constexpr int CTAS_PER_SM = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
 };
 
 __device__ __forceinline__ int sgxt28(int x) {

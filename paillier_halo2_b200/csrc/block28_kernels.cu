@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_gtable_fill(B28Dev K, const i
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::THREADS, 2) k_encrypt(B28Dev K, const u64* __restrict__ m, const u64* __restrict__ r,
+__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K, const u64* __restrict__ m, const u64* __restrict__ r,
                                                             size_t count, u64* __restrict__ c_out, int4* scratch) {
     extern __shared__ int4 smem[];
     Smem<C> S(smem);
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(C::THREADS, 2) k_encrypt(B28Dev K, const u64* 
 
 // out[b] = product of the inputs assigned to CTA b (lane l of CTA b folds units b*32+l, +stride, ...), canonical
 template <class C>
-__global__ void __launch_bounds__(C::THREADS, 2) k_tally(B28Dev K, const u64* __restrict__ c, size_t count, u64* __restrict__ out) {
+__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, const u64* __restrict__ c, size_t count, u64* __restrict__ out) {
     extern __shared__ int4 smem[];
     Smem<C> S(smem);
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
@@ -415,14 +415,14 @@ static cudaError_t encrypt_cfg(Block28Key* key, const u64* d_m, const u64* d_r, 
 template <class C>
 static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64* d_out, cudaStream_t st) {
     const int wo = key->dev.words_out;
-    size_t cap = (size_t)2 * key->sms + 8;
+    size_t cap = (size_t)C::CTAS_PER_SM * key->sms + 8;
     if (!key->d_partials) {
         cudaError_t e = cudaMalloc(&key->d_partials, cap * wo * sizeof(u64));
         if (e != cudaSuccess) return e;
         key->partials_cap = cap;
     }
     size_t ctas = (count + 31) / 32;
-    if (ctas > (size_t)2 * key->sms) ctas = (size_t)2 * key->sms;
+    if (ctas > (size_t)C::CTAS_PER_SM * key->sms) ctas = (size_t)C::CTAS_PER_SM * key->sms;
     if (ctas <= 1) {
         k_tally<C><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out); count_launch();
         return cudaGetLastError();
@@ -432,13 +432,22 @@ static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64*
     return cudaGetLastError();
 }
 
-typedef Cfg<8, 19> Cfg2048;   // L = 152 digits: n^2 up to 4232 bits (|n| <= 2048 and the reference's default sizes)
+// Compiled configurations <G warps, BL digits per block>: L = G*BL digits of 28 bits; n^2 must fit KN - 2 bits.
+typedef Cfg<4, 19> Cfg1024;    // L =  76: n^2 up to 2102 bits (|n| <= 1024 and the reference's default sizes)
+typedef Cfg<8, 19> Cfg2048;    // L = 152: n^2 up to 4230 bits (|n| <= 2048)
+typedef Cfg<16, 14> Cfg3072;   // L = 224: n^2 up to 6246 bits (|n| <= 3072)
+typedef Cfg<16, 19> Cfg4096;   // L = 304: n^2 up to 8486 bits (|n| <= 4096)
+
+template <class C>
+static bool covers(uint32_t n_bits) { return 2 * (size_t)n_bits <= (size_t)C::KN - 2 && n_bits % 8 == 0; }
 
 Block28Key* block28_create(const BigInt& n, const BigInt& g, uint32_t n_bits, int device, cudaStream_t st,
                            std::string* why, cudaError_t* cuda_err) {
     *cuda_err = cudaSuccess;
-    if (2 * (size_t)n_bits <= (size_t)Cfg2048::KN - 2 && n_bits % 8 == 0)
-        return create_cfg<Cfg2048>(n, g, n_bits, device, st, cuda_err);
+    if (covers<Cfg1024>(n_bits)) return create_cfg<Cfg1024>(n, g, n_bits, device, st, cuda_err);
+    if (covers<Cfg2048>(n_bits)) return create_cfg<Cfg2048>(n, g, n_bits, device, st, cuda_err);
+    if (covers<Cfg3072>(n_bits)) return create_cfg<Cfg3072>(n, g, n_bits, device, st, cuda_err);
+    if (covers<Cfg4096>(n_bits)) return create_cfg<Cfg4096>(n, g, n_bits, device, st, cuda_err);
     if (why) *why = "block28: no compiled configuration covers this key size";
     return nullptr;
 }
@@ -455,10 +464,16 @@ void block28_destroy(Block28Key* key) {
 const char* block28_name(const Block28Key* key) { return key->name.c_str(); }
 void block28_chain_counts(const Block28Key* key, uint64_t* n_sqr, uint64_t* n_mul) { *n_sqr = key->n_sqr; *n_mul = key->n_mul; }
 cudaError_t block28_encrypt(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st) {
-    return encrypt_cfg<Cfg2048>(key, d_m, d_r, count, d_c, st);
+    if (key->G == 4) return encrypt_cfg<Cfg1024>(key, d_m, d_r, count, d_c, st);
+    if (key->G == 8) return encrypt_cfg<Cfg2048>(key, d_m, d_r, count, d_c, st);
+    if (key->BL == 14) return encrypt_cfg<Cfg3072>(key, d_m, d_r, count, d_c, st);
+    return encrypt_cfg<Cfg4096>(key, d_m, d_r, count, d_c, st);
 }
 cudaError_t block28_tally(Block28Key* key, const u64* d_c, size_t count, u64* d_out, cudaStream_t st) {
-    return tally_cfg<Cfg2048>(key, d_c, count, d_out, st);
+    if (key->G == 4) return tally_cfg<Cfg1024>(key, d_c, count, d_out, st);
+    if (key->G == 8) return tally_cfg<Cfg2048>(key, d_c, count, d_out, st);
+    if (key->BL == 14) return tally_cfg<Cfg3072>(key, d_c, count, d_out, st);
+    return tally_cfg<Cfg4096>(key, d_c, count, d_out, st);
 }
 
 }  // namespace pb200

@@ -97,15 +97,17 @@ def test_golden_witness_records_and_digests(built_lib):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("n_bits,count", [(1024, 70), (2048, 45)])
+@pytest.mark.parametrize("n_bits,count", [(1024, 70), (2048, 45), (3072, 33), (4096, 20)])
 def test_seeded_batch_vs_oracle(built_lib, engine, n_bits, count):
     key_d = workload.load_key(n_bits)
     n, g = key_d["n"], key_d["g_rand"]
     m_w, r_w = workload.units(n_bits, count)
     ms, rs = words_to_ints(m_w), words_to_ints(r_w)
+    if engine == 1 and n_bits > 2048:
+        count = 4   # the thread-per-ciphertext engine is slow at these sizes; keep the GPU suite short
     with _key(n, g, n_bits, 64, engine) as key:
-        got = words_to_ints(key.encrypt_words(m_w, r_w))
-    assert got == [paillier_enc_native(n, g, m, r) for m, r in zip(ms, rs)]
+        got = words_to_ints(key.encrypt_words(m_w[:count], r_w[:count]))
+    assert got == [paillier_enc_native(n, g, m, r) for m, r in zip(ms[:count], rs[:count])]
 
 
 @pytest.mark.parametrize("engine", ENGINES)
