@@ -142,6 +142,73 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_tally(args):
+    """BASELINE.json configs[2]: product of 2^20 ciphertexts mod n^2, sharded over the GPUs with one all-gather of
+    the per-GPU partials (NCCL) and a final combine.  Strong scaling (total work fixed)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from paillier_halo2_b200 import PaillierKey, _lib, workload
+    from paillier_halo2_b200.shard import shard_range, tally_sharded_gpu
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    kd = workload.load_key(N_BITS)
+    total = 1 << 20
+    key = PaillierKey(kd["n"], kd["g_std"], N_BITS, 64, device=local_rank)
+    lo, hi = shard_range(total, rank, world)
+    c_all = workload.ciphertexts(N_BITS, total, kd["n"]) if total <= (1 << 20) else None
+    d_c = torch.from_numpy(c_all[lo:hi].view(np.int64)).cuda()
+    stream = torch.cuda.ExternalStream(key.stream, device=torch.device("cuda", local_rank))
+    partial = torch.empty(key.words_out, dtype=torch.int64, device="cuda")
+    for _ in range(args.warmup):
+        out = tally_sharded_gpu(key, d_c, hi - lo, world)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = lib.pb200_kernel_launches()
+    kern_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); key.tally_dev(d_c.data_ptr(), hi - lo, partial.data_ptr()); e1.record(stream)
+        key.sync(); kern_ms += e0.elapsed_time(e1)
+        out = tally_sharded_gpu(key, d_c, hi - lo, world)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches = lib.pb200_kernel_launches() - launches0
+    t = torch.tensor([dt, kern_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt, kern_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        from oracle import cpu_ref
+        want = cpu_ref.tally(kd["n"], N_BITS // 64, c_all, threads=cpu_ref.hardware_threads())
+        ok = bool((out.cpu().numpy().view(np.uint64) == want).all())
+        w_mul, _ = mac_counts(N_BITS)
+        peak, src = imad_peak()
+        shard = hi - lo
+        ksec = kern_ms * 1e-3 / args.steps
+        line = {"metric": f"paillier_tally_ciphertexts_per_s_n{N_BITS}", "value": total * 2 * args.steps / dt, "unit": "ciphertexts/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / (2 * args.steps),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64 accumulators over signed 28-bit digits",
+                "data": "synthetic", "config": {"workload": f"product of 2^20 ciphertexts mod n^2, |n|={N_BITS}, sharded over {world} GPU(s), "
+                                                            "NCCL all-gather of partials + combine (BASELINE.json configs[2])", "engine": key.engine},
+                "gpu_launches": int(launches), "parity_vs_cpu_fold": ok,
+                "roofline": {"bound": "imad", "achieved": shard * w_mul / ksec / 1e12, "peak": peak / 1e12, "unit": "TMAC/s",
+                             "frac": shard * w_mul / ksec / peak, "peak_source": src,
+                             "hbm_gbs_achieved": shard * key.words_out * 8 / ksec / 1e9,
+                             "note": "per-GPU shard fold kernel (k_tally x2 launches); one modmul per 512 B read: compute-bound, HBM GB/s reported because north_star asks for it"}}
+        print(json.dumps(line), flush=True)
+    key.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,12 +220,16 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--engine", type=int, default=0)
     ap.add_argument("--n-bits", type=int, default=2048, help="key size |n| (default 2048, the BASELINE metric; others are the sweep)")
+    ap.add_argument("--workload", default="encrypt", choices=["encrypt", "tally"],
+                    help="encrypt: the BASELINE metric (default); tally: product of 2^20 ciphertexts sharded over the GPUs (configs[2])")
     args = ap.parse_args()
     global N_BITS, METRIC
     N_BITS = args.n_bits
     METRIC = f"paillier_enc_per_s_n{N_BITS}"
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "tally":
+        return run_tally(args)
 
     import numpy as np
     import torch

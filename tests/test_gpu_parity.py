@@ -156,3 +156,19 @@ def test_repack_limbs_88(built_lib):
         got = key.repack_limbs(vals, 528, 88)
     from oracle.paillier_oracle import decompose
     assert got == [decompose(v, 6, 88) for v in vals]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_tally_sharded_single_gpu(built_lib, engine):
+    """The multi-GPU tally path (shard -> per-shard partial -> combine) emulated on one GPU: 4 shards folded
+    separately, partials combined with pb200_tally_combine; must equal the oracle fold and the 1-shard result."""
+    from paillier_halo2_b200.shard import shard_range
+    n_bits = 2048
+    kd = workload.load_key(n_bits)
+    n = kd["n"]
+    c_w = workload.ciphertexts(n_bits, 1500, n)
+    want = tally_native(n, words_to_ints(c_w))
+    with _key(n, n + 1, n_bits, 64, engine) as key:
+        partials = np.stack([key.tally_words(c_w[slice(*shard_range(len(c_w), r, 4))]) for r in range(4)])
+        assert words_to_ints(key.tally_combine_words(partials))[0] == want
+        assert words_to_ints(key.tally_words(c_w))[0] == want
