@@ -76,7 +76,8 @@ int pb200_key_n2(const pb200_key* key, uint64_t* n2_out);
 /* name of the arithmetic engine selected for this key size, e.g. "block28<8,19>" or "simple64" */
 const char* pb200_key_engine(const pb200_key* key);
 /* choose the engine explicitly: 0 = automatic (fastest available), 1 = simple64 (thread per
- * ciphertext, always available, used as the on-GPU cross-check), 2 = block28 (warp-role Barrett) */
+ * ciphertext, always available, used as the on-GPU cross-check), 2 = block28 (warp-role Barrett, all
+ * products on the IMAD pipe), 3 = block28t (same, constant-operand Barrett phases on the tensor pipe) */
 int pb200_key_set_engine(pb200_key* key, int engine);
 void* pb200_key_stream(const pb200_key* key);        /* cudaStream_t the key enqueues on */
 /* modular squarings and multiplications the selected engine executes per encryption (the chain the

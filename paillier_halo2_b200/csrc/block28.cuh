@@ -41,8 +41,18 @@ struct Cfg {
     static constexpr int KN = BETA - MARGIN;            // bit length of Nt
     static constexpr int THREADS = 32 * G_;
     static constexpr int ENTRY4 = G_ * CH;              // int4 per value in global tables (one lane)
-    // shared memory: V, B, Q (L digits each), T (2L digits), constants mu, Nt, two_sh
-    static constexpr int SMEM_INT4 = 5 * VAL4 + 3 * ENTRY4;
+    // IMMA variant of the constant-operand phases: numbers as signed 7-bit digits (4 per 28-bit digit)
+    static constexpr int K7 = 4 * L;                                  // s8 digits per number
+    static constexpr int KSTEPS = (K7 + 31) / 32;                     // k-steps of mma.m16n8k32
+    static constexpr bool HALF_LAST = (K7 % 32) != 0;                 // last k-step only half populated (K7 % 32 == 16)
+    static constexpr int RS = K7 + ((((K7 / 4) % 8) == 4) ? 0 : ((4 - ((K7 / 4) % 8) + 8) % 8) * 4);   // row stride, (RS/4) % 8 == 4
+    static constexpr int PAD7 = 48;
+    static constexpr int XLEN = K7 + 2 * PAD7;                        // reversed constant table, zero padded
+    static constexpr int RTAB4 = (4 * XLEN + 15) / 16;                // int4 per constant (4 byte-shifted copies)
+    static constexpr int NP_HIGH = (L + 2 + 3) / 4, NP_LOW = (L + 3) / 4;   // tile pairs (4 digits each) per phase
+    static constexpr int NPW = (NP_HIGH + G_ - 1) / G_;               // tile pairs per warp
+    // shared memory: V, B, Q (L digits each), T (2L digits), constants mu, Nt, two_sh, reversed s8 tables of mu, Nt
+    static constexpr int SMEM_INT4 = 5 * VAL4 + 3 * ENTRY4 + 2 * RTAB4;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_INT4 * 16;
     // resident CTAs per SM the kernels are compiled for (shared memory and 64K registers / 128 per thread)
     static constexpr int BY_SMEM = (int)((227 * 1024) / SMEM_BYTES), BY_REGS = 512 / THREADS;
@@ -166,10 +176,12 @@ struct Pending {
 template <class C>
 struct Smem {
     int4* V; int4* B; int4* Q; int4* T; const int4* mu; const int4* Nt; const int4* two_sh;   // V must stay first
+    const char* rmu; const char* rnt;      // reversed, byte-shifted s8 tables of mu and Nt (IMMA phases)
     __device__ __forceinline__ Smem(int4* base) {
         V = base; B = V + C::VAL4; Q = B + C::VAL4; T = Q + C::VAL4;
         int4* k = T + 2 * C::VAL4;
         mu = k; Nt = k + C::ENTRY4; two_sh = k + 2 * C::ENTRY4;
+        rmu = (const char*)(k + 3 * C::ENTRY4); rnt = (const char*)(k + 3 * C::ENTRY4 + C::RTAB4);
     }
 };
 
@@ -329,13 +341,210 @@ __device__ __noinline__ void run_phase(int4* smem_base, const int4* Y, int ph) {
     __syncthreads();
 }
 
+// ---- IMMA variant of phases B and C ------------------------------------------------------------------
+// Both multiply a per-lane number by a per-key constant: over the 32 lanes of the CTA that is a GEMM
+//   C[lane][p] = sum_k A7[lane][k] * K7[p - k]          (A7, K7: signed 7-bit digits, 4 per 28-bit digit)
+// run on the tensor pipe with mma.sync.m16n8k32.s8 (measured 1880 MAC/clk/SM, profiles/imma_peak_r01.json,
+// against 26 MAC/clk/SM for the IMAD inner loop).  The Toeplitz operand is never materialised: a B fragment is
+// four consecutive bytes of the REVERSED constant, read from one of four byte-shifted copies so every read is
+// an aligned 32-bit word.  The s32 columns are folded back into 28-bit digits (lo + carry into the next digit).
+__device__ __forceinline__ void mma_s8(int (&d)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ int sgxt7(int x) { int r; asm("bfe.s32 %0, %1, 0, 7;" : "=r"(r) : "r"(x)); return r; }
+// one 28-bit digit -> four signed 7-bit digits packed in a word (the top one absorbs the remainder, |.| <= 65)
+__device__ __forceinline__ unsigned split7_pack(int d) {
+    int e0 = sgxt7(d); d = (d - e0) >> 7;
+    int e1 = sgxt7(d); d = (d - e1) >> 7;
+    int e2 = sgxt7(d); d = (d - e2) >> 7;
+    return (unsigned)(e0 & 255) | ((unsigned)(e1 & 255) << 8) | ((unsigned)(e2 & 255) << 16) | ((unsigned)d << 24);
+}
+
+// A-operand bytes live in the Q buffer: As[lane][RS]; output arrays LO (in T blocks G..2G-1) and CA (in B): [digit][lane]
+template <class C> __device__ __forceinline__ char* as_ptr(Smem<C>& S) { return (char*)S.Q; }
+template <class C> __device__ __forceinline__ int* lo_ptr(Smem<C>& S) { return (int*)(S.T + C::VAL4); }
+template <class C> __device__ __forceinline__ int* ca_ptr(Smem<C>& S) { return (int*)S.B; }
+
+// C[lane][p] for the tile pairs of this warp, p = p_base + 16*U + ...; folded: LO[jj] / CA[jj+1], jj = 4U + t
+template <class C, bool HIGH>
+__device__ __noinline__ void phase_mma(int4* smem_base) {
+    constexpr int G = C::G, L = C::L, K7 = C::K7;
+    Smem<C> S(smem_base);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int P_BASE = HIGH ? 4 * (L - 2) : 0;
+    constexpr int NP = HIGH ? C::NP_HIGH : C::NP_LOW;
+    constexpr int NOUT = HIGH ? L + 2 : L;
+    const char* As = as_ptr<C>(S);
+    const char* rtab = HIGH ? S.rmu : S.rnt;
+    int acc[C::NPW][2][2][4];       // [pair][tile h][m-tile][c0..c3]
+#pragma unroll
+    for (int q = 0; q < C::NPW; q++)
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[q][h][mt][i] = 0;
+    // B-fragment base pointers: column n = g of tile h of pair U is p = P_BASE + 16U + 4(g>>1) + (g&1) + 2h
+    const char* bptr[C::NPW][2];
+#pragma unroll
+    for (int q = 0; q < C::NPW; q++) {
+        const int U = warp + q * G;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int p = P_BASE + 16 * U + 4 * (g >> 1) + (g & 1) + 2 * h;
+            const int idx0 = C::PAD7 + K7 - 1 - p + 4 * t;       // + 32*ks: index of the first of 4 ascending bytes
+            const int sft = idx0 & 3;
+            bptr[q][h] = rtab + sft * C::XLEN + (idx0 - sft);
+        }
+    }
+    const char* arow = As + g * C::RS + 4 * t;
+#pragma unroll 1
+    for (int ks = 0; ks < C::KSTEPS; ks++) {
+        unsigned a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            const char* ap = arow + mt * 16 * C::RS + 32 * ks;
+            a[mt][0] = *(const unsigned*)(ap);
+            a[mt][1] = *(const unsigned*)(ap + 8 * C::RS);
+            a[mt][2] = *(const unsigned*)(ap + 16);
+            a[mt][3] = *(const unsigned*)(ap + 8 * C::RS + 16);
+            if (C::HALF_LAST && ks == C::KSTEPS - 1) { a[mt][2] = 0; a[mt][3] = 0; }
+        }
+#pragma unroll
+        for (int q = 0; q < C::NPW; q++) {
+            const int U = warp + q * G;
+            const int P0 = P_BASE + 16 * U;                     // pair covers columns [P0, P0+16)
+            // some (k, p) of this k-step x pair has 0 <= p - k <= K7-1 ?
+            const bool valid = U < NP && (P0 + 15 - 32 * ks >= 0) && (P0 - (32 * ks + 31) <= K7 - 1);
+            if (valid) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const unsigned b0 = *(const unsigned*)(bptr[q][h] + 32 * ks);
+                    const unsigned b1 = *(const unsigned*)(bptr[q][h] + 32 * ks + 16);
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) mma_s8(acc[q][h][mt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+                }
+            }
+        }
+    }
+    // fold: thread (g, t) owns the 4 radix-2^7 columns of digit jj = 4U + t for rows g, g+8 of each m-tile
+    int* LO = lo_ptr<C>(S);
+    int* CA = ca_ptr<C>(S);
+#pragma unroll
+    for (int q = 0; q < C::NPW; q++) {
+        const int U = warp + q * G;
+        const int jj = 4 * U + t;
+        if (U < NP && jj < NOUT) {
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    long long v = (long long)acc[q][0][mt][2 * r] + ((long long)acc[q][0][mt][2 * r + 1] << 7)
+                                + ((long long)acc[q][1][mt][2 * r] << 14) + ((long long)acc[q][1][mt][2 * r + 1] << 21);
+                    int lo = sgxt28((int)v);
+                    int ca = (int)((v - lo) >> W);
+                    const int m = 16 * mt + g + 8 * r;
+                    LO[jj * 32 + m] = lo;
+                    CA[(jj + 1) * 32 + m] = ca;
+                }
+        }
+    }
+    __syncthreads();
+}
+
+// q1 (T digits [L-1, 2L-1)) -> s8 rows in As.  One (block = warp, lane) per thread.
+template <class C>
+__device__ __forceinline__ void q1_to_bytes(Smem<C>& S, int warp, int lane) {
+    int a[C::CH * 4];
+    load_q1_block<C>(a, S.T, warp, lane);
+    unsigned* row = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + warp * C::BL;
+#pragma unroll
+    for (int k = 0; k < C::BL; k++) row[k] = split7_pack(a[k]);
+    if (C::K7 < C::KSTEPS * 32 && warp == C::G - 1) {           // zero the tail of a half populated last k-step
+        unsigned* tail = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + C::L;
+#pragma unroll
+        for (int k = 0; k < (C::KSTEPS * 32 - C::K7) / 4; k++) if (4 * (C::L + k) < C::RS) tail[k] = 0;
+    }
+    __syncthreads();
+}
+
+// phase B tail: ripple LO/CA (digits jj = j + 2, two guard digits) into strict q-hat digits, as s8 rows in As
+template <class C>
+__device__ __forceinline__ void qhat_to_bytes(Smem<C>& S, int warp, int lane) {
+    const int* LO = lo_ptr<C>(S);
+    const int* CA = ca_ptr<C>(S);
+    int carry = 0;
+    if (warp == 0) {      // the guard digits only feed their carry into digit 0
+        int t0 = LO[0 * 32 + lane];
+        carry = (t0 - sgxt28(t0)) >> W;
+        int t1 = LO[1 * 32 + lane] + CA[1 * 32 + lane] + carry;
+        carry = (t1 - sgxt28(t1)) >> W;
+    }
+    unsigned w[C::BL];
+#pragma unroll
+    for (int k = 0; k < C::BL; k++) {
+        const int jj = warp * C::BL + k + 2;
+        int tt = LO[jj * 32 + lane] + CA[jj * 32 + lane] + carry;
+        int d = sgxt28(tt);
+        carry = (tt - d) >> W;
+        w[k] = split7_pack(d);
+    }
+    __syncthreads();                                              // every warp has read LO/CA of its block
+    unsigned* row = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + warp * C::BL;
+#pragma unroll
+    for (int k = 0; k < C::BL; k++) row[k] = w[k];
+    __syncthreads();
+    if (warp + 1 < C::G) {                                        // carry out of this block into the lowest 7-bit digit of the next
+        unsigned* nx = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + (warp + 1) * C::BL;
+        unsigned v = *nx;
+        int e0 = (int)(signed char)(v & 255) + carry;
+        *nx = (v & ~255u) | ((unsigned)e0 & 255u);
+    }
+    __syncthreads();
+}
+
+// phase C tail: V block = ripple(T_lo block - LO - CA), carry into digit 0 of the next block
+template <class C>
+__device__ __forceinline__ void low_to_value(Smem<C>& S, int warp, int lane) {
+    const int* LO = lo_ptr<C>(S);
+    const int* CA = ca_ptr<C>(S);
+    int a[C::CH * 4];
+    load_block<C>(a, blk_ptr<C>(S.T, warp, lane), 32);
+    int carry = 0;
+#pragma unroll
+    for (int k = 0; k < C::BL; k++) {
+        const int j = warp * C::BL + k;
+        int tt = a[k] - LO[j * 32 + lane] - (j > 0 ? CA[j * 32 + lane] : 0) + carry;
+        int d = sgxt28(tt);
+        carry = (tt - d) >> W;
+        a[k] = d;
+    }
+#pragma unroll
+    for (int k = C::BL; k < C::CH * 4; k++) a[k] = 0;
+    store_block<C>(blk_ptr<C>(S.V, warp, lane), a);
+    __syncthreads();
+    if (warp + 1 < C::G) *(int*)blk_ptr<C>(S.V, warp + 1, lane) += carry;
+    __syncthreads();
+}
+
 // V <- V * Y mod Nt (lazy).  SQR: Y ignored, V <- V^2.
-template <class C, bool SQR>
+template <class C, bool SQR, bool MMA = false>
 __device__ __forceinline__ void mulmod(Smem<C>& S, const int4* Y, int role, int lane) {
     int4* base = S.V;
     run_phase<C>(base, Y, SQR ? PH_SQR : PH_MUL);
-    run_phase<C>(base, nullptr, PH_HIGH);
-    run_phase<C>(base, nullptr, PH_LOW);
+    if (!MMA) {
+        run_phase<C>(base, nullptr, PH_HIGH);
+        run_phase<C>(base, nullptr, PH_LOW);
+    } else {
+        q1_to_bytes<C>(S, role, lane);
+        phase_mma<C, true>(base);
+        qhat_to_bytes<C>(S, role, lane);
+        phase_mma<C, false>(base);
+        low_to_value<C>(S, role, lane);
+    }
 }
 
 }  // namespace b28

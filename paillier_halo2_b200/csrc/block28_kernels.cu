@@ -11,6 +11,7 @@
 #include "engine.hpp"
 #include "block28.cuh"
 #include <vector>
+#include <cstring>
 
 namespace pb200 {
 using namespace b28;
@@ -101,18 +102,18 @@ __device__ __forceinline__ void scatter_entry(int4* entry, const int4* buf, int 
 template <class C>
 __device__ __forceinline__ void load_consts(int4* smem_base, const B28Dev& K) {
     int4* k = smem_base + 5 * C::VAL4;
-    for (int i = threadIdx.x; i < 3 * C::ENTRY4; i += C::THREADS) k[i] = K.consts[i];
+    for (int i = threadIdx.x; i < 3 * C::ENTRY4 + 2 * C::RTAB4; i += C::THREADS) k[i] = K.consts[i];
     __syncthreads();
 }
 
 // V <- V * (constant in shared memory, ENTRY4 int4, broadcast)
-template <class C>
+template <class C, bool MMA>
 __device__ __forceinline__ void mulmod_const(Smem<C>& S, const int4* cst, int role, int lane) {
     // expand the constant into the per-lane B buffer (keeps phase_product on one code path)
 #pragma unroll
     for (int c = 0; c < C::CH; c++) S.B[(role * C::CH + c) * 32 + lane] = cst[role * C::CH + c];
     __syncthreads();
-    mulmod<C, false>(S, S.B, role, lane);
+    mulmod<C, false, MMA>(S, S.B, role, lane);
 }
 
 // Exact canonicalisation of the lazy value in V (one thread per lane, role 0): out = ((V * 2^sh) mod Nt) >> sh,
@@ -169,9 +170,9 @@ __device__ void canonical_out(int4* V, const int4* NtC, const B28Dev& K, u64* ou
     }
 }
 
-template <class C>
+template <class C, bool MMA>
 __device__ __forceinline__ void finalize(Smem<C>& S, const B28Dev& K, u64* out, bool active, int role, int lane) {
-    mulmod_const<C>(S, S.two_sh, role, lane);
+    mulmod_const<C, MMA>(S, S.two_sh, role, lane);
     if (role == 0 && active) canonical_out<C>(S.V, S.Nt, K, out, lane);
     __syncthreads();
 }
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_gtable_fill(B28Dev K, const i
     }
 }
 
-template <class C>
+template <class C, bool MMA>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K, const u64* __restrict__ m, const u64* __restrict__ r,
                                                             size_t count, u64* __restrict__ c_out, int4* scratch) {
     extern __shared__ int4 smem[];
@@ -228,23 +229,23 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K
     // ---- r^n: odd powers table, then the per-key window schedule
     load_value<C>(S.V, r + unit * K.words_in, K.words_in, role, lane);
     copy_to_global<C>(tab, S.V, role, lane);                                   // tab[0] = r
-    mulmod<C, true>(S, nullptr, role, lane);                                   // r^2
+    mulmod<C, true, MMA>(S, nullptr, role, lane);                                   // r^2
     copy_to_global<C>(tab + (size_t)TABN * C::VAL4, S.V, role, lane);
     __syncthreads();
     copy_from_global<C>(S.V, tab, role, lane);
     for (int j = 1; j < TABN; j++) {
         copy_from_global<C>(S.B, tab + (size_t)TABN * C::VAL4, role, lane);
-        mulmod<C, false>(S, S.B, role, lane);                                  // r^(2j+1)
+        mulmod<C, false, MMA>(S, S.B, role, lane);                                  // r^(2j+1)
         copy_to_global<C>(tab + (size_t)j * C::VAL4, S.V, role, lane);
     }
     __syncthreads();
     copy_from_global<C>(S.V, tab + (size_t)K.first_idx * C::VAL4, role, lane);
     for (int o = 0; o < K.n_ops; o++) {
         int2 op = K.ops[o];
-        for (int s = 0; s < op.x; s++) mulmod<C, true>(S, nullptr, role, lane);
+        for (int s = 0; s < op.x; s++) mulmod<C, true, MMA>(S, nullptr, role, lane);
         if (op.y >= 0) {
             copy_from_global<C>(S.B, tab + (size_t)op.y * C::VAL4, role, lane);
-            mulmod<C, false>(S, S.B, role, lane);
+            mulmod<C, false, MMA>(S, S.B, role, lane);
         }
     }
     copy_to_global<C>(tab + (size_t)(TABN + 1) * C::VAL4, S.V, role, lane);    // rn
@@ -258,16 +259,16 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K
     for (int i = 1; i < K.n_windows; i++) {
         int d = (int)((mw[i >> 3] >> (8 * (i & 7))) & 255);
         gather_entry<C>(S.B, K.tg + ((size_t)i * 256 + d) * C::ENTRY4, role, lane);
-        mulmod<C, false>(S, S.B, role, lane);
+        mulmod<C, false, MMA>(S, S.B, role, lane);
     }
     // ---- c = gm * rn, canonical
     copy_from_global<C>(S.B, tab + (size_t)(TABN + 1) * C::VAL4, role, lane);
-    mulmod<C, false>(S, S.B, role, lane);
-    finalize<C>(S, K, c_out + unit * K.words_out, active, role, lane);
+    mulmod<C, false, MMA>(S, S.B, role, lane);
+    finalize<C, MMA>(S, K, c_out + unit * K.words_out, active, role, lane);
 }
 
 // out[b] = product of the inputs assigned to CTA b (lane l of CTA b folds units b*32+l, +stride, ...), canonical
-template <class C>
+template <class C, bool MMA>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, const u64* __restrict__ c, size_t count, u64* __restrict__ out) {
     extern __shared__ int4 smem[];
     Smem<C> S(smem);
@@ -289,16 +290,16 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, 
             store_block<C>(blk_ptr<C>(S.B, role, lane), a);
         }
         __syncthreads();
-        mulmod<C, false>(S, S.B, role, lane);
+        mulmod<C, false, MMA>(S, S.B, role, lane);
     }
     // fold the 32 lanes: B[lane] = V[lane ^ off]
     for (int off = 16; off >= 1; off >>= 1) {
 #pragma unroll
         for (int ch = 0; ch < C::CH; ch++) S.B[(role * C::CH + ch) * 32 + lane] = S.V[(role * C::CH + ch) * 32 + (lane ^ off)];
         __syncthreads();
-        mulmod<C, false>(S, S.B, role, lane);
+        mulmod<C, false, MMA>(S, S.B, role, lane);
     }
-    finalize<C>(S, K, out + (size_t)blockIdx.x * K.words_out, lane == 0, role, lane);
+    finalize<C, MMA>(S, K, out + (size_t)blockIdx.x * K.words_out, lane == 0, role, lane);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -311,6 +312,7 @@ struct Block28Key {
     u64* d_partials = nullptr; size_t partials_cap = 0;
     int sms = 148;
     uint64_t n_sqr = 0, n_mul = 0;   // modular squarings / multiplications per encryption
+    bool use_mma = true;             // constant-operand phases on the tensor pipe (engine 3) or on IMAD (engine 2)
 };
 
 template <class C>
@@ -326,13 +328,32 @@ static void to_entry(const BigInt& v, std::vector<int>& out) {   // centred digi
     if (carry != 0 || v.bits() > (size_t)W * C::L - 1) throw std::runtime_error("block28: constant does not fit");
 }
 
+// reversed, zero padded, byte-shifted s8 table of a constant's 7-bit digits (B operand of the IMMA phases)
+template <class C>
+static void to_rtab(const std::vector<int>& entry, std::vector<int>& out_words) {
+    std::vector<signed char> k7(C::K7, 0);
+    for (int p = 0; p < C::L; p++) {
+        int d = entry[(p / C::BL) * C::CH * 4 + (p % C::BL)];
+        for (int i = 0; i < 3; i++) { int e = ((d + 64) & 127) - 64; k7[4 * p + i] = (signed char)e; d = (d - e) >> 7; }
+        if (d < -128 || d > 127) throw std::runtime_error("block28: constant digit does not split into s8");
+        k7[4 * p + 3] = (signed char)d;
+    }
+    std::vector<signed char> rfull(C::XLEN + 8, 0);
+    for (int j = 0; j < C::K7; j++) rfull[C::PAD7 + (C::K7 - 1 - j)] = k7[j];
+    std::vector<signed char> tab((size_t)C::RTAB4 * 16, 0);
+    for (int sft = 0; sft < 4; sft++)
+        for (int x = 0; x < C::XLEN; x++) tab[(size_t)sft * C::XLEN + x] = x + sft < C::XLEN ? rfull[x + sft] : 0;
+    out_words.resize((size_t)C::RTAB4 * 4);
+    memcpy(out_words.data(), tab.data(), tab.size());
+}
+
 #define CUK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { *cuda_err = e_; block28_destroy(key); return nullptr; } } while (0)
 
 template <class C>
 static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits, int device, cudaStream_t st, cudaError_t* cuda_err) {
     Block28Key* key = new Block28Key();
     key->G = C::G; key->BL = C::BL;
-    key->name = "block28<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">";
+    key->name = "block28t<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">";
     cudaDeviceProp prop;
     CUK(cudaGetDeviceProperties(&prop, device));
     key->sms = prop.multiProcessorCount;
@@ -346,6 +367,10 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     all.insert(all.end(), e_mu.begin(), e_mu.end());
     all.insert(all.end(), e_nt.begin(), e_nt.end());
     all.insert(all.end(), e_sh.begin(), e_sh.end());
+    std::vector<int> r_mu, r_nt;
+    to_rtab<C>(e_mu, r_mu); to_rtab<C>(e_nt, r_nt);
+    all.insert(all.end(), r_mu.begin(), r_mu.end());
+    all.insert(all.end(), r_nt.begin(), r_nt.end());
     CUK(cudaMalloc(&key->d_consts, all.size() * sizeof(int)));
     CUK(cudaMemcpyAsync(key->d_consts, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     // sliding-window schedule for the exponent n
@@ -384,8 +409,10 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     // comb table
     CUK(cudaFuncSetAttribute(k_gtable_bases<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     CUK(cudaFuncSetAttribute(k_gtable_fill<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    CUK(cudaFuncSetAttribute(k_encrypt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    CUK(cudaFuncSetAttribute(k_tally<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    CUK((cudaFuncSetAttribute(k_encrypt<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    CUK((cudaFuncSetAttribute(k_encrypt<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    CUK((cudaFuncSetAttribute(k_tally<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    CUK((cudaFuncSetAttribute(k_tally<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
     int4* d_bases = nullptr;
     CUK(cudaMalloc(&d_bases, (size_t)n_windows * C::ENTRY4 * sizeof(int4)));
     k_gtable_bases<C><<<1, C::THREADS, C::SMEM_BYTES, st>>>(K, key->d_gwords, d_bases); count_launch();
@@ -407,7 +434,8 @@ static cudaError_t encrypt_cfg(Block28Key* key, const u64* d_m, const u64* d_r, 
         if (e != cudaSuccess) return e;
         key->scratch_ctas = ctas;
     }
-    k_encrypt<C><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch);
+    if (key->use_mma) k_encrypt<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch);
+    else k_encrypt<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch);
     count_launch();
     return cudaGetLastError();
 }
@@ -424,11 +452,19 @@ static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64*
     size_t ctas = (count + 31) / 32;
     if (ctas > (size_t)C::CTAS_PER_SM * key->sms) ctas = (size_t)C::CTAS_PER_SM * key->sms;
     if (ctas <= 1) {
-        k_tally<C><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out); count_launch();
+        if (key->use_mma) k_tally<C, true><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out);
+        else k_tally<C, false><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out);
+        count_launch();
         return cudaGetLastError();
     }
-    k_tally<C><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, key->d_partials); count_launch();
-    k_tally<C><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->d_partials, ctas, d_out); count_launch();
+    if (key->use_mma) {
+        k_tally<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, key->d_partials);
+        k_tally<C, true><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->d_partials, ctas, d_out);
+    } else {
+        k_tally<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, key->d_partials);
+        k_tally<C, false><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->d_partials, ctas, d_out);
+    }
+    count_launch(2);
     return cudaGetLastError();
 }
 
@@ -462,6 +498,10 @@ void block28_destroy(Block28Key* key) {
     delete key;
 }
 const char* block28_name(const Block28Key* key) { return key->name.c_str(); }
+void block28_set_mma(Block28Key* key, bool on) {
+    key->use_mma = on;
+    key->name = std::string(on ? "block28t<" : "block28<") + std::to_string(key->G) + "," + std::to_string(key->BL) + ">";
+}
 void block28_chain_counts(const Block28Key* key, uint64_t* n_sqr, uint64_t* n_mul) { *n_sqr = key->n_sqr; *n_mul = key->n_mul; }
 cudaError_t block28_encrypt(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st) {
     if (key->G == 4) return encrypt_cfg<Cfg1024>(key, d_m, d_r, count, d_c, st);

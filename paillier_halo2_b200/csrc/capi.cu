@@ -148,9 +148,10 @@ const char* pb200_key_engine(const pb200_key* k) {
     return use_fast(k) ? k->engine_name.c_str() : "simple64";
 }
 int pb200_key_set_engine(pb200_key* k, int engine) {
-    if (!k || engine < 0 || engine > 2) return PB200_ERR_INVALID_ARG;
-    if (engine == 2 && !k->fast) return PB200_ERR_UNSUPPORTED;
+    if (!k || engine < 0 || engine > 3) return PB200_ERR_INVALID_ARG;
+    if (engine >= 2 && !k->fast) return PB200_ERR_UNSUPPORTED;
     k->engine = engine;
+    if (k->fast) { block28_set_mma(k->fast, engine != 2); k->engine_name = block28_name(k->fast); }
     return PB200_OK;
 }
 void* pb200_key_stream(const pb200_key* k) { return k ? (void*)k->stream : nullptr; }

@@ -35,6 +35,7 @@ Block28Key* block28_create(const BigInt& n, const BigInt& g, uint32_t n_bits, in
                            std::string* why, cudaError_t* cuda_err);
 void block28_destroy(Block28Key*);
 const char* block28_name(const Block28Key*);
+void block28_set_mma(Block28Key*, bool on);   // constant-operand phases on the tensor pipe (IMMA) or on IMAD
 void block28_chain_counts(const Block28Key*, uint64_t* n_sqr, uint64_t* n_mul);
 cudaError_t block28_encrypt(Block28Key*, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st);
 cudaError_t block28_tally(Block28Key*, const u64* d_c, size_t count, u64* d_out, cudaStream_t st);

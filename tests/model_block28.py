@@ -224,3 +224,81 @@ def canonical(P, keyc, R, N):
     v %= Nt
     assert v % (1 << sh) == 0
     return v >> sh
+
+
+# ---------------------------------------------------------------------------------------------
+# IMMA variant of phases B and C: each signed 28-bit digit splits carry-free into four signed 7-bit digits
+# (s8 operands of mma.sync m16n8k32), the constant is a Toeplitz operand, s32 columns are folded back.
+
+def split7(d):
+    """28-bit digit (|d| <= 2^27 + small) -> 4 signed 7-bit digits, the top one absorbs the remainder"""
+    out = []
+    for _ in range(3):
+        e = ((d + 64) & 127) - 64
+        out.append(e)
+        d = (d - e) >> 7
+    out.append(d)
+    assert all(-128 <= e <= 127 for e in out), out
+    return out
+
+
+def digits7(D):
+    out = []
+    for d in D:
+        out.extend(split7(d))
+    return out
+
+
+def conv_columns(A7, B7, p_lo, p_hi):
+    """s32 column sums c_p = sum_k A7[k] * B7[p-k] for p in [p_lo, p_hi)"""
+    n = len(B7)
+    cols = []
+    for p in range(p_lo, p_hi):
+        s = 0
+        for k in range(max(0, p - n + 1), min(len(A7), p + 1)):
+            s += A7[k] * B7[p - k]
+        assert -(1 << 31) < s < (1 << 31), "s32 accumulator overflow"
+        cols.append(s)
+    return cols
+
+
+def fold28(cols):
+    """groups of 4 radix-2^7 columns -> (lo, carry) per 28-bit digit; digit j = lo[j] + carry[j-1]"""
+    lo, carry = [], []
+    for j in range(len(cols) // 4):
+        v = cols[4 * j] + (cols[4 * j + 1] << 7) + (cols[4 * j + 2] << 14) + (cols[4 * j + 3] << 21)
+        l = sgxt(v)
+        lo.append(l)
+        carry.append((v - l) >> W)
+    return lo, carry
+
+
+def mulmod_imma(P, keyc, A, B, sqr=False):
+    sh, Nt, mu = keyc
+    G, BL, L = P.G, P.BL, P.L
+    X = product(P, A, B, 2 * G, "full", sqr)
+    q1 = X[L - 1:2 * L - 1]
+    q1[L - 1] += X[2 * L - 1] << W
+    Nt_d, mu_d = keyc_digits(P, keyc)
+    # phase B: digits j >= L of q1*mu, two guard digits below
+    cols = conv_columns(digits7(q1), digits7(mu_d), 4 * (L - 2), 4 * 2 * L)
+    lo, carry = fold28(cols)                      # index jj = j - (L-2)
+    qh = []
+    c = 0
+    for jj in range(len(lo)):
+        t = lo[jj] + (carry[jj - 1] if jj else 0) + c
+        d = sgxt(t)
+        c = (t - d) >> W
+        if jj >= 2:
+            qh.append(d)
+    # phase C: low L digits of qh*Nt (exact)
+    cols = conv_columns(digits7(qh), digits7(Nt_d), 0, 4 * L)
+    lo, carry = fold28(cols)
+    out = []
+    c = 0
+    for j in range(L):
+        t = X[j] - lo[j] - (carry[j - 1] if j else 0) + c
+        d = sgxt(t)
+        c = (t - d) >> W
+        out.append(d)
+    return out

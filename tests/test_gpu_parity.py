@@ -12,7 +12,7 @@ from util import h, kat
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = [1, 2]  # simple64, block28 (skipped per key when block28 does not cover the size)
+ENGINES = [1, 2, 3]  # simple64, block28 (IMAD only), block28t (IMAD + IMMA); 2/3 skipped when the size is not covered
 
 
 def _key(n, g, n_bits, limb_bits, engine):
