@@ -361,10 +361,15 @@ __device__ __forceinline__ unsigned split7_pack(int d) {
     return (unsigned)(e0 & 255) | ((unsigned)(e1 & 255) << 8) | ((unsigned)(e2 & 255) << 16) | ((unsigned)d << 24);
 }
 
-// A-operand bytes live in the Q buffer: As[lane][RS]; output arrays LO (in T blocks G..2G-1) and CA (in B): [digit][lane]
+// A-operand bytes live in the Q buffer: As[lane][RS]; output arrays LO (in T blocks G..2G-1) and CA (in B):
+// [digit][lane rotated by 8*digit] so that both the fold (lanes vary in (g, t)) and the ripple (lanes vary in
+// the ciphertext index) hit 32 distinct banks.
 template <class C> __device__ __forceinline__ char* as_ptr(Smem<C>& S) { return (char*)S.Q; }
 template <class C> __device__ __forceinline__ int* lo_ptr(Smem<C>& S) { return (int*)(S.T + C::VAL4); }
 template <class C> __device__ __forceinline__ int* ca_ptr(Smem<C>& S) { return (int*)S.B; }
+__device__ __forceinline__ int dl_index(int jj, int m) { return jj * 32 + ((m + 8 * jj) & 31); }
+
+__device__ __forceinline__ unsigned lds32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 
 // C[lane][p] for the tile pairs of this warp, p = p_base + 16*U + ...; folded: LO[jj] / CA[jj+1], jj = 4U + t
 template <class C, bool HIGH>
@@ -376,79 +381,68 @@ __device__ __noinline__ void phase_mma(int4* smem_base) {
     constexpr int P_BASE = HIGH ? 4 * (L - 2) : 0;
     constexpr int NP = HIGH ? C::NP_HIGH : C::NP_LOW;
     constexpr int NOUT = HIGH ? L + 2 : L;
-    const char* As = as_ptr<C>(S);
-    const char* rtab = HIGH ? S.rmu : S.rnt;
-    int acc[C::NPW][2][2][4];       // [pair][tile h][m-tile][c0..c3]
+    const unsigned as_base = (unsigned)__cvta_generic_to_shared(as_ptr<C>(S)) + g * C::RS + 4 * t;
+    const unsigned rt_base = (unsigned)__cvta_generic_to_shared(HIGH ? S.rmu : S.rnt);
+    int* LO = lo_ptr<C>(S);
+    int* CA = ca_ptr<C>(S);
+#pragma unroll 1
+    for (int q = 0; q < C::NPW; q++) {
+        const int U = warp + q * G;                              // tile pair: columns [P0, P0+16) = digits 4U .. 4U+3
+        if (U >= NP) break;
+        const int P0 = P_BASE + 16 * U;
+        // k-steps with some (k, p): 0 <= p - k <= K7-1, k in [32ks, 32ks+32), p in [P0, P0+16)
+        int ks_lo = (P0 - (K7 - 1) - 31 + 31) / 32; if (P0 - (K7 - 1) - 31 <= 0) ks_lo = 0;
+        int ks_hi = (P0 + 15) / 32; if (ks_hi > C::KSTEPS - 1) ks_hi = C::KSTEPS - 1;
+        // B-fragment addresses: column n = g of tile h is p = P0 + 4(g>>1) + (g&1) + 2h; 4 ascending bytes of the reversed table
+        unsigned baddr[2];
 #pragma unroll
-    for (int q = 0; q < C::NPW; q++)
+        for (int h = 0; h < 2; h++) {
+            const int p = P0 + 4 * (g >> 1) + (g & 1) + 2 * h;
+            const int idx0 = C::PAD7 + K7 - 1 - p + 4 * t;
+            const int sft = idx0 & 3;
+            baddr[h] = rt_base + sft * C::XLEN + (idx0 - sft);
+        }
+        int acc[2][2][4];           // [tile h][m-tile][c0..c3]
 #pragma unroll
         for (int h = 0; h < 2; h++)
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-                for (int i = 0; i < 4; i++) acc[q][h][mt][i] = 0;
-    // B-fragment base pointers: column n = g of tile h of pair U is p = P_BASE + 16U + 4(g>>1) + (g&1) + 2h
-    const char* bptr[C::NPW][2];
+                for (int i = 0; i < 4; i++) acc[h][mt][i] = 0;
+#pragma unroll 2
+        for (int ks = ks_lo; ks <= ks_hi; ks++) {
+            const unsigned ko = 32u * ks;
+            unsigned a[2][4];
 #pragma unroll
-    for (int q = 0; q < C::NPW; q++) {
-        const int U = warp + q * G;
+            for (int mt = 0; mt < 2; mt++) {
+                const unsigned ap = as_base + mt * 16 * C::RS + ko;
+                a[mt][0] = lds32(ap);
+                a[mt][1] = lds32(ap + 8 * C::RS);
+                a[mt][2] = lds32(ap + 16);
+                a[mt][3] = lds32(ap + 8 * C::RS + 16);
+                if (C::HALF_LAST && ks == C::KSTEPS - 1) { a[mt][2] = 0; a[mt][3] = 0; }
+            }
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int p = P_BASE + 16 * U + 4 * (g >> 1) + (g & 1) + 2 * h;
-            const int idx0 = C::PAD7 + K7 - 1 - p + 4 * t;       // + 32*ks: index of the first of 4 ascending bytes
-            const int sft = idx0 & 3;
-            bptr[q][h] = rtab + sft * C::XLEN + (idx0 - sft);
-        }
-    }
-    const char* arow = As + g * C::RS + 4 * t;
-#pragma unroll 1
-    for (int ks = 0; ks < C::KSTEPS; ks++) {
-        unsigned a[2][4];
+            for (int h = 0; h < 2; h++) {
+                const unsigned b0 = lds32(baddr[h] + ko), b1 = lds32(baddr[h] + ko + 16);
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
-            const char* ap = arow + mt * 16 * C::RS + 32 * ks;
-            a[mt][0] = *(const unsigned*)(ap);
-            a[mt][1] = *(const unsigned*)(ap + 8 * C::RS);
-            a[mt][2] = *(const unsigned*)(ap + 16);
-            a[mt][3] = *(const unsigned*)(ap + 8 * C::RS + 16);
-            if (C::HALF_LAST && ks == C::KSTEPS - 1) { a[mt][2] = 0; a[mt][3] = 0; }
-        }
-#pragma unroll
-        for (int q = 0; q < C::NPW; q++) {
-            const int U = warp + q * G;
-            const int P0 = P_BASE + 16 * U;                     // pair covers columns [P0, P0+16)
-            // some (k, p) of this k-step x pair has 0 <= p - k <= K7-1 ?
-            const bool valid = U < NP && (P0 + 15 - 32 * ks >= 0) && (P0 - (32 * ks + 31) <= K7 - 1);
-            if (valid) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const unsigned b0 = *(const unsigned*)(bptr[q][h] + 32 * ks);
-                    const unsigned b1 = *(const unsigned*)(bptr[q][h] + 32 * ks + 16);
-#pragma unroll
-                    for (int mt = 0; mt < 2; mt++) mma_s8(acc[q][h][mt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
-                }
+                for (int mt = 0; mt < 2; mt++) mma_s8(acc[h][mt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
             }
         }
-    }
-    // fold: thread (g, t) owns the 4 radix-2^7 columns of digit jj = 4U + t for rows g, g+8 of each m-tile
-    int* LO = lo_ptr<C>(S);
-    int* CA = ca_ptr<C>(S);
-#pragma unroll
-    for (int q = 0; q < C::NPW; q++) {
-        const int U = warp + q * G;
+        // fold: thread (g, t) owns the 4 radix-2^7 columns of digit jj = 4U + t for rows g, g+8 of each m-tile
         const int jj = 4 * U + t;
-        if (U < NP && jj < NOUT) {
+        if (jj < NOUT) {
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
 #pragma unroll
                 for (int r = 0; r < 2; r++) {
-                    long long v = (long long)acc[q][0][mt][2 * r] + ((long long)acc[q][0][mt][2 * r + 1] << 7)
-                                + ((long long)acc[q][1][mt][2 * r] << 14) + ((long long)acc[q][1][mt][2 * r + 1] << 21);
+                    long long v = (long long)acc[0][mt][2 * r] + ((long long)acc[0][mt][2 * r + 1] << 7)
+                                + ((long long)acc[1][mt][2 * r] << 14) + ((long long)acc[1][mt][2 * r + 1] << 21);
                     int lo = sgxt28((int)v);
                     int ca = (int)((v - lo) >> W);
                     const int m = 16 * mt + g + 8 * r;
-                    LO[jj * 32 + m] = lo;
-                    CA[(jj + 1) * 32 + m] = ca;
+                    LO[dl_index(jj, m)] = lo;
+                    CA[dl_index(jj + 1, m)] = ca;
                 }
         }
     }
@@ -478,16 +472,16 @@ __device__ __forceinline__ void qhat_to_bytes(Smem<C>& S, int warp, int lane) {
     const int* CA = ca_ptr<C>(S);
     int carry = 0;
     if (warp == 0) {      // the guard digits only feed their carry into digit 0
-        int t0 = LO[0 * 32 + lane];
+        int t0 = LO[dl_index(0, lane)];
         carry = (t0 - sgxt28(t0)) >> W;
-        int t1 = LO[1 * 32 + lane] + CA[1 * 32 + lane] + carry;
+        int t1 = LO[dl_index(1, lane)] + CA[dl_index(1, lane)] + carry;
         carry = (t1 - sgxt28(t1)) >> W;
     }
     unsigned w[C::BL];
 #pragma unroll
     for (int k = 0; k < C::BL; k++) {
         const int jj = warp * C::BL + k + 2;
-        int tt = LO[jj * 32 + lane] + CA[jj * 32 + lane] + carry;
+        int tt = LO[dl_index(jj, lane)] + CA[dl_index(jj, lane)] + carry;
         int d = sgxt28(tt);
         carry = (tt - d) >> W;
         w[k] = split7_pack(d);
@@ -517,7 +511,7 @@ __device__ __forceinline__ void low_to_value(Smem<C>& S, int warp, int lane) {
 #pragma unroll
     for (int k = 0; k < C::BL; k++) {
         const int j = warp * C::BL + k;
-        int tt = a[k] - LO[j * 32 + lane] - (j > 0 ? CA[j * 32 + lane] : 0) + carry;
+        int tt = a[k] - LO[dl_index(j, lane)] - (j > 0 ? CA[dl_index(j, lane)] : 0) + carry;
         int d = sgxt28(tt);
         carry = (tt - d) >> W;
         a[k] = d;
