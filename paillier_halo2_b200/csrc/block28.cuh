@@ -381,7 +381,8 @@ __device__ __noinline__ void phase_mma(int4* smem_base) {
     constexpr int P_BASE = HIGH ? 4 * (L - 2) : 0;
     constexpr int NP = HIGH ? C::NP_HIGH : C::NP_LOW;
     constexpr int NOUT = HIGH ? L + 2 : L;
-    const unsigned as_base = (unsigned)__cvta_generic_to_shared(as_ptr<C>(S)) + g * C::RS + 4 * t;
+    // ldmatrix.x4 row addresses: lanes 0-7 rows 0-7 (k bytes 0-15), 8-15 rows 8-15, 16-23 rows 0-7 (+16), 24-31 rows 8-15 (+16)
+    const unsigned as_base = (unsigned)__cvta_generic_to_shared(as_ptr<C>(S)) + ((lane & 7) + ((lane >> 3) & 1) * 8) * C::RS + (lane >> 4) * 16;
     const unsigned rt_base = (unsigned)__cvta_generic_to_shared(HIGH ? S.rmu : S.rnt);
     int* LO = lo_ptr<C>(S);
     int* CA = ca_ptr<C>(S);
@@ -416,10 +417,8 @@ __device__ __noinline__ void phase_mma(int4* smem_base) {
 #pragma unroll
             for (int mt = 0; mt < 2; mt++) {
                 const unsigned ap = as_base + mt * 16 * C::RS + ko;
-                a[mt][0] = lds32(ap);
-                a[mt][1] = lds32(ap + 8 * C::RS);
-                a[mt][2] = lds32(ap + 16);
-                a[mt][3] = lds32(ap + 8 * C::RS + 16);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(a[mt][0]), "=r"(a[mt][1]), "=r"(a[mt][2]), "=r"(a[mt][3]) : "r"(ap));
                 if (C::HALF_LAST && ks == C::KSTEPS - 1) { a[mt][2] = 0; a[mt][3] = 0; }
             }
 #pragma unroll
