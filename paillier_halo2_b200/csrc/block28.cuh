@@ -341,6 +341,143 @@ __device__ __noinline__ void run_phase(int4* smem_base, const int4* Y, int ph) {
     __syncthreads();
 }
 
+// ---- phase A specialised for the tensor engine ---------------------------------------------------------
+// Same arithmetic as run_phase<PG=0>, but with nothing else alive during the product loop (32-bit shared
+// addresses, compile-time strides, merge parameters recomputed afterwards): the register allocator then has
+// room to keep several IMAD.WIDE products in flight instead of stalling each IADD3 on the multiply before it.
+__device__ __forceinline__ int4 lds128(unsigned addr) {
+    int4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v;
+}
+// one triangular half of a block product: HI = false: columns x+y <= BL-1 into acc[x+y];
+// HI = true: columns x+y >= BL into acc[x+y-BL].  SQ: only x <= y, off-diagonal products doubled.
+template <class C, bool HI, bool SQ>
+__device__ __forceinline__ void mac_half(long long (&acc)[C::BL], const int (&a)[C::CH * 4], unsigned baddr) {
+    constexpr int BL = C::BL;
+#pragma unroll
+    for (int c = 0; c < C::CH; c++) {
+        int4 bv = lds128(baddr + c * 512);
+        int b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int y = 4 * c + e;
+            if (y < BL) {
+                int by = b4[e];
+                int by2 = by + by;
+#pragma unroll
+                for (int x = 0; x < BL; x++) {
+                    const bool in_half = HI ? (x + y >= BL) : (x + y <= BL - 1);
+                    if (in_half && (!SQ || x <= y)) madw(acc[HI ? x + y - BL : x + y], a[x], (SQ && x != y) ? by2 : by);
+                }
+            }
+        }
+    }
+}
+
+// all block pairs of anti-diagonal d, one triangular half
+template <class C, bool HI>
+__device__ __forceinline__ void job_half(long long (&acc)[C::BL], int d, int i_lo, int i_hi, int sqr, unsigned v_addr, unsigned y_addr) {
+    unsigned aa = v_addr + i_lo * (C::BLK4 * 16), ba = y_addr + (d - i_lo) * (C::BLK4 * 16);
+#pragma unroll 1
+    for (int i = i_lo; i <= i_hi; i++, aa += C::BLK4 * 16, ba -= C::BLK4 * 16) {
+        int a[C::CH * 4];
+#pragma unroll
+        for (int c = 0; c < C::CH; c++) { int4 v = lds128(aa + c * 512); a[4 * c] = v.x; a[4 * c + 1] = v.y; a[4 * c + 2] = v.z; a[4 * c + 3] = v.w; }
+        if (sqr && 2 * i == d) {
+            mac_half<C, HI, true>(acc, a, ba);
+        } else {
+            if (sqr) {
+#pragma unroll
+                for (int k = 0; k < C::BL; k++) a[k] += a[k];
+            }
+            mac_half<C, HI, false>(acc, a, ba);
+        }
+    }
+}
+
+// ripple BL column sums (+ carry in) into BL strict digits; returns the 64-bit carry out
+template <class C>
+__device__ __forceinline__ long long ripple_cols(const long long (&acc)[C::BL], int ncols, long long carry, int (&dig)[C::CH * 4]) {
+#pragma unroll
+    for (int k = 0; k < C::BL; k++) {
+        if (k < ncols) {
+            long long t = acc[k] + carry;
+            int d = sgxt28((int)t);
+            carry = (t - d) >> W;
+            dig[k] = d;
+        }
+    }
+    return carry;
+}
+
+template <class C>
+__device__ __noinline__ void phase_product(int4* smem_base, const int4* Y, int sqr) {
+    constexpr int G = C::G, BL = C::BL;
+    Smem<C> S(smem_base);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned v_addr = (unsigned)__cvta_generic_to_shared(S.V) + lane * 16;
+    const unsigned y_addr = sqr ? v_addr : (unsigned)__cvta_generic_to_shared(Y) + lane * 16;
+    Pending<C> pend;
+    pend.blk = -1;
+    int blk0 = -1, spill0 = 0;
+    int4* stash = S.Q + threadIdx.x;
+    const int njobs = warp < G - 1 ? 2 : 1;
+#pragma unroll 1
+    for (int half = 0; half < njobs; half++) {
+        const int d = warp + half * G;
+        const int i_lo = half ? d - G + 1 : 0;
+        const int i_hi = sqr ? d / 2 : (half ? G - 1 : d);
+        long long carry;
+        {   // columns 0 .. BL-1 -> Lo digits
+            long long acc[BL];
+#pragma unroll
+            for (int k = 0; k < BL; k++) acc[k] = 0;
+            job_half<C, false>(acc, d, i_lo, i_hi, sqr, v_addr, y_addr);
+            int lo[C::CH * 4];
+            carry = ripple_cols<C>(acc, BL, 0, lo);
+#pragma unroll
+            for (int k = BL; k < C::CH * 4; k++) lo[k] = 0;
+            store_block<C>(blk_ptr<C>(S.T, d, lane), lo);
+        }
+        {   // columns BL .. 2BL-2 -> Hi digits, last digit and spill from the final carry
+            long long acc[BL];
+#pragma unroll
+            for (int k = 0; k < BL; k++) acc[k] = 0;
+            job_half<C, true>(acc, d, i_lo, i_hi, sqr, v_addr, y_addr);
+            carry = ripple_cols<C>(acc, BL - 1, carry, pend.hi);
+            int dtop = sgxt28((int)carry);
+            pend.hi[BL - 1] = dtop;
+            pend.spill = (int)((carry - dtop) >> W);
+#pragma unroll
+            for (int k = BL; k < C::CH * 4; k++) pend.hi[k] = 0;
+        }
+        pend.carry = 0;
+        pend.blk = d;
+        if (half == 0 && njobs == 2) {
+#pragma unroll
+            for (int c = 0; c < C::CH; c++)
+                stash[c * C::THREADS] = make_int4(pend.hi[4 * c], pend.hi[4 * c + 1], pend.hi[4 * c + 2], pend.hi[4 * c + 3]);
+            blk0 = d; spill0 = pend.spill;
+        }
+    }
+    if (warp == G - 1) store_zero_block<C>(S.T, 2 * G - 1, lane);
+    __syncthreads();
+    int carry0 = 0;
+    if (blk0 >= 0) {
+        int h0[C::CH * 4];
+        load_block<C>(h0, stash, C::THREADS);
+        int4* p = blk_ptr<C>(S.T, blk0 + 1, lane);
+        carry0 = add_ripple_block<C>(p, p, h0, 1);
+    }
+    {
+        int4* p = blk_ptr<C>(S.T, pend.blk + 1, lane);
+        pend.carry = add_ripple_block<C>(p, p, pend.hi, 1);
+    }
+    __syncthreads();
+    if (blk0 >= 0) *(int*)blk_ptr<C>(S.T, blk0 + 2, lane) += carry0 + spill0;
+    if (pend.blk + 2 <= 2 * G - 1) *(int*)blk_ptr<C>(S.T, pend.blk + 2, lane) += pend.carry + pend.spill;
+    __syncthreads();
+}
+
 // ---- IMMA variant of phases B and C ------------------------------------------------------------------
 // Both multiply a per-lane number by a per-key constant: over the 32 lanes of the CTA that is a GEMM
 //   C[lane][p] = sum_k A7[lane][k] * K7[p - k]          (A7, K7: signed 7-bit digits, 4 per 28-bit digit)
@@ -527,7 +664,8 @@ __device__ __forceinline__ void low_to_value(Smem<C>& S, int warp, int lane) {
 template <class C, bool SQR, bool MMA = false>
 __device__ __forceinline__ void mulmod(Smem<C>& S, const int4* Y, int role, int lane) {
     int4* base = S.V;
-    run_phase<C>(base, Y, SQR ? PH_SQR : PH_MUL);
+    if (MMA) phase_product<C>(base, Y, SQR ? 1 : 0);
+    else run_phase<C>(base, Y, SQR ? PH_SQR : PH_MUL);
     if (!MMA) {
         run_phase<C>(base, nullptr, PH_HIGH);
         run_phase<C>(base, nullptr, PH_LOW);
