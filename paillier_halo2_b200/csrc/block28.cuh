@@ -148,13 +148,15 @@ __device__ __forceinline__ int add_ripple_block(int4* p_dst, const int4* p_src, 
     constexpr int BL = C::BL;
     int a[C::CH * 4];
     load_block<C>(a, p_src, 32);
+    // biased form: t' = value + 2^27 + carry; carry' = t' >> 28 (floor), digit = (t' & M) - 2^27: the serial chain
+    // per digit is one add and one shift, the digit itself is off the critical path
     int carry = 0;
 #pragma unroll
     for (int k = 0; k < BL; k++) {
-        int t = a[k] + sign * h[k] + carry;
-        int d = sgxt28(t);
-        carry = (t - d) >> W;
-        a[k] = d;
+        int s0 = a[k] + sign * h[k] + (1 << (W - 1));
+        int t = s0 + carry;
+        carry = t >> W;
+        a[k] = (t & ((1 << W) - 1)) - (1 << (W - 1));
     }
 #pragma unroll
     for (int k = BL; k < C::CH * 4; k++) a[k] = 0;
@@ -400,10 +402,9 @@ __device__ __forceinline__ long long ripple_cols(const long long (&acc)[C::BL], 
 #pragma unroll
     for (int k = 0; k < C::BL; k++) {
         if (k < ncols) {
-            long long t = acc[k] + carry;
-            int d = sgxt28((int)t);
-            carry = (t - d) >> W;
-            dig[k] = d;
+            long long t = (acc[k] + (1ll << (W - 1))) + carry;     // biased: chain = 64-bit add -> 64-bit shift
+            carry = t >> W;
+            dig[k] = ((int)t & ((1 << W) - 1)) - (1 << (W - 1));
         }
     }
     return carry;
@@ -617,10 +618,9 @@ __device__ __forceinline__ void qhat_to_bytes(Smem<C>& S, int warp, int lane) {
 #pragma unroll
     for (int k = 0; k < C::BL; k++) {
         const int jj = warp * C::BL + k + 2;
-        int tt = LO[dl_index(jj, lane)] + CA[dl_index(jj, lane)] + carry;
-        int d = sgxt28(tt);
-        carry = (tt - d) >> W;
-        w[k] = split7_pack(d);
+        int tt = (LO[dl_index(jj, lane)] + CA[dl_index(jj, lane)] + (1 << (W - 1))) + carry;
+        carry = tt >> W;
+        w[k] = split7_pack((tt & ((1 << W) - 1)) - (1 << (W - 1)));
     }
     __syncthreads();                                              // every warp has read LO/CA of its block
     unsigned* row = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + warp * C::BL;
@@ -647,10 +647,9 @@ __device__ __forceinline__ void low_to_value(Smem<C>& S, int warp, int lane) {
 #pragma unroll
     for (int k = 0; k < C::BL; k++) {
         const int j = warp * C::BL + k;
-        int tt = a[k] - LO[dl_index(j, lane)] - (j > 0 ? CA[dl_index(j, lane)] : 0) + carry;
-        int d = sgxt28(tt);
-        carry = (tt - d) >> W;
-        a[k] = d;
+        int tt = (a[k] - LO[dl_index(j, lane)] - (j > 0 ? CA[dl_index(j, lane)] : 0) + (1 << (W - 1))) + carry;
+        carry = tt >> W;
+        a[k] = (tt & ((1 << W) - 1)) - (1 << (W - 1));
     }
 #pragma unroll
     for (int k = C::BL; k < C::CH * 4; k++) a[k] = 0;
