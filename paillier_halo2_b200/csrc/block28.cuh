@@ -569,17 +569,22 @@ __device__ __noinline__ void phase_mma(int4* smem_base) {
         // fold: thread (g, t) owns the 4 radix-2^7 columns of digit jj = 4U + t for rows g, g+8 of each m-tile
         const int jj = 4 * U + t;
         if (jj < NOUT) {
+            // v = c0 + c1 2^7 + c2 2^14 + c3 2^21 (|c| < 2^23) in 32-bit pieces: v = lowp + hr 2^14 + hq 2^28
+            const int x0 = (g + 8 * jj) & 31, x1 = (g + 8 * (jj + 1)) & 31;
+            int* lo_row = LO + jj * 32;
+            int* ca_row = CA + (jj + 1) * 32;
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
 #pragma unroll
                 for (int r = 0; r < 2; r++) {
-                    long long v = (long long)acc[0][mt][2 * r] + ((long long)acc[0][mt][2 * r + 1] << 7)
-                                + ((long long)acc[1][mt][2 * r] << 14) + ((long long)acc[1][mt][2 * r + 1] << 21);
-                    int lo = sgxt28((int)v);
-                    int ca = (int)((v - lo) >> W);
-                    const int m = 16 * mt + g + 8 * r;
-                    LO[dl_index(jj, m)] = lo;
-                    CA[dl_index(jj + 1, m)] = ca;
+                    const int lowp = acc[0][mt][2 * r] + (acc[0][mt][2 * r + 1] << 7);
+                    const int highp = acc[1][mt][2 * r] + (acc[1][mt][2 * r + 1] << 7);
+                    const int tb = lowp + ((highp & 0x3FFF) << 14) + (1 << (W - 1));       // biased low part
+                    const int lo = (tb & ((1 << W) - 1)) - (1 << (W - 1));
+                    const int ca = (tb >> W) + (highp >> 14);
+                    const int off = 16 * mt + 8 * r;
+                    lo_row[(x0 + off) & 31] = lo;
+                    ca_row[(x1 + off) & 31] = ca;
                 }
         }
     }

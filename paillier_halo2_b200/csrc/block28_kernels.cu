@@ -12,6 +12,7 @@
 #include "block28.cuh"
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 namespace pb200 {
 using namespace b28;
@@ -30,7 +31,7 @@ struct B28Dev {            // per-key device-side descriptor (same for every con
     int words_in, words_out;
     int sh;                // Nt = n2 << sh
     unsigned nt_top;       // floor(Nt / 2^(28(L-2)))
-    int g_is_one_table;    // unused
+    unsigned sms;
 };
 
 // ---- device helpers --------------------------------------------------------------------------
@@ -405,6 +406,7 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     K.consts = key->d_consts; K.ops = key->d_ops; K.n_ops = (int)ops.size(); K.first_idx = first_idx;
     K.tg = key->d_tg; K.n_windows = n_windows; K.words_in = (int)win; K.words_out = (int)((2 * n_bits + 63) / 64);
     K.sh = sh;
+    K.sms = (unsigned)key->sms;
     K.nt_top = (unsigned)BigInt::shr(Nt, (size_t)W * (C::L - 2)).bits_at(0, 32);
     // comb table
     CUK(cudaFuncSetAttribute(k_gtable_bases<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
