@@ -191,12 +191,17 @@ class RefreshAux:
 
 
 class BigUintChip:
-    """Restatement of biguint-halo2 `BigUintChip` witness generation."""
+    """Restatement of biguint-halo2 `BigUintChip` witness generation.
 
-    def __init__(self, limb_bits: int, lookup_bits: Optional[int] = None):
+    `witness_source`: optional iterator of externally produced (q, rem) pairs, consumed by `mul_mod` in call
+    order INSTEAD of computing div_rem here — this is how the tests feed the GPU-produced witness stream
+    through the chip and let the constraints (not the oracle's own division) decide whether it is accepted."""
+
+    def __init__(self, limb_bits: int, lookup_bits: Optional[int] = None, witness_source=None):
         self.limb_bits = limb_bits
         self.lookup_bits = lookup_bits
         self.B = 1 << limb_bits
+        self.witness_source = iter(witness_source) if witness_source is not None else None
 
     # A.1 ------------------------------------------------------------------------------
     def range_check(self, ctx: Context, v: int, bits: int) -> None:
@@ -214,6 +219,9 @@ class BigUintChip:
         if bit_len % self.limb_bits != 0:
             raise AssertionError("assign_integer: bit_len % limb_bits != 0")
         nl = bit_len // self.limb_bits
+        if v >> bit_len:
+            ctx.constrain("assign_integer: value fits bit_len", False)
+            v &= (1 << bit_len) - 1
         limbs = decompose(v, nl, self.limb_bits)
         for l in limbs:
             ctx.load(l)
@@ -288,6 +296,8 @@ class BigUintChip:
         for i in range(n):
             s = a[i] - b[i] + carry + word_max
             ctx.constrain("is_equal_muled: sum non-negative", s >= 0)
+            if s < 0:
+                s = 0
             carry_next, cs = self.div_mod_unsafe(ctx, s, B)
             acc_extra += word_max
             q_acc, mod_acc = self.div_mod_unsafe(ctx, acc_extra, B)
@@ -308,7 +318,10 @@ class BigUintChip:
         full = a.value * b.value
         if n.value == 0:
             raise ZeroDivisionError("mul_mod by zero modulus")
-        q, rem = divmod(full, n.value)
+        if self.witness_source is not None:
+            q, rem = next(self.witness_source)      # GPU-fed witness: accepted or rejected by the constraints below
+        else:
+            q, rem = divmod(full, n.value)
         ctx.steps.append(MulModStep(kind, a.value, b.value, q, rem))
         q_as = self.assign_integer(ctx, q, L * self.limb_bits)
         rem_as = self.assign_integer(ctx, rem, L * self.limb_bits)
@@ -412,10 +425,11 @@ def check_constraints(ctx: Context) -> None:
 
 
 def paillier_enc_test(enc_bits: int, limb_bits: int, n: int, g: int, m: int, r: int, res: int,
-                      lookup_bits: Optional[int] = None) -> Context:
-    """src/bench.rs:33-75 — returns the filled Context (cells, steps) after all assertions."""
+                      lookup_bits: Optional[int] = None, witness_source=None) -> Context:
+    """src/bench.rs:33-75 — returns the filled Context (cells, steps) after all assertions.
+    witness_source: (q, rem) pairs in mul_mod call order (see BigUintChip)."""
     ctx = Context()
-    big = BigUintChip(limb_bits, lookup_bits)
+    big = BigUintChip(limb_bits, lookup_bits, witness_source)
     chip = PaillierChip.construct(big, enc_bits)
     n_as = big.assign_integer(ctx, n, enc_bits)
     g_as = big.assign_integer(ctx, g, enc_bits)
@@ -431,11 +445,11 @@ def paillier_enc_test(enc_bits: int, limb_bits: int, n: int, g: int, m: int, r: 
 
 
 def paillier_enc_add_test(enc_bits: int, limb_bits: int, n: int, g: int, c1: int, c2: int, res: int,
-                          lookup_bits: Optional[int] = None, c_bits: Optional[int] = None) -> Context:
+                          lookup_bits: Optional[int] = None, c_bits: Optional[int] = None, witness_source=None) -> Context:
     """src/bench.rs:77-117 — c1, c2 are assigned with enc_bits in the reference (half-width,
     src/paillier.rs:216-221); pass c_bits=2*enc_bits for real ciphertexts."""
     ctx = Context()
-    big = BigUintChip(limb_bits, lookup_bits)
+    big = BigUintChip(limb_bits, lookup_bits, witness_source)
     chip = PaillierChip.construct(big, enc_bits)
     n_as = big.assign_integer(ctx, n, enc_bits)
     g_as = big.assign_integer(ctx, g, enc_bits)

@@ -248,6 +248,20 @@ class PaillierKey:
         return [[int(out[i, j, 0]) | (int(out[i, j, 1]) << 64) for j in range(nl)] for i in range(len(vals))]
 
 
+def chip_order(m: int, n: int, g_chain: Sequence[Tuple[int, int]], unit_records: Sequence[Tuple[int, int]]):
+    """Interleave the per-key g-chain squarings with one unit's record stream into the order in which
+    PaillierChip::encrypt issues its mul_mods (src/paillier.rs:51,55,57; INTEGRATION.md §3):
+    g-chain: for bit i of m low->high: sqr_i [, mul]; then the unit's r-chain records; then the final one."""
+    out = []
+    it = iter(unit_records)
+    for i in range(m.bit_length()):
+        out.append(g_chain[i])
+        if (m >> i) & 1:
+            out.append(next(it))
+    out.extend(it)
+    return out
+
+
 MASK64 = (1 << 64) - 1
 DIGEST_INIT = 0xCBF29CE484222325
 DIGEST_PRIME = 0x100000001B3

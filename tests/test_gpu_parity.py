@@ -172,3 +172,35 @@ def test_tally_sharded_single_gpu(built_lib, engine):
         partials = np.stack([key.tally_words(c_w[slice(*shard_range(len(c_w), r, 4))]) for r in range(4)])
         assert words_to_ints(key.tally_combine_words(partials))[0] == want
         assert words_to_ints(key.tally_words(c_w))[0] == want
+
+
+@pytest.mark.parametrize("enc_bits,limb_bits", [(128, 64), (264, 88)])
+def test_gpu_fed_circuit_is_satisfied(built_lib, enc_bits, limb_bits):
+    """BASELINE.json configs[0] with the GPU as witness producer: the reference's test flow
+    (src/paillier.rs:113-182, k=16 / lookup_bits=15) where every mul_mod takes its (q, rem) from the CUDA stream
+    instead of num-bigint; the constraint re-checker (MockProver stand-in) must accept it, and reject a tampered one."""
+    from oracle.paillier_oracle import paillier_enc_add_test, paillier_enc_test
+    from paillier_halo2_b200.api import chip_order
+    rng = random.Random(1000 + enc_bits)
+    n = rng.getrandbits(enc_bits) | 1
+    g, m, r = (rng.getrandbits(enc_bits) for _ in range(3))
+    with PaillierKey(n, g, enc_bits, limb_bits) as key:
+        cs, units, gcounts = key.encrypt_witness([m], [r])
+        gch = key.g_chain()
+        stream = chip_order(m, n, gch, units[0])
+        ctx = paillier_enc_test(enc_bits, limb_bits, n, g, m, r, cs[0], lookup_bits=15, witness_source=stream)
+        assert len(ctx.steps) == len(stream) and cs[0] == paillier_enc_native(n, g, m, r)
+        # limb formatting of a witness value through K5 equals the cells the chip assigned for it
+        q_last, rem_last = stream[-1]
+        assert key.repack_limbs([rem_last], 2 * enc_bits, limb_bits)[0] == [(rem_last >> (limb_bits * i)) & ((1 << limb_bits) - 1)
+                                                                              for i in range(2 * enc_bits // limb_bits)]
+        bad = list(stream)
+        bad[len(bad) // 2] = (bad[len(bad) // 2][0] + 1, bad[len(bad) // 2][1])
+        with pytest.raises(AssertionError):
+            paillier_enc_test(enc_bits, limb_bits, n, g, m, r, cs[0], lookup_bits=15, witness_source=bad)
+        # add: one mul_mod group, quotient from the GPU
+        c1, c2 = rng.getrandbits(enc_bits), rng.getrandbits(enc_bits)
+        res, q = key.paillier_add_native([c1], [c2], c_bits=enc_bits, want_q=True)
+        paillier_enc_add_test(enc_bits, limb_bits, n, g, c1, c2, res[0], lookup_bits=15, witness_source=[(q[0], res[0])])
+        with pytest.raises(AssertionError):
+            paillier_enc_add_test(enc_bits, limb_bits, n, g, c1, c2, res[0], lookup_bits=15, witness_source=[(q[0], res[0] ^ 2)])
