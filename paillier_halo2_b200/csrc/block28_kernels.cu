@@ -5,8 +5,8 @@
 // (:94-97).  Chain per unit (all modulo Nt, a multiple of n^2):
 //   r^n : left-to-right sliding window (w = 5) over the per-key exponent n; the 16 odd powers of r live in
 //         a per-CTA global scratch table (L2-resident), the window schedule is computed once per key;
-//   g^m : fixed-base comb, 8-bit windows: product of TG[i][byte_i(m)], TG[i][d] = g^(d * 2^(8i)) mod Nt
-//         built once per key by this engine (k_gtable_*);
+//   g^m : fixed-base comb, w-bit windows (w = 12 for |n| >= 1024, else 8): product of TG[i][digit_i(m)],
+//         TG[i][d] = g^(d * 2^(w i)) mod Nt, built once per key by this engine (k_gtable_*);
 //   c   : gm * rn, then one exact canonicalisation (finalize) and the shift back from Nt to n^2.
 #include "engine.hpp"
 #include "block28.cuh"
@@ -26,8 +26,9 @@ struct B28Dev {            // per-key device-side descriptor (same for every con
     const int2* ops;       // r-chain schedule: (number of squarings, table index or -1)
     int n_ops;
     int first_idx;         // table index the chain starts from
-    const int4* tg;        // comb table: [window][256][ENTRY4]
+    const int4* tg;        // comb table: [window][2^comb_bits][ENTRY4]
     int n_windows;
+    int comb_bits;         // window width of the fixed-base comb for g^m
     int words_in, words_out;
     int sh;                // Nt = n2 << sh
     unsigned nt_top;       // floor(Nt / 2^(28(L-2)))
@@ -179,7 +180,7 @@ __device__ __forceinline__ void finalize(Smem<C>& S, const B28Dev& K, u64* out, 
 }
 
 // ---- kernels ---------------------------------------------------------------------------------
-// comb table, stage 1: bases[i] = g^(2^(8i)) mod Nt, i < n_windows (one CTA; every lane computes the same value)
+// comb table, stage 1: bases[i] = g^(2^(w i)) mod Nt, i < n_windows (one CTA; every lane computes the same value)
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1) k_gtable_bases(B28Dev K, const u64* g_words, int4* bases) {
     extern __shared__ int4 smem[];
@@ -191,10 +192,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_gtable_bases(B28Dev K, const 
         if (lane == 0) scatter_entry<C>(bases + (size_t)i * C::ENTRY4, S.V, role, lane);
         __syncthreads();
         if (i + 1 < K.n_windows)
-            for (int s = 0; s < 8; s++) mulmod<C, true>(S, nullptr, role, lane);
+            for (int s = 0; s < K.comb_bits; s++) mulmod<C, true>(S, nullptr, role, lane);
     }
 }
-// comb table, stage 2: lane = window; TG[i][d] = bases[i]^d, d < 256
+// comb table, stage 2: lane = window; TG[i][d] = bases[i]^d, d < 2^w
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1) k_gtable_fill(B28Dev K, const int4* bases, int4* tg) {
     extern __shared__ int4 smem[];
@@ -204,15 +205,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_gtable_fill(B28Dev K, const i
     int win = blockIdx.x * 32 + lane;
     bool active = win < K.n_windows;
     if (!active) win = K.n_windows - 1;
-    int4* row = tg + (size_t)win * 256 * C::ENTRY4;
+    const int nd = 1 << K.comb_bits;
+    int4* row = tg + (size_t)win * nd * C::ENTRY4;
     set_one<C>(S.V, role, lane);
     if (active) scatter_entry<C>(row, S.V, role, lane);
     gather_entry<C>(S.V, bases + (size_t)win * C::ENTRY4, role, lane);
     gather_entry<C>(S.B, bases + (size_t)win * C::ENTRY4, role, lane);
-    for (int d = 1; d < 256; d++) {
+    for (int d = 1; d < nd; d++) {
         if (active) scatter_entry<C>(row + (size_t)d * C::ENTRY4, S.V, role, lane);
         __syncthreads();
-        if (d + 1 < 256) mulmod<C, false>(S, S.B, role, lane);
+        if (d + 1 < nd) mulmod<C, false>(S, S.B, role, lane);
     }
 }
 
@@ -253,13 +255,16 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K
     __syncthreads();
     // ---- g^m: comb over the bytes of m
     const u64* mw = m + unit * K.words_in;
-    {
-        int d0 = (int)(mw[0] & 255);
-        gather_entry<C>(S.V, K.tg + (size_t)d0 * C::ENTRY4, role, lane);
-    }
+    const int cb = K.comb_bits;
+    auto comb_digit = [&](int i) -> int {
+        const int bit = i * cb, w = bit >> 6, sft = bit & 63;
+        u64 v = mw[w] >> sft;
+        if (sft + cb > 64 && w + 1 < K.words_in) v |= mw[w + 1] << (64 - sft);
+        return (int)(v & ((1u << cb) - 1));
+    };
+    gather_entry<C>(S.V, K.tg + (size_t)comb_digit(0) * C::ENTRY4, role, lane);
     for (int i = 1; i < K.n_windows; i++) {
-        int d = (int)((mw[i >> 3] >> (8 * (i & 7))) & 255);
-        gather_entry<C>(S.B, K.tg + ((size_t)i * 256 + d) * C::ENTRY4, role, lane);
+        gather_entry<C>(S.B, K.tg + (((size_t)i << cb) + comb_digit(i)) * C::ENTRY4, role, lane);
         mulmod<C, false, MMA>(S, S.B, role, lane);
     }
     // ---- c = gm * rn, canonical
@@ -391,20 +396,22 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
         }
         if (pending) ops.push_back(make_int2(pending, -1));
     }
-    key->n_sqr = 1; key->n_mul = (TABN - 1) + (uint64_t)((n_bits + 7) / 8 - 1) + 1;   // r^2; table; comb; gm*rn
+    int comb_bits = n_bits >= 1024 ? 12 : 8;
+    if (const char* e = getenv("PB200_COMB_BITS")) { int v = atoi(e); if (v >= 4 && v <= 16) comb_bits = v; }
+    const int n_windows = (int)((n_bits + comb_bits - 1) / comb_bits);
+    key->n_sqr = 1; key->n_mul = (TABN - 1) + (uint64_t)(n_windows - 1) + 1;   // r^2; table; comb; gm*rn
     for (auto& o : ops) { key->n_sqr += (uint64_t)o.x; if (o.y >= 0) key->n_mul += 1; }
     CUK(cudaMalloc(&key->d_ops, (ops.size() + 1) * sizeof(int2)));
     if (!ops.empty()) CUK(cudaMemcpyAsync(key->d_ops, ops.data(), ops.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    int n_windows = (int)((n_bits + 7) / 8);
     uint32_t win = (n_bits + 63) / 64;
     std::vector<u64> gw(win);
     g.to_u64_le(gw.data(), win);
     CUK(cudaMalloc(&key->d_gwords, win * sizeof(u64)));
     CUK(cudaMemcpyAsync(key->d_gwords, gw.data(), win * sizeof(u64), cudaMemcpyHostToDevice, st));
-    CUK(cudaMalloc(&key->d_tg, (size_t)n_windows * 256 * C::ENTRY4 * sizeof(int4)));
+    CUK(cudaMalloc(&key->d_tg, ((size_t)n_windows << comb_bits) * C::ENTRY4 * sizeof(int4)));
     B28Dev& K = key->dev;
     K.consts = key->d_consts; K.ops = key->d_ops; K.n_ops = (int)ops.size(); K.first_idx = first_idx;
-    K.tg = key->d_tg; K.n_windows = n_windows; K.words_in = (int)win; K.words_out = (int)((2 * n_bits + 63) / 64);
+    K.tg = key->d_tg; K.n_windows = n_windows; K.comb_bits = comb_bits; K.words_in = (int)win; K.words_out = (int)((2 * n_bits + 63) / 64);
     K.sh = sh;
     K.sms = (unsigned)key->sms;
     K.nt_top = (unsigned)BigInt::shr(Nt, (size_t)W * (C::L - 2)).bits_at(0, 32);
