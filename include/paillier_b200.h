@@ -156,6 +156,15 @@ uint64_t pb200_witness_records_for(const pb200_key* key, const uint64_t* m_le);
 int pb200_encrypt_witness_digest(pb200_key* key, const uint64_t* m_le, const uint64_t* r_le, size_t count,
                                  uint64_t* c_out_le /* nullable */, uint64_t* digest_out);
 
+/* device-resident variant: d_m, d_r (count * words_in words), d_c_out (nullable, count * words_out words) and
+ * d_digest_out (count words) on the key's device; enqueued on the key's stream, no final synchronise, inputs
+ * are not range-checked (the host variant checks them against n_bits) */
+int pb200_encrypt_witness_digest_dev(pb200_key* key, const uint64_t* d_m_le, const uint64_t* d_r_le, size_t count,
+                                     uint64_t* d_c_out_le /* nullable */, uint64_t* d_digest_out);
+/* name of the engine that produces this key's witnesses: "block28w" (block28t arithmetic with an exact
+ * canonicalising tail per mul_mod) when the fast engine is selected and n has exactly n_bits bits, else "simple64" */
+const char* pb200_key_witness_engine(pb200_key* key);
+
 /* per-key g-chain squarings: record i (i < n_bits) = (q, rem) of (g^(2^i) mod n^2)^2 mod n^2.
  * out: n_bits * 2 * words_out words. */
 int pb200_key_g_chain(pb200_key* key, uint64_t* records_out);

@@ -67,6 +67,8 @@ SYMBOLS = {
     "pb200_encrypt_witness_batch": (C.c_int, [C.c_void_p, u64p, u64p, C.c_size_t, u64p, C.c_size_t, SINK_FN, C.c_void_p]),
     "pb200_witness_records_for": (C.c_uint64, [C.c_void_p, u64p]),
     "pb200_encrypt_witness_digest": (C.c_int, [C.c_void_p, u64p, u64p, C.c_size_t, u64p, u64p]),
+    "pb200_encrypt_witness_digest_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "pb200_key_witness_engine": (C.c_char_p, [C.c_void_p]),
     "pb200_key_g_chain": (C.c_int, [C.c_void_p, u64p]),
     "pb200_repack_limbs": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_uint32, C.c_uint32, u64p]),
 }

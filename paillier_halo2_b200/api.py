@@ -94,6 +94,11 @@ class PaillierKey:
     def engine(self) -> str:
         return self._lib.pb200_key_engine(self._h).decode()
 
+    @property
+    def witness_engine(self) -> str:
+        """Engine that produces this key's witnesses: "block28w" or "simple64"."""
+        return self._lib.pb200_key_witness_engine(self._h).decode()
+
     def set_engine(self, engine: int) -> None:
         check(self._lib.pb200_key_set_engine(self._h, engine), "pb200_key_set_engine")
 
@@ -115,6 +120,11 @@ class PaillierKey:
     def encrypt_dev(self, d_m: int, d_r: int, count: int, d_c: int) -> None:
         """Device-pointer variant (pb200_encrypt_batch_dev): enqueues on the key's stream, no synchronise."""
         check(self._lib.pb200_encrypt_batch_dev(self._h, d_m, d_r, count, d_c), "pb200_encrypt_batch_dev")
+
+    def encrypt_witness_digest_dev(self, d_m: int, d_r: int, count: int, d_c: int, d_digest: int) -> None:
+        """Device-pointer variant (pb200_encrypt_witness_digest_dev): enqueues on the key's stream, no synchronise."""
+        check(self._lib.pb200_encrypt_witness_digest_dev(self._h, d_m, d_r, count, d_c or None, d_digest),
+              "pb200_encrypt_witness_digest_dev")
 
     def tally_dev(self, d_c: int, count: int, d_out: int) -> None:
         check(self._lib.pb200_tally_dev(self._h, d_c, count, d_out), "pb200_tally_dev")

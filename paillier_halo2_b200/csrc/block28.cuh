@@ -27,6 +27,8 @@
 namespace pb200 {
 namespace b28 {
 
+typedef uint64_t u64w;
+
 constexpr int W = 28;
 constexpr int MARGIN = 10;
 
@@ -54,6 +56,7 @@ struct Cfg {
     // shared memory: V, B, Q (L digits each), T (2L digits), constants mu, Nt, two_sh, reversed s8 tables of mu, Nt
     static constexpr int SMEM_INT4 = 5 * VAL4 + 3 * ENTRY4 + 2 * RTAB4;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_INT4 * 16;
+    static constexpr size_t SMEM_W_BYTES = SMEM_BYTES + 128;          // witness kernel: + one int per lane (k estimate)
     // resident CTAs per SM the kernels are compiled for (shared memory and 64K registers / 128 per thread)
     static constexpr int BY_SMEM = (int)((227 * 1024) / SMEM_BYTES), BY_REGS = 512 / THREADS;
     static constexpr int CTAS_PER_SM = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
@@ -680,6 +683,196 @@ __device__ __forceinline__ void mulmod(Smem<C>& S, const int4* Y, int role, int 
         phase_mma<C, false>(base);
         low_to_value<C>(S, role, lane);
     }
+}
+
+
+// ---- witness step: exact (q, rem) of one mul_mod ------------------------------------------------------
+// Replaces the witness computation of BigUintChip::mul_mod (called from /root/reference/src/paillier.rs:51,55,57
+// through pow_mod_fixed_exp): q = floor(a b / n^2), rem = a b mod n^2, both canonical.
+//
+// Chain values are kept as strict digits of x * 2^s with 2s = sh_w, Nt_w = n^2 << sh_w (sh_w even).  Then
+//   T = (a 2^s)(b 2^s) = (a b) 2^sh_w,   floor(T / Nt_w) = q,   T mod Nt_w = rem 2^sh_w,
+// so the engine's own Barrett phases (A on IMAD, B and C on the tensor pipe) estimate q directly:
+// q-hat is within one of q (fuzzed in tests/model_block28.py), V' = lo(T) - lo(q-hat Nt_w) = rem 2^sh_w + k Nt_w
+// with k in {-1, 0}.  The tail below makes both exact, per lane, with all G warps working on their own block:
+//   1. k estimated from the two top digits of V' (double precision, off by one only next to a multiple of Nt_w);
+//   2. R = V' - k Nt_w and q = q-hat + k rippled to unsigned digits per block, block carries resolved through
+//      shared flags (a carry that runs through a whole block costs one more round; rounds are counted with
+//      __syncthreads_or, typically two);
+//   3. range check R in [0, Nt_w) by per-block comparison; the rare miss adds/subtracts Nt_w once more;
+//   4. q and rem = R >> sh_w packed into 64-bit words (the record), hashed, optionally stored;
+//   5. the next chain operand, strict digits of rem 2^s = R >> s, written to `next_dst`.
+template <class C> __device__ __forceinline__ int* west_ptr(Smem<C>& S) { return (int*)(S.rnt + (size_t)C::RTAB4 * 16); }
+
+struct WStep {             // per-step outputs of one lane (null = not wanted)
+    u64w* rec;             // 2*words_out words: q then rem
+    u64w* rem_out;         // words_out words: rem only (the ciphertext of the final step)
+};
+
+template <int L>
+__device__ __forceinline__ u64w extract64(const int* F, int bit, int lane) {
+    const int p = bit / W, off = bit - p * W;
+    u64w w = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int pp = p + i;
+        const u64w d = pp < L ? (u64w)(unsigned)F[pp * 32 + lane] : (u64w)0;
+        const int sft = W * i - off;
+        if (i == 0) w = d >> off;
+        else if (sft < 64) w |= d << sft;
+    }
+    return w;
+}
+
+template <int BL>
+__device__ __forceinline__ int add_carry_block(int (&d)[BL], int cin) {
+    if (!cin) return 0;
+    int c = cin;
+#pragma unroll
+    for (int k = 0; k < BL; k++) { int t = d[k] + c; d[k] = t & ((1 << W) - 1); c = t >> W; }
+    return c;
+}
+
+template <class C>
+__device__ __noinline__ u64w w_tail(int4* smem_base, int4* next_dst, WStep out, int sh, int words_out,
+                                                  double inv, const u64w* __restrict__ cpow) {
+    constexpr int G = C::G, BL = C::BL, L = C::L, MSK = (1 << W) - 1;
+    Smem<C> S(smem_base);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* est = west_ptr<C>(S);
+    int* scr = (int*)S.Q;                         // the s8 rows are dead once q-hat has been decoded
+    int* cfR[2] = {scr, scr + G * 32};
+    int* cfQ[2] = {scr + 2 * G * 32, scr + 3 * G * 32};
+    int* cmpf = scr + 4 * G * 32;
+    u64w* hsum = (u64w*)(scr + 5 * G * 32);
+    const int* LO = lo_ptr<C>(S);
+    const int* CA = ca_ptr<C>(S);
+    const int* ntu = (const int*)S.two_sh + warp * C::CH * 4;      // unsigned digits of Nt_w, this block (broadcast reads)
+    // raw digits of V' = lo(T) - lo(q-hat Nt_w) and the digits of q-hat, this block
+    int rd[BL], qd[BL];
+    {
+        int a[C::CH * 4];
+        load_block<C>(a, blk_ptr<C>(S.T, warp, lane), 32);
+        const unsigned* row = (const unsigned*)(as_ptr<C>(S) + lane * C::RS) + warp * BL;
+#pragma unroll
+        for (int k = 0; k < BL; k++) {
+            const int j = warp * BL + k;
+            rd[k] = a[k] - LO[dl_index(j, lane)] - (j > 0 ? CA[dl_index(j, lane)] : 0);
+            const unsigned v = row[k];
+            qd[k] = ((int)(v << 24) >> 24) + (((int)(v << 16) >> 24) << 7) + (((int)(v << 8) >> 24) << 14) + (((int)v >> 24) << 21);
+        }
+    }
+    if (warp == G - 1) {       // k estimate: strict top two digits of V' (computed mod 2^(28L), |V'| < 2^beta)
+        int carry = 0, d_hi = 0, d_lo = 0;
+#pragma unroll
+        for (int k = 0; k < BL; k++) {
+            int t = rd[k] + carry + (1 << (W - 1));
+            carry = t >> W;
+            int d = (t & MSK) - (1 << (W - 1));
+            if (k == BL - 2) d_lo = d;
+            if (k == BL - 1) d_hi = d;
+        }
+        double vt = (double)d_hi * 268435456.0 + (double)d_lo;
+        int ke = (int)floor(vt * inv);
+        est[lane] = ke < -3 ? -3 : (ke > 3 ? 3 : ke);
+    }
+    __syncthreads();
+    int adj = est[lane];
+    int rnd = 0;
+    bool first = true;
+    for (;;) {
+        // R -= adj * Nt_w, q += adj: local ripples to unsigned digits
+        int cR = 0, cQ = (warp == 0) ? adj : 0;
+        if (first || adj) {
+#pragma unroll
+            for (int k = 0; k < BL; k++) { int t = rd[k] - adj * ntu[k] + cR; rd[k] = t & MSK; cR = t >> W; }
+#pragma unroll
+            for (int k = 0; k < BL; k++) { int t = qd[k] + cQ; qd[k] = t & MSK; cQ = t >> W; }
+        } else cQ = 0;
+        first = false;
+        for (;;) {             // carries between blocks (numbers are taken mod 2^(28L): the top block's carry leaves)
+            if (warp == G - 1) { cR = 0; cQ = 0; }
+            cfR[rnd][warp * 32 + lane] = cR; cfQ[rnd][warp * 32 + lane] = cQ;
+            if (!__syncthreads_or((cR | cQ) != 0)) break;
+            const int iR = warp ? cfR[rnd][(warp - 1) * 32 + lane] : 0, iQ = warp ? cfQ[rnd][(warp - 1) * 32 + lane] : 0;
+            cR = add_carry_block<BL>(rd, iR);
+            cQ = add_carry_block<BL>(qd, iQ);
+            rnd ^= 1;
+        }
+        // R in [0, Nt_w)?  negative values show as a top digit >= 2^27
+        int cmp = 0;
+#pragma unroll
+        for (int k = 0; k < BL; k++) if (rd[k] != ntu[k]) cmp = rd[k] > ntu[k] ? 1 : -1;
+        if (warp == G - 1 && rd[BL - 1] >= (1 << (W - 1))) cmp = -2;
+        cmpf[warp * 32 + lane] = cmp;
+        __syncthreads();
+        int c = 0;
+#pragma unroll
+        for (int b = G - 1; b >= 0; b--) { const int f = cmpf[b * 32 + lane]; if (c == 0) c = f; }
+        adj = c == -2 ? -1 : (c >= 0 ? 1 : 0);
+        if (!__syncthreads_or(adj != 0)) break;
+        rnd ^= 1;
+    }
+    // canonical digits, flat [digit][lane], over the T buffer: R then q
+    int* Rf = (int*)S.T;
+    int* Qf = Rf + L * 32;
+#pragma unroll
+    for (int k = 0; k < BL; k++) { Rf[(warp * BL + k) * 32 + lane] = rd[k]; Qf[(warp * BL + k) * 32 + lane] = qd[k]; }
+    __syncthreads();
+    // record words: q = bits [64j, 64j+64) of q, rem = the same bits of R >> sh
+    u64w h = 0;
+    const int wpw = (words_out + G - 1) / G;
+    for (int i = 0; i < wpw; i++) {
+        const int j = warp * wpw + i;
+        if (j < words_out) {
+            const u64w wq = extract64<L>(Qf, 64 * j, lane), wr = extract64<L>(Rf, 64 * j + sh, lane);
+            h += wq * cpow[j] + wr * cpow[words_out + j];
+            if (out.rec) { out.rec[j] = wq; out.rec[words_out + j] = wr; }
+            if (out.rem_out) out.rem_out[j] = wr;
+        }
+    }
+    hsum[warp * 32 + lane] = h;
+    int carry = 0;
+    if (next_dst) {            // strict digits of R >> s (= rem 2^s), this block
+        const int s = sh >> 1, pd = s / W, off = s - pd * W;
+        int a[C::CH * 4];
+#pragma unroll
+        for (int k = 0; k < BL; k++) {
+            const int p = warp * BL + k + pd;
+            const unsigned lo = p < L ? (unsigned)Rf[p * 32 + lane] : 0u, hi = p + 1 < L ? (unsigned)Rf[(p + 1) * 32 + lane] : 0u;
+            const int x = (int)(((lo >> off) | (off ? hi << (W - off) : 0u)) & MSK);
+            const int t = x + carry + (1 << (W - 1));
+            carry = t >> W;
+            a[k] = (t & MSK) - (1 << (W - 1));
+        }
+#pragma unroll
+        for (int k = BL; k < C::CH * 4; k++) a[k] = 0;
+        store_block<C>(blk_ptr<C>(next_dst, warp, lane), a);
+    }
+    __syncthreads();
+    if (next_dst && warp + 1 < G) *(int*)blk_ptr<C>(next_dst, warp + 1, lane) += carry;
+    u64w H = 0;
+    if (warp == 0) {
+#pragma unroll
+        for (int b = 0; b < G; b++) H += hsum[b * 32 + lane];
+    }
+    __syncthreads();
+    return H;
+}
+
+// one witnessed mul_mod: operands V (and Y, or V itself when sqr) are strict digits of a 2^s, b 2^s with a, b canonical;
+// V is preserved.  Returns the record hash (valid in warp 0).
+template <class C>
+__device__ __forceinline__ u64w mulmod_w(int4* smem_base, const int4* Y, int sqr, int4* next_dst, WStep out,
+                                                       int sh, int words_out, double inv, const u64w* cpow) {
+    Smem<C> S(smem_base);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    phase_product<C>(smem_base, Y, sqr);
+    q1_to_bytes<C>(S, role, lane);
+    phase_mma<C, true>(smem_base);
+    qhat_to_bytes<C>(S, role, lane);
+    phase_mma<C, false>(smem_base);
+    return w_tail<C>(smem_base, next_dst, out, sh, words_out, inv, cpow);
 }
 
 }  // namespace b28

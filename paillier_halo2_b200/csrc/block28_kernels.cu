@@ -308,6 +308,170 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, 
     finalize<C, MMA>(S, K, out + (size_t)blockIdx.x * K.words_out, lane == 0, role, lane);
 }
 
+
+// ---- witness kernels (reference chain with exact (q, rem) per mul_mod) ---------------------------------
+struct WitDev {
+    const int4* gtab;          // [n_bits][ENTRY4]: strict digits of (g^(2^i) mod n^2) * 2^s   (i = 0: g itself)
+    const int4* one_s;         // ENTRY4: 2^s
+    const u64* cpow;           // C^(j+1), j < 2*words_out (record hash, include/paillier_b200.h)
+    const u64* n_words;        // exponent of the r-chain
+    int exp_bits;              // bits(n)
+    int sh;                    // Nt_w = n^2 << sh, sh even; chain values carry the factor 2^(sh/2)
+    double inv;                // 2^(28(L-2)) / Nt_w
+};
+struct WitIO {
+    const u64* m; const u64* r; size_t count;
+    u64* c_out;                // nullable
+    u64* records; const u64* offsets;   // nullable: unit u's records start at record index offsets[u]
+    u64* digest;               // nullable
+    int4* scratch;             // 2 values per CTA: acc of the r-chain, gm
+};
+
+// per-lane buffer <- strict digits of (src << shl)
+template <class C>
+__device__ __forceinline__ void load_value_shl(int4* buf, const u64* src, int nwords, int shl, int role, int lane) {
+    int a[C::CH * 4];
+    int carry = 0;
+#pragma unroll
+    for (int k = 0; k < C::BL; k++) {
+        const int bit = W * (role * C::BL + k) - shl;
+        u64 v = 0;
+        if (bit >= 0) {
+            const int wi = bit >> 6, sh = bit & 63;
+            const u64 lo = wi < nwords ? src[wi] : 0, hi = wi + 1 < nwords ? src[wi + 1] : 0;
+            v = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+        } else if (bit > -W) {
+            v = src[0] << (-bit);
+        }
+        const int t = (int)(v & ((1u << W) - 1)) + carry;
+        const int d = sgxt28(t);
+        carry = (t - d) >> W;
+        a[k] = d;
+    }
+#pragma unroll
+    for (int k = C::BL; k < C::CH * 4; k++) a[k] = 0;
+    store_block<C>(blk_ptr<C>(buf, role, lane), a);
+    __syncthreads();
+    if (role + 1 < C::G) *(int*)blk_ptr<C>(buf, role + 1, lane) += carry;
+    __syncthreads();
+}
+
+// table entries of the witness chain from 64-bit words: entry i = strict digits of (value_i << shl), one thread per entry.
+// value_0 = g (words_in words); value_i = rem of g-chain record i-1 (words_out words at gchain + (i-1)*2*wo + wo)
+template <class C>
+__global__ void k_wtab(const u64* __restrict__ g_words, int words_in, const u64* __restrict__ gchain, int words_out,
+                       int n_entries, int shl, int4* __restrict__ gtab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_entries) return;
+    const u64* src = i == 0 ? g_words : gchain + (size_t)(i - 1) * 2 * words_out + words_out;
+    const int nwords = i == 0 ? words_in : words_out;
+    int* dst = (int*)(gtab + (size_t)i * C::ENTRY4);
+    for (int k = 0; k < C::ENTRY4 * 4; k++) dst[k] = 0;
+    int carry = 0;
+    for (int p = 0; p < C::L; p++) {
+        const int bit = W * p - shl;
+        u64 v = 0;
+        if (bit >= 0) {
+            const int wi = bit >> 6, sh = bit & 63;
+            const u64 lo = wi < nwords ? src[wi] : 0, hi = wi + 1 < nwords ? src[wi + 1] : 0;
+            v = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+        } else if (bit > -W) {
+            v = src[0] << (-bit);
+        }
+        const int t = (int)(v & ((1u << W) - 1)) + carry;
+        const int d = sgxt28(t);
+        carry = (t - d) >> W;
+        dst[(p / C::BL) * C::CH * 4 + (p % C::BL)] = d;
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void bcast_entry(int4* buf, const int4* entry, int role, int lane) {
+#pragma unroll
+    for (int c = 0; c < C::CH; c++) buf[(role * C::CH + c) * 32 + lane] = __ldg(entry + role * C::CH + c);
+    __syncthreads();
+}
+
+// One unit per lane, the reference's chain (src/paillier.rs:51,55,57 -> pow_mod_fixed_exp):
+//   g-chain: the popcount(m) multiplications acc *= g^(2^i) (the squarings are per key: gtab);
+//   r-chain: for every bit i of n, sqr_i = cur^2 and, if the bit is set, acc *= cur; then gm * rn.
+// Lanes walk their own set bits of m (inactive lanes multiply by one and emit nothing); the r-chain is uniform.
+// In the r-chain the multiplication of an iteration is computed BEFORE its squaring (cur stays in V), the
+// records keep the reference's order (sqr_i, then mul_i).
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_witness(B28Dev K, WitDev Wd, WitIO A) {
+    extern __shared__ int4 smem[];
+    Smem<C> S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    load_consts<C>(smem, K);
+    size_t unit = (size_t)blockIdx.x * 32 + lane;
+    const bool active = unit < A.count;
+    if (!active) unit = A.count - 1;
+    const int wo = K.words_out;
+    const size_t recw = 2 * (size_t)wo;
+    const u64* mw = A.m + unit * K.words_in;
+    int pc = 0;
+    for (int w = 0; w < K.words_in; w++) pc += __popcll(mw[w]);
+    int maxpc = pc;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) maxpc = max(maxpc, __shfl_xor_sync(0xffffffffu, maxpc, off));
+    u64* rec = (A.records && active) ? A.records + A.offsets[unit] * recw : nullptr;
+    u64 D = PB200_DIGEST_INIT;                                    // running digest of the unit (kept by warp 0)
+    int4* sc_acc = A.scratch + (size_t)blockIdx.x * 2 * C::VAL4;
+    int4* sc_gm = sc_acc + C::VAL4;
+    // ---- g-chain
+    bcast_entry<C>(S.V, Wd.one_s, role, lane);
+    {
+        int wi = 0; u64 cur = mw[0];
+        for (int t = 0; t < maxpc; t++) {
+            const bool act = t < pc;
+            const int4* e = Wd.one_s;
+            if (act) {
+                while (!cur) cur = mw[++wi];
+                const int b = __ffsll((long long)cur) - 1;
+                cur &= cur - 1;
+                e = Wd.gtab + (size_t)(64 * wi + b) * C::ENTRY4;
+            }
+            bcast_entry<C>(S.B, e, role, lane);
+            WStep o; o.rec = (act && rec) ? rec + (size_t)t * recw : nullptr; o.rem_out = nullptr;
+            const u64 H = mulmod_w<C>(smem, S.B, 0, S.V, o, Wd.sh, wo, Wd.inv, Wd.cpow);
+            if (act) D = (D ^ H) * PB200_DIGEST_PRIME;
+        }
+    }
+    copy_to_global<C>(sc_gm, S.V, role, lane);
+    // ---- r-chain
+    bcast_entry<C>(S.B, Wd.one_s, role, lane);
+    copy_to_global<C>(sc_acc, S.B, role, lane);
+    load_value_shl<C>(S.V, A.r + unit * K.words_in, K.words_in, Wd.sh >> 1, role, lane);
+    size_t idx = (size_t)pc;
+    for (int i = 0; i < Wd.exp_bits; i++) {
+        const bool bit = (Wd.n_words[i >> 6] >> (i & 63)) & 1;
+        u64 Hm = 0;
+        if (bit) {
+            copy_from_global<C>(S.B, sc_acc, role, lane);
+            WStep o; o.rec = rec ? rec + (idx + 1) * recw : nullptr; o.rem_out = nullptr;
+            Hm = mulmod_w<C>(smem, S.B, 0, S.B, o, Wd.sh, wo, Wd.inv, Wd.cpow);
+            copy_to_global<C>(sc_acc, S.B, role, lane);
+        }
+        WStep o; o.rec = rec ? rec + idx * recw : nullptr; o.rem_out = nullptr;
+        const u64 Hs = mulmod_w<C>(smem, nullptr, 1, S.V, o, Wd.sh, wo, Wd.inv, Wd.cpow);
+        D = (D ^ Hs) * PB200_DIGEST_PRIME;
+        if (bit) D = (D ^ Hm) * PB200_DIGEST_PRIME;
+        idx += bit ? 2 : 1;
+    }
+    // ---- final: mul_mod(gm, rn)
+    __syncthreads();
+    copy_from_global<C>(S.V, sc_gm, role, lane);
+    copy_from_global<C>(S.B, sc_acc, role, lane);
+    {
+        WStep o; o.rec = rec ? rec + idx * recw : nullptr;
+        o.rem_out = (A.c_out && active) ? A.c_out + unit * wo : nullptr;
+        const u64 H = mulmod_w<C>(smem, S.B, 0, nullptr, o, Wd.sh, wo, Wd.inv, Wd.cpow);
+        D = (D ^ H) * PB200_DIGEST_PRIME;
+    }
+    if (role == 0 && active && A.digest) A.digest[unit] = D;
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 struct Block28Key {
     int G = 0, BL = 0;
@@ -319,6 +483,12 @@ struct Block28Key {
     int sms = 148;
     uint64_t n_sqr = 0, n_mul = 0;   // modular squarings / multiplications per encryption
     bool use_mma = true;             // constant-operand phases on the tensor pipe (engine 3) or on IMAD (engine 2)
+    // witness engine (lazy: block28_witness_prepare)
+    BigInt n; uint32_t n_bits = 0;
+    bool wit_ready = false;
+    int4* d_wconsts = nullptr; int4* d_gtab = nullptr; int4* d_one_s = nullptr; u64* d_cpow = nullptr; u64* d_nwords = nullptr;
+    int4* d_wscratch = nullptr; size_t wscratch_ctas = 0;
+    B28Dev wdev{}; WitDev wit{};
 };
 
 template <class C>
@@ -359,6 +529,7 @@ template <class C>
 static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits, int device, cudaStream_t st, cudaError_t* cuda_err) {
     Block28Key* key = new Block28Key();
     key->G = C::G; key->BL = C::BL;
+    key->n = n; key->n_bits = n_bits;
     key->name = "block28t<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">";
     cudaDeviceProp prop;
     CUK(cudaGetDeviceProperties(&prop, device));
@@ -477,6 +648,76 @@ static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64*
     return cudaGetLastError();
 }
 
+
+// ---- witness engine: per-key constants and launcher ------------------------------------------------------
+#define CUW(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+
+template <class C>
+static cudaError_t witness_prepare_cfg(Block28Key* key, const u64* d_gchain, cudaStream_t st) {
+    const BigInt& n = key->n;
+    BigInt n2 = BigInt::mul(n, n);
+    int sh = C::KN - (int)n2.bits();
+    if (sh & 1) sh -= 1;                                   // chain values carry 2^(sh/2)
+    BigInt Nt = BigInt::shl(n2, sh);
+    BigInt mu = BigInt::div(BigInt::pow2(2 * (size_t)C::BETA), Nt);
+    std::vector<int> e_mu, e_nt, e_ntu(C::ENTRY4 * 4, 0), e_one, all;
+    to_entry<C>(mu, e_mu); to_entry<C>(Nt, e_nt); to_entry<C>(BigInt::pow2(sh / 2), e_one);
+    for (int p = 0; p < C::L; p++) e_ntu[(p / C::BL) * C::CH * 4 + (p % C::BL)] = (int)Nt.bits_at((size_t)W * p, W);
+    all.insert(all.end(), e_mu.begin(), e_mu.end());
+    all.insert(all.end(), e_nt.begin(), e_nt.end());
+    all.insert(all.end(), e_ntu.begin(), e_ntu.end());     // in the slot the value engine uses for 2^sh
+    std::vector<int> r_mu, r_nt;
+    to_rtab<C>(e_mu, r_mu); to_rtab<C>(e_nt, r_nt);
+    all.insert(all.end(), r_mu.begin(), r_mu.end());
+    all.insert(all.end(), r_nt.begin(), r_nt.end());
+    CUW(cudaMalloc(&key->d_wconsts, all.size() * sizeof(int)));
+    CUW(cudaMemcpyAsync(key->d_wconsts, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUW(cudaMalloc(&key->d_one_s, e_one.size() * sizeof(int)));
+    CUW(cudaMemcpyAsync(key->d_one_s, e_one.data(), e_one.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int wo = key->dev.words_out, wi = key->dev.words_in;
+    std::vector<u64> cpow(2 * (size_t)wo);
+    { u64 c = PB200_DIGEST_C; for (size_t j = 0; j < cpow.size(); j++) { cpow[j] = c; c *= PB200_DIGEST_C; } }
+    CUW(cudaMalloc(&key->d_cpow, cpow.size() * sizeof(u64)));
+    CUW(cudaMemcpyAsync(key->d_cpow, cpow.data(), cpow.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    std::vector<u64> nw(wi);
+    n.to_u64_le(nw.data(), wi);
+    CUW(cudaMalloc(&key->d_nwords, nw.size() * sizeof(u64)));
+    CUW(cudaMemcpyAsync(key->d_nwords, nw.data(), nw.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CUW(cudaMalloc(&key->d_gtab, (size_t)key->n_bits * C::ENTRY4 * sizeof(int4)));
+    k_wtab<C><<<(key->n_bits + 63) / 64, 64, 0, st>>>(key->d_gwords, wi, d_gchain, wo, (int)key->n_bits, sh / 2, key->d_gtab);
+    count_launch();
+    CUW(cudaGetLastError());
+    CUW(cudaStreamSynchronize(st));                        // the staging vectors above go out of scope
+    // 2^(28(L-2)) / Nt_w from the top 52 bits of Nt_w
+    BigInt top = BigInt::shr(Nt, (size_t)W * (C::L - 2) - 20);
+    double topd = (double)top.bits_at(32, 32) * 4294967296.0 + (double)top.bits_at(0, 32);
+    key->wdev = key->dev; key->wdev.consts = key->d_wconsts; key->wdev.sh = sh;
+    WitDev& Wd = key->wit;
+    Wd.gtab = key->d_gtab; Wd.one_s = key->d_one_s; Wd.cpow = key->d_cpow; Wd.n_words = key->d_nwords;
+    Wd.exp_bits = (int)n.bits(); Wd.sh = sh; Wd.inv = 1048576.0 / topd;
+    CUW(cudaFuncSetAttribute(k_witness<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES));
+    key->wit_ready = true;
+    return cudaSuccess;
+}
+
+template <class C>
+static cudaError_t witness_cfg(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, u64* d_records,
+                               const u64* d_offsets, u64* d_digest, cudaStream_t st) {
+    size_t ctas = (count + 31) / 32;
+    if (ctas > key->wscratch_ctas) {
+        if (key->d_wscratch) cudaFree(key->d_wscratch);
+        key->d_wscratch = nullptr; key->wscratch_ctas = 0;
+        CUW(cudaMalloc(&key->d_wscratch, ctas * 2 * C::VAL4 * sizeof(int4)));
+        key->wscratch_ctas = ctas;
+    }
+    WitIO A;
+    A.m = d_m; A.r = d_r; A.count = count; A.c_out = d_c; A.records = d_records; A.offsets = d_offsets; A.digest = d_digest;
+    A.scratch = key->d_wscratch;
+    k_witness<C><<<(unsigned)ctas, C::THREADS, C::SMEM_W_BYTES, st>>>(key->wdev, key->wit, A);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // Compiled configurations <G warps, BL digits per block>: L = G*BL digits of 28 bits; n^2 must fit KN - 2 bits.
 typedef Cfg<4, 19> Cfg1024;    // L =  76: n^2 up to 2102 bits (|n| <= 1024 and the reference's default sizes)
 typedef Cfg<8, 19> Cfg2048;    // L = 152: n^2 up to 4230 bits (|n| <= 2048)
@@ -504,6 +745,12 @@ void block28_destroy(Block28Key* key) {
     if (key->d_gwords) cudaFree(key->d_gwords);
     if (key->d_scratch) cudaFree(key->d_scratch);
     if (key->d_partials) cudaFree(key->d_partials);
+    if (key->d_wconsts) cudaFree(key->d_wconsts);
+    if (key->d_gtab) cudaFree(key->d_gtab);
+    if (key->d_one_s) cudaFree(key->d_one_s);
+    if (key->d_cpow) cudaFree(key->d_cpow);
+    if (key->d_nwords) cudaFree(key->d_nwords);
+    if (key->d_wscratch) cudaFree(key->d_wscratch);
     delete key;
 }
 const char* block28_name(const Block28Key* key) { return key->name.c_str(); }
@@ -523,6 +770,28 @@ cudaError_t block28_tally(Block28Key* key, const u64* d_c, size_t count, u64* d_
     if (key->G == 8) return tally_cfg<Cfg2048>(key, d_c, count, d_out, st);
     if (key->BL == 14) return tally_cfg<Cfg3072>(key, d_c, count, d_out, st);
     return tally_cfg<Cfg4096>(key, d_c, count, d_out, st);
+}
+
+
+// The witness engine needs canonical chain values below n^2 from the first step on: n must fill its declared width
+// (then g, r < 2^n_bits <= 2n <= n^2).  Other keys keep the simple64 witness path.
+bool block28_witness_supported(const Block28Key* key) { return key->use_mma && key->n.bits() == key->n_bits && key->n_bits >= 8; }
+cudaError_t block28_witness_prepare(Block28Key* key, const u64* d_gchain, cudaStream_t st) {
+    if (key->wit_ready) return cudaSuccess;
+    try {
+        if (key->G == 4) return witness_prepare_cfg<Cfg1024>(key, d_gchain, st);
+        if (key->G == 8) return witness_prepare_cfg<Cfg2048>(key, d_gchain, st);
+        if (key->BL == 14) return witness_prepare_cfg<Cfg3072>(key, d_gchain, st);
+        return witness_prepare_cfg<Cfg4096>(key, d_gchain, st);
+    } catch (const std::exception&) { return cudaErrorInvalidValue; }
+}
+cudaError_t block28_witness(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, u64* d_records,
+                            const u64* d_offsets, u64* d_digest, cudaStream_t st) {
+    if (!count) return cudaSuccess;
+    if (key->G == 4) return witness_cfg<Cfg1024>(key, d_m, d_r, count, d_c, d_records, d_offsets, d_digest, st);
+    if (key->G == 8) return witness_cfg<Cfg2048>(key, d_m, d_r, count, d_c, d_records, d_offsets, d_digest, st);
+    if (key->BL == 14) return witness_cfg<Cfg3072>(key, d_m, d_r, count, d_c, d_records, d_offsets, d_digest, st);
+    return witness_cfg<Cfg4096>(key, d_m, d_r, count, d_c, d_records, d_offsets, d_digest, st);
 }
 
 }  // namespace pb200

@@ -186,6 +186,25 @@ static int ensure_gchain(pb200_key* k) {
     return PB200_OK;
 }
 
+// witness producer for this key: the block28t witness engine when the fast engine is selected and n fills its
+// declared width, else simple64 (both on the GPU).  Prepares the per-key tables on first use.
+static int witness_engine(pb200_key* k, bool* fast) {
+    *fast = false;
+    int rc = ensure_gchain(k); if (rc) return rc;
+    if (!use_fast(k) || !block28_witness_supported(k->fast)) return PB200_OK;
+    CU(block28_witness_prepare(k->fast, k->d_gchain, k->stream));
+    *fast = true;
+    return PB200_OK;
+}
+static int run_witness(pb200_key* k, const u64* d_m, const u64* d_r, size_t count, u64* d_c, u64* d_records,
+                       const u64* d_offsets, u64* d_digest) {
+    bool fast = false;
+    int rc = witness_engine(k, &fast); if (rc) return rc;
+    if (fast) CU(block28_witness(k->fast, d_m, d_r, count, d_c, d_records, d_offsets, d_digest, k->stream));
+    else CU(simple_encrypt(k->d_simple, k->d_gchain, d_m, d_r, count, d_c, d_records, d_offsets, d_digest, k->d_flags, k->stream));
+    return PB200_OK;
+}
+
 // ---- encrypt --------------------------------------------------------------------------------
 int pb200_encrypt_batch_dev(pb200_key* k, const uint64_t* d_m, const uint64_t* d_r, size_t count, uint64_t* d_c) {
     if (!k || (count && (!d_m || !d_r || !d_c))) return PB200_ERR_INVALID_ARG;
@@ -303,7 +322,6 @@ int pb200_encrypt_witness_batch(pb200_key* k, const uint64_t* m, const uint64_t*
     int rc = check_inputs(k, m, count); if (rc) return rc;
     rc = check_inputs(k, r, count); if (rc) return rc;
     CU(cudaSetDevice(k->device));
-    rc = ensure_gchain(k); if (rc) return rc;
     const size_t rec_words = 2 * (size_t)k->words_out;
     uint64_t fixed = pb200_witness_records_for(k, m) - popcount_words(m, k->words_in);  // bits(n)+popcount(n)+1
     size_t max_unit_records = (size_t)fixed + k->n_bits;
@@ -329,8 +347,9 @@ int pb200_encrypt_witness_batch(pb200_key* k, const uint64_t* m, const uint64_t*
         CU(cudaMemcpyAsync(k->in_a.p, m + first * k->words_in, bin, cudaMemcpyHostToDevice, k->stream));
         CU(cudaMemcpyAsync(k->in_b.p, r + first * k->words_in, bin, cudaMemcpyHostToDevice, k->stream));
         CU(cudaMemcpyAsync(k->offs.p, offsets.data(), (nu + 1) * sizeof(u64), cudaMemcpyHostToDevice, k->stream));
-        CU(simple_encrypt(k->d_simple, k->d_gchain, (const u64*)k->in_a.p, (const u64*)k->in_b.p, nu, (u64*)k->out_a.p,
-                          (u64*)k->scratch.p, (const u64*)k->offs.p, nullptr, k->d_flags, k->stream));
+        rc = run_witness(k, (const u64*)k->in_a.p, (const u64*)k->in_b.p, nu, (u64*)k->out_a.p, (u64*)k->scratch.p,
+                         (const u64*)k->offs.p, nullptr);
+        if (rc) return rc;
         host_records.resize(total_records * rec_words);
         CU(cudaMemcpyAsync(host_records.data(), k->scratch.p, total_records * rec_words * sizeof(u64), cudaMemcpyDeviceToHost, k->stream));
         if (c_out) CU(cudaMemcpyAsync(c_out + first * k->words_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
@@ -351,17 +370,28 @@ int pb200_encrypt_witness_digest(pb200_key* k, const uint64_t* m, const uint64_t
     int rc = check_inputs(k, m, count); if (rc) return rc;
     rc = check_inputs(k, r, count); if (rc) return rc;
     CU(cudaSetDevice(k->device));
-    rc = ensure_gchain(k); if (rc) return rc;
     size_t bin = count * k->words_in * sizeof(u64), bout = count * k->words_out * sizeof(u64);
     CU(k->in_a.reserve(bin)); CU(k->in_b.reserve(bin)); CU(k->out_a.reserve(bout)); CU(k->out_b.reserve(count * sizeof(u64)));
     CU(cudaMemcpyAsync(k->in_a.p, m, bin, cudaMemcpyHostToDevice, k->stream));
     CU(cudaMemcpyAsync(k->in_b.p, r, bin, cudaMemcpyHostToDevice, k->stream));
-    CU(simple_encrypt(k->d_simple, k->d_gchain, (const u64*)k->in_a.p, (const u64*)k->in_b.p, count, (u64*)k->out_a.p,
-                      nullptr, nullptr, (u64*)k->out_b.p, k->d_flags, k->stream));
+    rc = run_witness(k, (const u64*)k->in_a.p, (const u64*)k->in_b.p, count, (u64*)k->out_a.p, nullptr, nullptr, (u64*)k->out_b.p);
+    if (rc) return rc;
     CU(cudaMemcpyAsync(digest_out, k->out_b.p, count * sizeof(u64), cudaMemcpyDeviceToHost, k->stream));
     if (c_out) CU(cudaMemcpyAsync(c_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
     CU(cudaStreamSynchronize(k->stream));
     return take_flags(k);
+}
+
+int pb200_encrypt_witness_digest_dev(pb200_key* k, const uint64_t* d_m, const uint64_t* d_r, size_t count, uint64_t* d_c,
+                                     uint64_t* d_digest) {
+    if (!k || !d_digest || (count && (!d_m || !d_r))) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    CU(cudaSetDevice(k->device));
+    return run_witness(k, (const u64*)d_m, (const u64*)d_r, count, (u64*)d_c, nullptr, nullptr, (u64*)d_digest);
+}
+const char* pb200_key_witness_engine(pb200_key* k) {
+    if (!k) return "";
+    return (use_fast(k) && block28_witness_supported(k->fast)) ? "block28w" : "simple64";
 }
 
 // ---- limb formatting ------------------------------------------------------------------------

@@ -39,5 +39,11 @@ void block28_set_mma(Block28Key*, bool on);   // constant-operand phases on the 
 void block28_chain_counts(const Block28Key*, uint64_t* n_sqr, uint64_t* n_mul);
 cudaError_t block28_encrypt(Block28Key*, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st);
 cudaError_t block28_tally(Block28Key*, const u64* d_c, size_t count, u64* d_out, cudaStream_t st);
+// witness engine: the reference's chain with exact (q, rem) per mul_mod (block28t arithmetic + exact tail)
+bool block28_witness_supported(const Block28Key*);
+cudaError_t block28_witness_prepare(Block28Key*, const u64* d_gchain /* simple64 g-chain records */, cudaStream_t st);
+cudaError_t block28_witness(Block28Key*, const u64* d_m, const u64* d_r, size_t count, u64* d_c /*nullable*/,
+                            u64* d_records /*nullable*/, const u64* d_offsets /*nullable*/, u64* d_digest /*nullable*/,
+                            cudaStream_t st);
 
 }  // namespace pb200

@@ -302,3 +302,149 @@ def mulmod_imma(P, keyc, A, B, sqr=False):
         c = (t - d) >> W
         out.append(d)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Witness step (block28.cuh: w_tail / mulmod_w): exact (q, rem) of one mul_mod on canonical operands.
+# Chain values are kept as strict digits of x * 2^s, 2s = sh_w, Nt_w = n^2 << sh_w.
+
+def witness_key(P, N: int):
+    """per-key constants of the witness engine: sh_w even"""
+    sh = P.kN - N.bit_length()
+    if sh & 1:
+        sh -= 1
+    Nt = N << sh
+    mu = (1 << (2 * P.beta)) // Nt
+    assert mu.bit_length() <= W * P.L - 1
+    inv = float(1 << 20) / float(Nt >> (W * (P.L - 2) - 20))
+    return (sh, Nt, mu), inv
+
+
+def _imma_parts(P, keyc, A, B, sqr):
+    """phases A, B, C of mulmod_imma, returning T digits, q-hat digits and the raw (unrippled) digits of V'"""
+    L = P.L
+    X = product(P, A, B, 2 * P.G, "full", sqr)
+    q1 = X[L - 1:2 * L - 1]
+    q1[L - 1] += X[2 * L - 1] << W
+    Nt_d, mu_d = keyc_digits(P, keyc)
+    cols = conv_columns(digits7(q1), digits7(mu_d), 4 * (L - 2), 4 * 2 * L)
+    lo, carry = fold28(cols)
+    qh, c = [], 0
+    for jj in range(len(lo)):
+        t = lo[jj] + (carry[jj - 1] if jj else 0) + c
+        d = sgxt(t)
+        c = (t - d) >> W
+        if jj >= 2:
+            qh.append(d)
+    qh = qh[:L]
+    cols = conv_columns(digits7(qh), digits7(Nt_d), 0, 4 * L)
+    lo, carry = fold28(cols)
+    raw = [X[j] - lo[j] - (carry[j - 1] if j else 0) for j in range(L)]
+    return qh, raw
+
+
+def _resolve(P, digs, couts):
+    """carries between blocks through flags, one round per barrier; the top block's carry leaves (mod 2^(28L))"""
+    G, BL = P.G, P.BL
+    rounds = 0
+    while True:
+        couts[G - 1] = 0
+        rounds += 1
+        if not any(couts):
+            return rounds
+        cins = [0] + couts[:G - 1]
+        couts = [0] * G
+        for b in range(G):
+            c = cins[b]
+            if c:
+                for k in range(BL):
+                    t = digs[b * BL + k] + c
+                    digs[b * BL + k] = t & (M - 1)
+                    c = t >> W
+                couts[b] = c
+
+
+def extract64(F, L, bit):
+    p, off = divmod(bit, W)
+    w = 0
+    for i in range(4):
+        d = F[p + i] if p + i < L else 0
+        sft = W * i - off
+        if i == 0:
+            w = d >> off
+        elif sft < 64:
+            w |= (d << sft) & ((1 << 64) - 1)
+    return w
+
+
+def witness_step(P, keyw, inv, A, B, words_out, sqr=False, stats=None):
+    """A, B: strict digits of a*2^s, b*2^s.  Returns (q, rem, next) with next = strict digits of rem*2^s."""
+    import math
+    sh, Nt, mu = keyw
+    G, BL, L = P.G, P.BL, P.L
+    qd, rd = _imma_parts(P, keyw, A, B, sqr)
+    ntu = [(Nt >> (W * p)) & (M - 1) for p in range(L)]
+    # k estimate from the strict top two digits of the top block
+    c, top = 0, []
+    for k in range(BL):
+        t = rd[(G - 1) * BL + k] + c
+        d = sgxt(t)
+        c = (t - d) >> W
+        top.append(d)
+    adj = max(-3, min(3, math.floor((top[BL - 1] * float(M) + top[BL - 2]) * inv)))
+    first, passes = True, 0
+    while True:
+        passes += 1
+        if first or adj:
+            cR, cQ = [0] * G, [0] * G
+            for b in range(G):
+                c = 0
+                for k in range(BL):
+                    t = rd[b * BL + k] - adj * ntu[b * BL + k] + c
+                    assert abs(t) < (1 << 31)
+                    rd[b * BL + k] = t & (M - 1)
+                    c = t >> W
+                cR[b] = c
+                c = adj if b == 0 else 0
+                for k in range(BL):
+                    t = qd[b * BL + k] + c
+                    qd[b * BL + k] = t & (M - 1)
+                    c = t >> W
+                cQ[b] = c
+            r1 = _resolve(P, rd, cR)
+            r2 = _resolve(P, qd, cQ)
+            if stats is not None:
+                stats["rounds"] = max(stats.get("rounds", 0), r1, r2)
+        first = False
+        c = 0
+        for b in range(G - 1, -1, -1):
+            f = 0
+            for k in range(BL):
+                if rd[b * BL + k] != ntu[b * BL + k]:
+                    f = 1 if rd[b * BL + k] > ntu[b * BL + k] else -1
+            if b == G - 1 and rd[L - 1] >= H:
+                f = -2
+            if c == 0:
+                c = f
+        adj = -1 if c == -2 else (1 if c >= 0 else 0)
+        if not adj:
+            break
+        assert passes < 8
+    if stats is not None:
+        stats["passes"] = max(stats.get("passes", 0), passes)
+    q = sum(extract64(qd, L, 64 * j) << (64 * j) for j in range(words_out))
+    rem = sum(extract64(rd, L, 64 * j + sh) << (64 * j) for j in range(words_out))
+    s = sh >> 1
+    pd, off = divmod(s, W)
+    nxt, c = [], 0
+    for p0 in range(L):
+        p = p0 + pd
+        lo = rd[p] if p < L else 0
+        hi = rd[p + 1] if p + 1 < L else 0
+        x = ((lo >> off) | ((hi << (W - off)) if off else 0)) & (M - 1)
+        t = x + c
+        d = sgxt(t)
+        c = (t - d) >> W
+        nxt.append(d)
+    assert c == 0
+    return q, rem, nxt

@@ -74,10 +74,14 @@ def test_golden_tally(built_lib, engine):
             assert key.tally([]) == 1 % (h(case["n"]) ** 2)
 
 
-def test_golden_witness_records_and_digests(built_lib):
+@pytest.mark.parametrize("engine", [1, 3])
+def test_golden_witness_records_and_digests(built_lib, engine):
+    """engine 1: simple64 witnesses; engine 3: the block28w witness engine wherever n fills its declared width"""
     for case in kat()["witness"]:
         n, g, n_bits = h(case["n"]), h(case["g"]), case["n_bits"]
         with PaillierKey(n, g, n_bits, case["limb_bits"]) as key:
+            key.set_engine(engine)
+            assert key.witness_engine == ("block28w" if engine == 3 and n.bit_length() == n_bits else "simple64")
             wo = key.words_out
             ms = [h(u["m"]) for u in case["units"]]
             rs = [h(u["r"]) for u in case["units"]]
@@ -94,6 +98,52 @@ def test_golden_witness_records_and_digests(built_lib):
                     assert [hex(x) for x in recs[0]] == u["first"] and [hex(x) for x in recs[-1]] == u["last"]
             gch = key.g_chain()
             assert witness_digest(gch, wo) == h(case["g_chain_digest"])
+
+
+def _witness_edge_units(n, n_bits, rng, extra):
+    top = (1 << n_bits) - 1
+    ms = [0, 1, 2, top, n - 1, 1 << (n_bits - 1), 3, rng.getrandbits(32)]
+    rs = [1, 1, top, top, n - 1, n + 1 if n + 1 <= top else n, 0, n]
+    for _ in range(extra):
+        ms.append(rng.getrandbits(n_bits)); rs.append(rng.getrandbits(n_bits))
+    return ms, rs
+
+
+@pytest.mark.parametrize("n_bits,extra", [(128, 40), (264, 40), (1024, 30), (2048, 27), (3072, 3), (4096, 2)])
+def test_witness_engine_vs_oracle(built_lib, n_bits, extra):
+    """block28w (exact tail on the block28t arithmetic) against the oracle's (q, rem) stream: digests for every unit
+    (edge cases: m = 0, 1, all ones; r = 0, 1, n, all ones), full records for a few, and against simple64."""
+    rng = random.Random(77 + n_bits)
+    if n_bits >= 1024:
+        kd = workload.load_key(n_bits)
+        n, g = kd["n"], kd["g_rand"]
+    else:
+        n = rng.getrandbits(n_bits) | (1 << (n_bits - 1)) | 1
+        g = rng.getrandbits(n_bits)
+    ms, rs = _witness_edge_units(n, n_bits, rng, extra)
+    limb_bits = 88 if n_bits == 264 else 64
+    with PaillierKey(n, g, n_bits, limb_bits) as key:
+        assert key.witness_engine == "block28w"
+        wo = key.words_out
+        cs, digests = key.encrypt_witness_digest(ms, rs)
+        nfull = 3 if n_bits <= 2048 else 1
+        cs_r, units, gcounts = key.encrypt_witness(ms[:nfull] + ms[-1:], rs[:nfull] + rs[-1:], max_chunk_units=3)
+        key.set_engine(1)
+        assert key.witness_engine == "simple64"
+        ncross = len(ms) if n_bits <= 1024 else 9
+        cs_s, digests_s = key.encrypt_witness_digest(ms[:ncross], rs[:ncross])
+    assert cs_s == cs[:ncross] and digests_s == digests[:ncross]
+    for i, (m, r) in enumerate(zip(ms, rs)):
+        c, steps = encrypt_steps(n, g, m, r)
+        # the per-unit stream omits the per-key g-chain squarings
+        gsq = m.bit_length()
+        gmul = bin(m).count("1")
+        mine = [(s.q, s.rem) for s in steps[:gsq + gmul] if s.kind == "mul"] + [(s.q, s.rem) for s in steps[gsq + gmul:]]
+        assert cs[i] == c, i
+        assert digests[i] == witness_digest(mine, wo), i
+        if i < nfull:
+            assert units[i] == mine and gcounts[i] == gmul and cs_r[i] == c
+    assert cs_r[-1] == cs[-1] and witness_digest(units[-1], wo) == digests[-1]
 
 
 @pytest.mark.parametrize("engine", ENGINES)
