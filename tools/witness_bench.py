@@ -1,16 +1,34 @@
-import sys, time
+"""Throughput of the witness path (pb200_encrypt_witness_digest_dev, inputs resident in HBM): units/s and mul_mod/s."""
+import sys, time, json
 sys.path.insert(0, '/root/repo')
 import numpy as np
+import torch
 from paillier_halo2_b200 import PaillierKey, workload
-from paillier_halo2_b200.api import words_to_ints
-for n_bits, count in ((2048, 4096), (1024, 8192)):
+
+def run(n_bits, count, engine):
     kd = workload.load_key(n_bits)
     m_w, r_w = workload.units(n_bits, count)
-    ms, rs = words_to_ints(m_w), words_to_ints(r_w)
+    dev = torch.device("cuda:0")
+    d_m = torch.from_numpy(m_w.view(np.int64)).to(dev); d_r = torch.from_numpy(r_w.view(np.int64)).to(dev)
     with PaillierKey(kd["n"], kd["g_rand"], n_bits, 64) as key:
-        key.encrypt_witness_digest(ms[:64], rs[:64])
+        key.set_engine(engine)
+        wo = key.words_out
+        d_c = torch.empty((count, wo), dtype=torch.int64, device=dev)
+        d_d = torch.empty(count, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), min(count, 64), d_c.data_ptr(), d_d.data_ptr()); key.sync()
         t0 = time.perf_counter()
-        cs, dig = key.encrypt_witness_digest(ms, rs)
+        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), count, d_c.data_ptr(), d_d.data_ptr()); key.sync()
         dt = time.perf_counter() - t0
-        recs = sum(key.witness_records_for(m) for m in ms[:16]) / 16
-        print(f"simple64 witness digest |n|={n_bits}: {count/dt:.1f} units/s, {recs:.0f} records/unit, {count*recs/dt/1e6:.2f} M mul_mod/s, {count*recs*2*key.words_out*8/dt/1e9:.2f} GB/s of witness")
+        recs = float(np.mean([key.witness_records_for(int.from_bytes(m_w[i].tobytes(), "little")) for i in range(16)]))
+        out = {"n_bits": n_bits, "count": count, "engine": key.witness_engine, "units_per_s": count / dt, "records_per_unit": recs,
+               "mul_mod_per_s": count * recs / dt, "witness_GBps": count * recs * 2 * wo * 8 / dt / 1e9, "seconds": dt}
+        print(json.dumps(out), flush=True)
+        return out
+
+if __name__ == "__main__":
+    res = []
+    for n_bits, count in ((2048, 65536), (1024, 65536), (3072, 16384), (4096, 8192)):
+        res.append(run(n_bits, count, 3))
+    res.append(run(2048, 2048, 1))
+    json.dump(res, open("/root/repo/gpurun_out/witness_bench.json", "w"), indent=1)
