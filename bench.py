@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--units", type=int, default=UNITS, help="units per GPU per step (default: the BASELINE config, 2^16)")
     ap.add_argument("--g", default="rand", choices=["rand", "std"], help="rand: random g (headline); std: g = n+1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-witness", action="store_true", help="skip the witness-mode leg")
     ap.add_argument("--engine", type=int, default=0)
     ap.add_argument("--n-bits", type=int, default=2048, help="key size |n| (default 2048, the BASELINE metric; others are the sweep)")
     ap.add_argument("--workload", default="encrypt", choices=["encrypt", "tally"],
@@ -326,6 +327,55 @@ def main():
     e2e_s = float(t.item())
     e2e_value = world * units * args.steps / e2e_s
 
+    # ---- witness mode (BASELINE.json configs[1]: "witnesses checked bit-exact"): the reference's own LSB-first chain with the
+    # exact (q, rem) of every mul_mod, digested on the device (pb200_encrypt_witness_digest_dev), same units, inputs in HBM
+    witness = None
+    if not args.no_witness:
+        d_dig = torch.empty(units, dtype=torch.int64, device="cuda")
+        d_cw = torch.empty((units, key.words_out), dtype=torch.int64, device="cuda")
+        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), min(units, 4096), d_cw.data_ptr(), d_dig.data_ptr())
+        barrier()
+        wl0 = lib.pb200_kernel_launches()
+        w_evs = []
+        for _ in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), units, d_cw.data_ptr(), d_dig.data_ptr())
+            e1.record(stream)
+            w_evs.append((e0, e1))
+        barrier()
+        w_ms = sum(a.elapsed_time(b) for a, b in w_evs) / len(w_evs)
+        t = torch.tensor([w_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        w_ms = float(t.item())
+        if rank == 0:
+            from oracle.paillier_oracle import encrypt_steps
+            from paillier_halo2_b200.api import witness_digest, words_to_ints
+            pop_n = bin(kd["n"]).count("1")
+            pop_m = float(np.mean([bin(v).count("1") for v in words_to_ints(m_w[:256])]))
+            w_sqr_n, w_mul_n = kd["n"].bit_length(), pop_n + pop_m + 1
+            a_wit = w_sqr_n * w_sqr + w_mul_n * w_mul
+            ok = bool((d_cw.cpu().numpy().view(np.uint64) == d_c.cpu().numpy().view(np.uint64)).all())
+            dig = d_dig.cpu().numpy().view(np.uint64)
+            for i in (0, units - 1):
+                mi, ri = words_to_ints(m_w[i:i + 1])[0], words_to_ints(r_w[i:i + 1])[0]
+                _, steps = encrypt_steps(kd["n"], g, mi, ri)
+                gs = mi.bit_length() + bin(mi).count("1")
+                mine = [(x.q, x.rem) for x in steps[:gs] if x.kind == "mul"] + [(x.q, x.rem) for x in steps[gs:]]
+                ok = ok and int(dig[i]) == witness_digest(mine, key.words_out)
+            peak_w, _ = imad_peak()
+            witness = {"value": world * units / (w_ms * 1e-3), "unit": "units/s", "engine": key.witness_engine, "ms_per_launch": w_ms,
+                       "records_per_unit": w_sqr_n + w_mul_n, "mul_mod_per_s": world * units * (w_sqr_n + w_mul_n) / (w_ms * 1e-3),
+                       "witness_stream_GBps": world * units * (w_sqr_n + w_mul_n) * 2 * key.words_out * 8 / (w_ms * 1e-3) / 1e9,
+                       "chain": {"mod_sqr": w_sqr_n, "mod_mul": w_mul_n, "mac_per_unit": a_wit},
+                       "frac_of_imad_peak": units * a_wit / (w_ms * 1e-3) / peak_w,
+                       "gpu_launches": int(lib.pb200_kernel_launches() - wl0),
+                       "parity": ok,
+                       "note": "reference chain (SURVEY.md A.5: bits(n) square_mod + popcount(n) + popcount(m) + 1 mul_mod per unit), exact (q, rem) "
+                               "per step folded into a 64-bit digest per unit on the device; ciphertexts equal the fast chain's; the digests of "
+                               "the first and last unit are re-derived from the oracle's (q, rem) stream"}
+
     # parity spot check of the last step's output against the CPU port (a checker, never the thing measured)
     parity = None
     if rank == 0:
@@ -353,6 +403,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity_spot_check": parity,
+            "witness": witness,
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC/s (32x32->64 multiply-accumulate)",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get((N_BITS, units)), "peak_source": peak_src,
                          "note": "algorithmic MACs = units x (mod_sqr x W_sqr + mod_mul x W_mul), W for 32-bit limbs over n^2 "

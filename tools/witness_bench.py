@@ -27,6 +27,9 @@ def run(n_bits, count, engine):
         return out
 
 if __name__ == "__main__":
+    if len(sys.argv) == 3:      # one configuration: n_bits count (ncu target)
+        run(int(sys.argv[1]), int(sys.argv[2]), 3)
+        sys.exit(0)
     res = []
     for n_bits, count in ((2048, 65536), (1024, 65536), (3072, 16384), (4096, 8192)):
         res.append(run(n_bits, count, 3))
