@@ -177,6 +177,50 @@ int pb200_key_g_chain(pb200_key* key, uint64_t* records_out);
 int pb200_repack_limbs(pb200_key* key, const uint64_t* values_le, size_t count, uint32_t value_bits,
                        uint32_t limb_bits, uint64_t* limbs_out /* count * (value_bits/limb_bits) * 2 words */);
 
+/* ---- advice cells (K4) -----------------------------------------------------------------------
+ * Replaces: the witness-cell arithmetic BigUintChip performs around every mul_mod that PaillierChip::encrypt/add
+ * issue (src/paillier.rs:51,55,57,81), of assign_integer (src/bench.rs:44-66) and of the square+refresh of n
+ * (src/paillier.rs:39-45, :69-75); semantics in SURVEY.md Appendix A.1-A.4, A.6.  A CELL is one BN254 Fr advice
+ * value = 4 little-endian u64 words: the canonical integer (montgomery = 0; the values never wrap the field) or
+ * its Montgomery form x * 2^256 mod p (montgomery = 1), the in-memory representation of halo2curves' Fr.
+ * lookup_bits = RangeChip lookup width (15 and 13 in the reference, src/paillier.rs:169, src/bench.rs:163);
+ * 0 omits the range-check decomposition cells.
+ *
+ * Cell order of one mul_mod(a, b, n^2) group (L = 2*n_bits/limb_bits limbs):
+ *   q    : per limb [limb, ceil(limb_bits/lookup_bits) chunks (low to high), top chunk << pad if limb_bits % lookup_bits]
+ *   rem  : same
+ *   ab   : 2L-1 no-carry columns  sum_j a_j b_(i-j)
+ *   qn   : 2L-1 columns of q * n^2
+ *   qn+r : 2L-1 sums (rem_i added for i < L)
+ *   eq   : per column i: carry_(i+1), cs_i, q_acc_i, mod_acc_i, then (i < 2L-2) the chunks of carry_(i+1) at carry_bits
+ *   1 cell: the is_equal_muled flag (1). */
+typedef struct pb200_cell_layout {
+    uint32_t limbs;              /* L */
+    uint32_t cells_per_limb;     /* 1 + chunks + (limb_bits % lookup_bits != 0) */
+    uint32_t carry_bits;
+    uint32_t cells_per_mulmod;
+    uint32_t cells_n2;           /* cells of square(n) + refresh */
+    uint32_t off_rem, off_ab, off_qn, off_qn_rem, off_eq, eq_stride;
+} pb200_cell_layout;
+int pb200_cells_layout(pb200_key* key, uint32_t lookup_bits, pb200_cell_layout* out);
+/* a, b, q, rem: count * words_out words each (q, rem as produced by the witness stream / pb200_add_batch);
+ * cells_out: count * cells_per_mulmod * 4 words.  PB200_ERR_RANGE if some (q, rem) does not satisfy
+ * a*b = q*n^2 + rem (the chip's equality constraint would fail).  _dev: device pointers, no synchronise,
+ * no check. */
+int pb200_mulmod_cells_batch(pb200_key* key, const uint64_t* a_le, const uint64_t* b_le, const uint64_t* q_le,
+                             const uint64_t* rem_le, size_t count, uint32_t lookup_bits, int montgomery,
+                             uint64_t* cells_out);
+int pb200_mulmod_cells_batch_dev(pb200_key* key, const uint64_t* d_a_le, const uint64_t* d_b_le, const uint64_t* d_q_le,
+                                 const uint64_t* d_rem_le, size_t count, uint32_t lookup_bits, int montgomery,
+                                 uint64_t* d_cells_out);
+/* assign_integer(value, value_bits) for `count` values of PB200_WORDS(value_bits) words:
+ * cells_out: count * (value_bits/limb_bits) * cells_per_limb * 4 words */
+int pb200_assign_cells_batch(pb200_key* key, const uint64_t* values_le, size_t count, uint32_t value_bits,
+                             uint32_t lookup_bits, int montgomery, uint64_t* cells_out);
+/* square(n) columns, the refresh div/mod chain, the range-check chunks of the refreshed n^2 limbs:
+ * cells_out: cells_n2 * 4 words */
+int pb200_key_n2_cells(pb200_key* key, uint32_t lookup_bits, int montgomery, uint64_t* cells_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,8 +70,21 @@ SYMBOLS = {
     "pb200_encrypt_witness_digest_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "pb200_key_witness_engine": (C.c_char_p, [C.c_void_p]),
     "pb200_key_g_chain": (C.c_int, [C.c_void_p, u64p]),
+    "pb200_cells_layout": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "pb200_mulmod_cells_batch": (C.c_int, [C.c_void_p, u64p, u64p, u64p, u64p, C.c_size_t, C.c_uint32, C.c_int, u64p]),
+    "pb200_mulmod_cells_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]),
+    "pb200_assign_cells_batch": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, u64p]),
+    "pb200_key_n2_cells": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, u64p]),
     "pb200_repack_limbs": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_uint32, C.c_uint32, u64p]),
 }
+
+
+
+class CellLayout(C.Structure):
+    """pb200_cell_layout (include/paillier_b200.h)"""
+    _fields_ = [(n, C.c_uint32) for n in ("limbs", "cells_per_limb", "carry_bits", "cells_per_mulmod", "cells_n2", "off_rem", "off_ab",
+                                          "off_qn", "off_qn_rem", "off_eq", "eq_stride")]
+
 
 _lib = None
 

@@ -46,7 +46,101 @@ def _p(a: np.ndarray):
     return a.ctypes.data_as(_lib.u64p)
 
 
-class PaillierKey:
+BN254_FR = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def _cells_to_ints(arr: np.ndarray) -> List[int]:
+    """(n, 4) u64 cells -> integers (the 4 words little-endian)"""
+    raw = np.ascontiguousarray(arr, dtype="<u8").tobytes()
+    return [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(len(raw) // 32)]
+
+
+class CellMixin:
+    """K4: advice-cell values (BN254 Fr, 4 x u64) produced on the GPU (include/paillier_b200.h, "advice cells")."""
+
+    def cells_layout(self, lookup_bits: int) -> dict:
+        lay = _lib.CellLayout()
+        check(self._lib.pb200_cells_layout(self._h, lookup_bits, C.byref(lay)), "pb200_cells_layout")
+        return {n: int(getattr(lay, n)) for n, _ in lay._fields_}
+
+    def mulmod_cells_words(self, a_w, b_w, q_w, rem_w, lookup_bits: int, montgomery: bool = False) -> np.ndarray:
+        count = a_w.shape[0]
+        per = self.cells_layout(lookup_bits)["cells_per_mulmod"]
+        out = np.empty((count, per, 4), dtype="<u8")
+        check(self._lib.pb200_mulmod_cells_batch(self._h, _p(a_w), _p(b_w), _p(q_w), _p(rem_w), count, lookup_bits, int(montgomery), _p(out)),
+              "pb200_mulmod_cells_batch")
+        return out
+
+    def mulmod_cells_dev(self, d_a: int, d_b: int, d_q: int, d_rem: int, count: int, lookup_bits: int, montgomery: bool, d_cells: int) -> None:
+        """Device-pointer variant (pb200_mulmod_cells_batch_dev): enqueues on the key's stream, no synchronise."""
+        check(self._lib.pb200_mulmod_cells_batch_dev(self._h, d_a, d_b, d_q, d_rem, count, lookup_bits, int(montgomery), d_cells),
+              "pb200_mulmod_cells_batch_dev")
+
+    def add_dev(self, d_c1: int, d_c2: int, c_words: int, count: int, d_out: int, d_q: int) -> None:
+        check(self._lib.pb200_add_batch_dev(self._h, d_c1, d_c2, c_words, count, d_out, d_q or None), "pb200_add_batch_dev")
+
+    def mulmod_cells(self, groups: Sequence[Tuple[int, int, int, int]], lookup_bits: int, montgomery: bool = False) -> List[List[int]]:
+        """groups: (a, b, q, rem) per mul_mod -> the group's cells in BigUintChip assignment order."""
+        if not groups:
+            return []
+        cols = [ints_to_words([g[i] for g in groups], self.words_out) for i in range(4)]
+        out = self.mulmod_cells_words(*cols, lookup_bits, montgomery)
+        return [_cells_to_ints(out[i]) for i in range(len(groups))]
+
+    def assign_cells(self, vals: Sequence[int], value_bits: int, lookup_bits: int, montgomery: bool = False) -> List[List[int]]:
+        """assign_integer(v, value_bits) for each value: [limb, range-check chunks...] per limb."""
+        v_w = ints_to_words(vals, words(value_bits))
+        per = (value_bits // self.limb_bits) * self.cells_layout(lookup_bits)["cells_per_limb"]
+        out = np.empty((len(vals), per, 4), dtype="<u8")
+        check(self._lib.pb200_assign_cells_batch(self._h, _p(v_w), len(vals), value_bits, lookup_bits, int(montgomery), _p(out)),
+              "pb200_assign_cells_batch")
+        return [_cells_to_ints(out[i]) for i in range(len(vals))]
+
+    def n2_cells(self, lookup_bits: int, montgomery: bool = False) -> List[int]:
+        """square(n) columns + refresh div/mod chain + range-check chunks of the refreshed limbs (src/paillier.rs:39-45)."""
+        out = np.empty((self.cells_layout(lookup_bits)["cells_n2"], 4), dtype="<u8")
+        check(self._lib.pb200_key_n2_cells(self._h, lookup_bits, int(montgomery), _p(out)), "pb200_key_n2_cells")
+        return _cells_to_ints(out)
+
+    def encrypt_cells(self, m: int, r: int, lookup_bits: int, montgomery: bool = False):
+        """Every advice cell of the reference's encrypt test flow (src/bench.rs:33-75: assign n, g, m, r; PaillierChip::encrypt;
+        assign res) for one unit, all values computed on the GPU: witnesses from the (q, rem) stream, cells from K4.
+        Returns (ciphertext, cells in assignment order)."""
+        n, g, eb = self.n, self.g, self.enc_bits
+        cs, units, _ = self.encrypt_witness([m], [r])
+        stream = chip_order(m, n, self.g_chain(), units[0])
+        groups = []
+        it = iter(stream)
+        marks = []          # number of groups before each chain start (acc = assign_constant(1) is loaded there)
+        for base, e in ((g, m), (r, n)):
+            marks.append(len(groups))
+            acc, sq = 1, base
+            for i in range(e.bit_length()):
+                cur = sq
+                q, sq = next(it)
+                groups.append((cur, cur, q, sq))
+                if (e >> i) & 1:
+                    q, rem = next(it)
+                    groups.append((acc, cur, q, rem))
+                    acc = rem
+            if base == g:
+                gm = acc
+        q, c = next(it)
+        groups.append((gm, acc, q, c))
+        gcells = self.mulmod_cells(groups, lookup_bits, montgomery)
+        one = (1 << 256) % BN254_FR if montgomery else 1
+        cells: List[int] = []
+        for a in self.assign_cells([n, g, m, r], eb, lookup_bits, montgomery):
+            cells += a
+        cells += self.n2_cells(lookup_bits, montgomery) + [0]
+        for gi, gc in enumerate(gcells):
+            cells += [one] * marks.count(gi)
+            cells += gc
+        cells += self.assign_cells([cs[0]], 2 * eb, lookup_bits, montgomery)[0]
+        return cs[0], cells
+
+
+class PaillierKey(CellMixin):
     """EncryptionPublicKeyAssigned{n, g} (src/paillier.rs:6-9) bound to one CUDA device."""
 
     def __init__(self, n: int, g: int, enc_bits: int, limb_bits: int = 64, device: int = 0):

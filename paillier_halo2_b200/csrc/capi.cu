@@ -5,7 +5,9 @@
 // CUDA kernels (block28_kernels.cu, simple64_kernels.cu); there is no CPU fallback.
 #include "../../include/paillier_b200.h"
 #include "engine.hpp"
+#include "cells.hpp"
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 
@@ -45,6 +47,11 @@ struct pb200_key {
     int engine = 0;                 // 0 auto, 1 simple64, 2 block28
     DevBuf in_a, in_b, out_a, out_b, scratch, offs;
     std::string engine_name;
+    // K4 cell expansion: per lookup_bits layout + device constants (n^2 limbs, word_max, q_acc, mod_acc), refresh spill vector
+    struct CellCtx { CellLayout Y; u64* d_consts = nullptr; int* d_inc = nullptr; int n_out = 0; int n2_cells = 0; };
+    std::map<uint32_t, CellCtx> cells;
+    DevBuf cin_a, cin_b, cin_q, cin_r;
+    int sms = 148;
 };
 
 static bool use_fast(const pb200_key* k) { return k->fast && k->engine != 1; }
@@ -115,6 +122,7 @@ int pb200_key_create(int device, uint32_t n_bits, uint32_t limb_bits, const uint
     delete h;
     if (e != cudaSuccess) { int rc = cuda_fail(e, "pb200_key_create"); pb200_key_destroy(k); return rc; }
     cudaError_t fe = cudaSuccess;
+    { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) k->sms = prop.multiProcessorCount; }
     k->fast = block28_create(n, g, n_bits, device, k->stream, &k->fast_why, &fe);
     if (fe != cudaSuccess) { int rc = cuda_fail(fe, "block28_create"); pb200_key_destroy(k); return rc; }
     k->engine_name = k->fast ? block28_name(k->fast) : "simple64";
@@ -131,6 +139,8 @@ void pb200_key_destroy(pb200_key* k) {
     if (k->d_gchain) cudaFree(k->d_gchain);
     if (k->d_flags) cudaFree(k->d_flags);
     k->in_a.release(); k->in_b.release(); k->out_a.release(); k->out_b.release(); k->scratch.release(); k->offs.release();
+    k->cin_a.release(); k->cin_b.release(); k->cin_q.release(); k->cin_r.release();
+    for (auto& kv : k->cells) { if (kv.second.d_consts) cudaFree(kv.second.d_consts); if (kv.second.d_inc) cudaFree(kv.second.d_inc); }
     if (k->stream) cudaStreamDestroy(k->stream);
     delete k;
 }
@@ -392,6 +402,153 @@ int pb200_encrypt_witness_digest_dev(pb200_key* k, const uint64_t* d_m, const ui
 const char* pb200_key_witness_engine(pb200_key* k) {
     if (!k) return "";
     return (use_fast(k) && block28_witness_supported(k->fast)) ? "block28w" : "simple64";
+}
+
+// ---- K4: advice cells ------------------------------------------------------------------------------------
+static BigInt low_bits(const BigInt& v, size_t bits) { return BigInt::sub(v, BigInt::shl(BigInt::shr(v, bits), bits)); }
+static void put128(std::vector<u64>& dst, const BigInt& v) { u64 w[2]; v.to_u64_le(w, 2); dst.push_back(w[0]); dst.push_back(w[1]); }
+
+static int cell_ctx(pb200_key* k, uint32_t lookup_bits, pb200_key::CellCtx** out) {
+    if (lookup_bits > 32) return PB200_ERR_INVALID_ARG;
+    auto it = k->cells.find(lookup_bits);
+    if (it != k->cells.end()) { *out = &it->second; return PB200_OK; }
+    pb200_key::CellCtx C;
+    CellLayout& Y = C.Y;
+    const int lb = (int)k->limb_bits, L = (int)(2 * k->n_bits / k->limb_bits), NC = 2 * L - 1, kn = (int)(k->n_bits / k->limb_bits);
+    Y.L = L; Y.limb_bits = lb; Y.lookup_bits = (int)lookup_bits;
+    BigInt B1 = BigInt::sub(BigInt::pow2(lb), BigInt(1));
+    BigInt word_max = BigInt::add(BigInt::mul(BigInt((uint64_t)L), BigInt::mul(B1, B1)), B1);       // A.6
+    Y.carry_bits = (int)BigInt::shl(word_max, 1).bits() - lb;
+    Y.kl = lookup_bits ? (lb + (int)lookup_bits - 1) / (int)lookup_bits : 0;
+    Y.xl = lookup_bits && (lb % (int)lookup_bits) ? 1 : 0;
+    Y.cpl = 1 + Y.kl + Y.xl;
+    Y.kc = lookup_bits ? (Y.carry_bits + (int)lookup_bits - 1) / (int)lookup_bits : 0;
+    Y.xc = lookup_bits && (Y.carry_bits % (int)lookup_bits) ? 1 : 0;
+    Y.off_rem = L * Y.cpl; Y.off_ab = 2 * L * Y.cpl; Y.off_qn = Y.off_ab + NC; Y.off_qnp = Y.off_qn + NC; Y.off_eq = Y.off_qnp + NC;
+    Y.eq_stride = 4 + Y.kc + Y.xc;
+    Y.n_cells = Y.off_eq + (NC - 1) * Y.eq_stride + 4 + 1;
+    std::vector<u64> h;
+    for (int i = 0; i < L; i++) put128(h, low_bits(BigInt::shr(k->n2, (size_t)i * lb), lb));
+    { u64 w[4]; word_max.to_u64_le(w, 4); h.insert(h.end(), w, w + 4); }
+    std::vector<u64> qa, ma;
+    BigInt acc;
+    for (int i = 0; i < NC; i++) {
+        acc = BigInt::add(acc, word_max);
+        BigInt qacc = BigInt::shr(acc, lb), macc = low_bits(acc, lb);
+        put128(qa, qacc); put128(ma, macc);
+        acc = qacc;
+    }
+    h.insert(h.end(), qa.begin(), qa.end()); h.insert(h.end(), ma.begin(), ma.end());
+    // RefreshAux::new(limb_bits, kn, kn) (A.3): how far each column of n*n can spill
+    std::vector<BigInt> vals(2 * kn - 1);
+    for (int i = 0; i < kn; i++) for (int j = 0; j < kn; j++) vals[i + j] = BigInt::add(vals[i + j], BigInt::mul(B1, B1));
+    std::vector<int> inc;
+    for (size_t i = 0; i < vals.size(); i++) {
+        BigInt v = vals[i], carry = BigInt::shr(v, lb);
+        int cnt = 0; size_t kk = 1;
+        while (!carry.is_zero()) {
+            if (i + kk >= vals.size()) vals.push_back(BigInt());
+            vals[i + kk] = BigInt::add(vals[i + kk], low_bits(carry, lb));
+            carry = BigInt::shr(carry, lb); cnt++; kk++;
+        }
+        vals[i] = low_bits(v, lb);
+        inc.push_back(cnt);
+    }
+    C.n_out = (int)inc.size();
+    C.n2_cells = (2 * kn - 1) + (lookup_bits ? C.n_out * (Y.kl + Y.xl) : 0);
+    for (int i = 0; i < 2 * kn - 1; i++) C.n2_cells += 2 * (inc[i] + 1);
+    CU(cudaMalloc(&C.d_consts, h.size() * sizeof(u64)));
+    CU(cudaMemcpy(C.d_consts, h.data(), h.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&C.d_inc, inc.size() * sizeof(int)));
+    CU(cudaMemcpy(C.d_inc, inc.data(), inc.size() * sizeof(int), cudaMemcpyHostToDevice));
+    k->cells[lookup_bits] = C;
+    *out = &k->cells[lookup_bits];
+    return PB200_OK;
+}
+
+int pb200_cells_layout(pb200_key* k, uint32_t lookup_bits, pb200_cell_layout* out) {
+    if (!k || !out) return PB200_ERR_INVALID_ARG;
+    CU(cudaSetDevice(k->device));
+    pb200_key::CellCtx* C = nullptr;
+    int rc = cell_ctx(k, lookup_bits, &C); if (rc) return rc;
+    out->limbs = (uint32_t)C->Y.L; out->cells_per_limb = (uint32_t)C->Y.cpl; out->carry_bits = (uint32_t)C->Y.carry_bits;
+    out->cells_per_mulmod = (uint32_t)C->Y.n_cells; out->cells_n2 = (uint32_t)C->n2_cells;
+    out->off_rem = (uint32_t)C->Y.off_rem; out->off_ab = (uint32_t)C->Y.off_ab; out->off_qn = (uint32_t)C->Y.off_qn;
+    out->off_qn_rem = (uint32_t)C->Y.off_qnp; out->off_eq = (uint32_t)C->Y.off_eq; out->eq_stride = (uint32_t)C->Y.eq_stride;
+    return PB200_OK;
+}
+
+int pb200_mulmod_cells_batch_dev(pb200_key* k, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_q, const uint64_t* d_rem,
+                                 size_t count, uint32_t lookup_bits, int montgomery, uint64_t* d_cells) {
+    if (!k || (count && (!d_a || !d_b || !d_q || !d_rem || !d_cells))) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    CU(cudaSetDevice(k->device));
+    pb200_key::CellCtx* C = nullptr;
+    int rc = cell_ctx(k, lookup_bits, &C); if (rc) return rc;
+    CU(cells_mulmod(C->Y, C->d_consts, (const u64*)d_a, (const u64*)d_b, (const u64*)d_q, (const u64*)d_rem, count, (int)k->words_out,
+                    montgomery ? 1 : 0, (u64*)d_cells, k->d_flags, k->sms, k->stream));
+    return PB200_OK;
+}
+
+int pb200_mulmod_cells_batch(pb200_key* k, const uint64_t* a, const uint64_t* b, const uint64_t* q, const uint64_t* rem, size_t count,
+                             uint32_t lookup_bits, int montgomery, uint64_t* cells_out) {
+    if (!k || (count && (!a || !b || !q || !rem || !cells_out))) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    CU(cudaSetDevice(k->device));
+    pb200_key::CellCtx* C = nullptr;
+    int rc = cell_ctx(k, lookup_bits, &C); if (rc) return rc;
+    const size_t bin = count * k->words_out * sizeof(u64), bout = count * (size_t)C->Y.n_cells * 32;
+    CU(k->cin_a.reserve(bin)); CU(k->cin_b.reserve(bin)); CU(k->cin_q.reserve(bin)); CU(k->cin_r.reserve(bin)); CU(k->scratch.reserve(bout));
+    CU(cudaMemcpyAsync(k->cin_a.p, a, bin, cudaMemcpyHostToDevice, k->stream));
+    CU(cudaMemcpyAsync(k->cin_b.p, b, bin, cudaMemcpyHostToDevice, k->stream));
+    CU(cudaMemcpyAsync(k->cin_q.p, q, bin, cudaMemcpyHostToDevice, k->stream));
+    CU(cudaMemcpyAsync(k->cin_r.p, rem, bin, cudaMemcpyHostToDevice, k->stream));
+    rc = pb200_mulmod_cells_batch_dev(k, (const uint64_t*)k->cin_a.p, (const uint64_t*)k->cin_b.p, (const uint64_t*)k->cin_q.p,
+                                      (const uint64_t*)k->cin_r.p, count, lookup_bits, montgomery, (uint64_t*)k->scratch.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(cells_out, k->scratch.p, bout, cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    int f = 0;
+    CU(cudaMemcpy(&f, k->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+    if (f) { CU(cudaMemset(k->d_flags, 0, sizeof(int))); return PB200_ERR_RANGE; }   // (q, rem) do not satisfy a*b = q*n^2 + rem
+    return PB200_OK;
+}
+
+int pb200_assign_cells_batch(pb200_key* k, const uint64_t* values, size_t count, uint32_t value_bits, uint32_t lookup_bits,
+                             int montgomery, uint64_t* cells_out) {
+    if (!k || !values || !cells_out || value_bits == 0 || value_bits % k->limb_bits || lookup_bits > 32) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    CU(cudaSetDevice(k->device));
+    const int lb = (int)k->limb_bits, nl = (int)(value_bits / k->limb_bits);
+    const int kl = lookup_bits ? (lb + (int)lookup_bits - 1) / (int)lookup_bits : 0, xl = lookup_bits && (lb % (int)lookup_bits) ? 1 : 0;
+    const int cpl = 1 + kl + xl, words = (int)PB200_WORDS(value_bits);
+    const size_t bin = count * words * sizeof(u64), bout = count * (size_t)nl * cpl * 32;
+    CU(k->cin_a.reserve(bin)); CU(k->scratch.reserve(bout));
+    CU(cudaMemcpyAsync(k->cin_a.p, values, bin, cudaMemcpyHostToDevice, k->stream));
+    CU(cells_assign((const u64*)k->cin_a.p, count, words, nl, lb, (int)lookup_bits, kl, cpl, montgomery ? 1 : 0, (u64*)k->scratch.p, k->stream));
+    CU(cudaMemcpyAsync(cells_out, k->scratch.p, bout, cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    return PB200_OK;
+}
+
+int pb200_key_n2_cells(pb200_key* k, uint32_t lookup_bits, int montgomery, uint64_t* cells_out) {
+    if (!k || !cells_out) return PB200_ERR_INVALID_ARG;
+    CU(cudaSetDevice(k->device));
+    pb200_key::CellCtx* C = nullptr;
+    int rc = cell_ctx(k, lookup_bits, &C); if (rc) return rc;
+    std::vector<u64> nw(k->words_in);
+    k->n.to_u64_le(nw.data(), k->words_in);
+    const size_t bout = (size_t)C->n2_cells * 32;
+    CU(k->cin_a.reserve(nw.size() * sizeof(u64))); CU(k->scratch.reserve(bout)); CU(k->offs.reserve(sizeof(int)));
+    CU(cudaMemcpyAsync(k->cin_a.p, nw.data(), nw.size() * sizeof(u64), cudaMemcpyHostToDevice, k->stream));
+    CU(cells_n2((const u64*)k->cin_a.p, (int)k->words_in, (int)(k->n_bits / k->limb_bits), (int)k->limb_bits, (int)lookup_bits, C->Y.kl,
+                C->Y.xl, C->d_inc, C->n_out, montgomery ? 1 : 0, (u64*)k->scratch.p, (int*)k->offs.p, k->d_flags, k->stream));
+    int written = 0;
+    CU(cudaMemcpyAsync(&written, k->offs.p, sizeof(int), cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaMemcpyAsync(cells_out, k->scratch.p, bout, cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    if (written != C->n2_cells) { t_cuda_error = "n2 cell count mismatch"; return PB200_ERR_CUDA; }
+    return take_flags(k);
 }
 
 // ---- limb formatting ------------------------------------------------------------------------

@@ -1,0 +1,326 @@
+// cells.cu — K4: the advice-cell values BigUintChip assigns around one mul_mod, produced on the GPU.
+//
+// Replaces the witness-cell arithmetic of biguint-halo2 that PaillierChip::encrypt/add drive
+// (/root/reference/src/paillier.rs:39-45,51,55,57,81; semantics restated in SURVEY.md Appendix A):
+//   k_cells_mulmod : one mul_mod(a, b, n^2) group (A.4 + A.6): q limbs, rem limbs (each followed by its range-check
+//                    chunks, A.1), the no-carry columns ab and q*n^2 (A.2), the sums q*n^2 + rem, and per column of
+//                    is_equal_muled the carry / cs / q_acc / mod_acc values with the carry's range-check chunks,
+//                    then the eq flag — in the order the chip assigns them;
+//   k_cells_assign : assign_integer (A.1) of arbitrary values: limb, chunks [, shifted top chunk];
+//   k_cells_n2     : square(n) + refresh (A.2, A.3) — per key.
+// Every cell is a BN254 Fr element written as 4 little-endian u64 words: canonical integer (the values never wrap
+// the field: < 2^183) or Montgomery form x * 2^256 mod p (halo2curves' in-memory representation).
+//
+// This is HBM-bound byte work: a mul_mod group at |n| = 2048 / 64-bit limbs / 15-bit lookups is 2 546 cells = 81 KB
+// of output for 8 K limb products, so the kernel is organised around coalesced 32-byte cell stores (thread c writes
+// cell c), with the group's primary values (limbs, columns, carries) staged in shared memory.
+#include "engine.hpp"
+#include "cells.hpp"
+
+namespace pb200 {
+
+typedef unsigned __int128 u128c;
+
+struct W4 { u64 w[4]; };
+
+__device__ __forceinline__ W4 w4_zero() { W4 r; r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0; return r; }
+__device__ __forceinline__ W4 w4_from128(u128c v) { W4 r; r.w[0] = (u64)v; r.w[1] = (u64)(v >> 64); r.w[2] = r.w[3] = 0; return r; }
+__device__ __forceinline__ void w4_add(W4& a, const W4& b) {
+    u128c c = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { c += (u128c)a.w[i] + b.w[i]; a.w[i] = (u64)c; c >>= 64; }
+}
+__device__ __forceinline__ void w4_sub(W4& a, const W4& b) {      // two's complement
+    u64 borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u64 ai = a.w[i], bi = b.w[i];
+        u64 d = ai - bi, b1 = ai < bi;
+        u64 d2 = d - borrow, b2 = d < borrow;
+        a.w[i] = d2; borrow = b1 | b2;
+    }
+}
+// acc += a * b, a and b up to 128 bits (hi words zero for limbs of <= 64 bits)
+__device__ __forceinline__ void w4_mac(W4& acc, u64 a0, u64 a1, u64 b0, u64 b1, bool wide) {
+    u128c p = (u128c)a0 * b0;
+    u128c c = (u128c)acc.w[0] + (u64)p; acc.w[0] = (u64)c; c >>= 64;
+    c += (u128c)acc.w[1] + (u64)(p >> 64); acc.w[1] = (u64)c; c >>= 64;
+    c += acc.w[2]; acc.w[2] = (u64)c; c >>= 64;
+    acc.w[3] += (u64)c;
+    if (wide) {
+        u128c p1 = (u128c)a0 * b1, p2 = (u128c)a1 * b0, p3 = (u128c)a1 * b1;
+        c = (u128c)acc.w[1] + (u64)p1 + (u64)p2; acc.w[1] = (u64)c; c >>= 64;
+        c += (u128c)acc.w[2] + (u64)(p1 >> 64) + (u64)(p2 >> 64) + (u64)p3; acc.w[2] = (u64)c; c >>= 64;
+        acc.w[3] += (u64)c + (u64)(p3 >> 64);
+    }
+}
+__device__ __forceinline__ W4 w4_shr(const W4& a, int s) {        // logical, 0 <= s < 256
+    W4 r; const int ws = s >> 6, bs = s & 63;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u64 lo = i + ws < 4 ? a.w[i + ws] : 0, hi = i + ws + 1 < 4 ? a.w[i + ws + 1] : 0;
+        r.w[i] = bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
+    }
+    return r;
+}
+__device__ __forceinline__ W4 w4_shl(const W4& a, int s) {        // 0 <= s < 64
+    W4 r;
+#pragma unroll
+    for (int i = 3; i >= 0; i--) r.w[i] = s ? (a.w[i] << s) | (i ? a.w[i - 1] >> (64 - s) : 0) : a.w[i];
+    return r;
+}
+__device__ __forceinline__ W4 w4_low(const W4& a, int bits) {     // a mod 2^bits, bits < 256
+    W4 r;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int lo = 64 * i;
+        r.w[i] = bits >= lo + 64 ? a.w[i] : (bits <= lo ? 0 : a.w[i] & ((1ull << (bits - lo)) - 1));
+    }
+    return r;
+}
+__device__ __forceinline__ bool w4_eq(const W4& a, const W4& b) { return a.w[0] == b.w[0] && a.w[1] == b.w[1] && a.w[2] == b.w[2] && a.w[3] == b.w[3]; }
+
+// bits [lo, lo+cnt) of a little-endian word array, cnt <= 128
+__device__ __forceinline__ u128c bits_of(const u64* v, int nwords, int lo, int cnt) {
+    const int wi = lo >> 6, sh = lo & 63;
+    u64 w0 = wi < nwords ? v[wi] : 0, w1 = wi + 1 < nwords ? v[wi + 1] : 0, w2 = wi + 2 < nwords ? v[wi + 2] : 0;
+    u64 a = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+    u64 b = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+    u128c r = ((u128c)b << 64) | a;
+    if (cnt < 128) r &= (((u128c)1) << cnt) - 1;
+    return r;
+}
+
+// ---- BN254 Fr, Montgomery form (R = 2^256) ----------------------------------------------------------------
+__device__ __constant__ u64 FR_P[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+__device__ __constant__ u64 FR_R2[4] = {0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x0216d0b17f4e44a5ull};
+#define FR_INV 0xc2e1f593efffffffull
+
+// x * R mod p for x < p (CIOS Montgomery product of x and R^2)
+__device__ __forceinline__ W4 fr_to_mont(const W4& x) {
+    u64 t[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u128c c = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { c += (u128c)x.w[j] * FR_R2[i] + t[j]; t[j] = (u64)c; c >>= 64; }
+        c += t[4]; t[4] = (u64)c; t[5] = (u64)(c >> 64);
+        const u64 m = t[0] * FR_INV;
+        c = (u128c)m * FR_P[0] + t[0]; c >>= 64;
+#pragma unroll
+        for (int j = 1; j < 4; j++) { c += (u128c)m * FR_P[j] + t[j]; t[j - 1] = (u64)c; c >>= 64; }
+        c += t[4]; t[3] = (u64)c; t[4] = t[5] + (u64)(c >> 64);
+    }
+    W4 r; r.w[0] = t[0]; r.w[1] = t[1]; r.w[2] = t[2]; r.w[3] = t[3];
+    // conditional subtraction
+    bool ge = t[4] != 0;
+    if (!ge) {
+        ge = true;
+#pragma unroll
+        for (int i = 3; i >= 0; i--) if (r.w[i] != FR_P[i]) { ge = r.w[i] > FR_P[i]; break; }
+    }
+    if (ge) { W4 p; p.w[0] = FR_P[0]; p.w[1] = FR_P[1]; p.w[2] = FR_P[2]; p.w[3] = FR_P[3]; w4_sub(r, p); }
+    return r;
+}
+
+__device__ __forceinline__ void store_cell(u64* out, size_t cell, W4 v, int mont) {
+    if (mont) v = fr_to_mont(v);
+    ulonglong4 o; o.x = v.w[0]; o.y = v.w[1]; o.z = v.w[2]; o.w = v.w[3];
+    reinterpret_cast<ulonglong4*>(out)[cell] = o;
+}
+
+// cell `sub` of an assigned value with a range check (A.1): 0 = the value, 1..k = lookup chunks, k+1 = shifted top chunk
+__device__ __forceinline__ W4 range_cell(const W4& v, int sub, int bits, int lookup, int k) {
+    if (sub == 0) return v;
+    if (sub <= k) return w4_low(w4_shr(v, (sub - 1) * lookup), lookup);
+    return w4_shl(w4_low(w4_shr(v, (k - 1) * lookup), lookup), lookup - bits % lookup);
+}
+
+// ---- k_cells_mulmod ---------------------------------------------------------------------------------------
+// One CTA works on one group at a time.  Shared memory: limbs of a, b, q, rem, n^2 (2 words each), the three
+// column arrays (4 words each), carries and cs (2 words each).
+__global__ void __launch_bounds__(128) k_cells_mulmod(CellLayout Y, const u64* __restrict__ consts /* n2 limbs, word_max, q_acc, mod_acc */,
+                                                      const u64* __restrict__ a, const u64* __restrict__ b,
+                                                      const u64* __restrict__ q, const u64* __restrict__ rem,
+                                                      size_t count, int words, int mont, u64* __restrict__ out, int* flags) {
+    extern __shared__ u64 sm[];
+    const int L = Y.L, NC = 2 * L - 1, lb = Y.limb_bits;
+    u64* s_a = sm;                 // [L][2]
+    u64* s_b = s_a + 2 * L;
+    u64* s_q = s_b + 2 * L;
+    u64* s_r = s_q + 2 * L;
+    u64* s_n = s_r + 2 * L;
+    W4* s_ab = (W4*)(s_n + 2 * L); // [NC]
+    W4* s_qn = s_ab + NC;
+    W4* s_qp = s_qn + NC;
+    u64* s_carry = (u64*)(s_qp + NC);   // [NC][2]  carry_{i+1}
+    u64* s_cs = s_carry + 2 * NC;       // [NC][2]
+    __shared__ int s_eq;
+    const bool wide = lb > 64;
+    const u64* c_n2 = consts;                  // [L][2]
+    const u64* c_wmax = consts + 2 * L;        // 4 words
+    const u64* c_qacc = c_wmax + 4;            // [NC][2]
+    const u64* c_macc = c_qacc + 2 * NC;       // [NC][2]
+    for (int i = threadIdx.x; i < 2 * L; i += blockDim.x) s_n[i] = c_n2[i];
+    for (size_t g = blockIdx.x; g < count; g += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < L; i += blockDim.x) {
+            u128c va = bits_of(a + g * words, words, i * lb, lb), vb = bits_of(b + g * words, words, i * lb, lb);
+            u128c vq = bits_of(q + g * words, words, i * lb, lb), vr = bits_of(rem + g * words, words, i * lb, lb);
+            s_a[2 * i] = (u64)va; s_a[2 * i + 1] = (u64)(va >> 64);
+            s_b[2 * i] = (u64)vb; s_b[2 * i + 1] = (u64)(vb >> 64);
+            s_q[2 * i] = (u64)vq; s_q[2 * i + 1] = (u64)(vq >> 64);
+            s_r[2 * i] = (u64)vr; s_r[2 * i + 1] = (u64)(vr >> 64);
+        }
+        __syncthreads();
+        // columns: thread i and thread NC-1-i together hold L+1 products per array -> pair the long with the short
+        for (int i = threadIdx.x; i < NC; i += blockDim.x) {
+            W4 ab = w4_zero(), qn = w4_zero();
+            const int j0 = i < L ? 0 : i - L + 1, j1 = i < L ? i : L - 1;
+            for (int j = j0; j <= j1; j++) {
+                w4_mac(ab, s_a[2 * j], s_a[2 * j + 1], s_b[2 * (i - j)], s_b[2 * (i - j) + 1], wide);
+                w4_mac(qn, s_q[2 * j], s_q[2 * j + 1], s_n[2 * (i - j)], s_n[2 * (i - j) + 1], wide);
+            }
+            s_ab[i] = ab; s_qn[i] = qn;
+            if (i < L) { W4 r4; r4.w[0] = s_r[2 * i]; r4.w[1] = s_r[2 * i + 1]; r4.w[2] = r4.w[3] = 0; w4_add(qn, r4); }
+            s_qp[i] = qn;
+        }
+        __syncthreads();
+        // is_equal_muled carry chain (A.6): sequential over the columns
+        if (threadIdx.x == 0) {
+            W4 carry = w4_zero(), wmax; wmax.w[0] = c_wmax[0]; wmax.w[1] = c_wmax[1]; wmax.w[2] = c_wmax[2]; wmax.w[3] = c_wmax[3];
+            int eq = 1, bad = 0;
+            for (int i = 0; i < NC; i++) {
+                W4 s = s_ab[i];
+                w4_sub(s, s_qp[i]); w4_add(s, carry); w4_add(s, wmax);
+                if (s.w[3] >> 63) { bad = 1; s = w4_zero(); }          // negative sum: the constraint would fail
+                carry = w4_shr(s, lb);
+                W4 cs = w4_low(s, lb);
+                s_carry[2 * i] = carry.w[0]; s_carry[2 * i + 1] = carry.w[1];
+                s_cs[2 * i] = cs.w[0]; s_cs[2 * i + 1] = cs.w[1];
+                if (carry.w[2] | carry.w[3]) bad = 1;
+                eq &= (cs.w[0] == c_macc[2 * i] && cs.w[1] == c_macc[2 * i + 1]);
+                if (i == NC - 1) eq &= (carry.w[0] == c_qacc[2 * i] && carry.w[1] == c_qacc[2 * i + 1]);
+            }
+            s_eq = eq;
+            if (bad || !eq) atomicOr(flags, 2);
+        }
+        __syncthreads();
+        // cells, coalesced: thread c writes cell c of the group
+        const size_t base = g * (size_t)Y.n_cells;
+        for (int c = threadIdx.x; c < Y.n_cells; c += blockDim.x) {
+            W4 v = w4_zero();
+            if (c < Y.off_ab) {                                        // q limbs, then rem limbs, with range checks
+                const int cc = c < Y.off_rem ? c : c - Y.off_rem;
+                const u64* src = c < Y.off_rem ? s_q : s_r;
+                const int limb = cc / Y.cpl, sub = cc - limb * Y.cpl;
+                W4 x; x.w[0] = src[2 * limb]; x.w[1] = src[2 * limb + 1]; x.w[2] = x.w[3] = 0;
+                v = range_cell(x, sub, lb, Y.lookup_bits, Y.kl);
+            } else if (c < Y.off_qn) v = s_ab[c - Y.off_ab];
+            else if (c < Y.off_qnp) v = s_qn[c - Y.off_qn];
+            else if (c < Y.off_eq) v = s_qp[c - Y.off_qnp];
+            else if (c == Y.n_cells - 1) v.w[0] = (u64)s_eq;
+            else {
+                const int cc = c - Y.off_eq;
+                const int i = cc / Y.eq_stride, sub = cc - i * Y.eq_stride;
+                if (sub == 0) { v.w[0] = s_carry[2 * i]; v.w[1] = s_carry[2 * i + 1]; }
+                else if (sub == 1) { v.w[0] = s_cs[2 * i]; v.w[1] = s_cs[2 * i + 1]; }
+                else if (sub == 2) { v.w[0] = c_qacc[2 * i]; v.w[1] = c_qacc[2 * i + 1]; }
+                else if (sub == 3) { v.w[0] = c_macc[2 * i]; v.w[1] = c_macc[2 * i + 1]; }
+                else {
+                    W4 x = w4_zero(); x.w[0] = s_carry[2 * i]; x.w[1] = s_carry[2 * i + 1];
+                    v = range_cell(x, sub - 3, Y.carry_bits, Y.lookup_bits, Y.kc);
+                }
+            }
+            store_cell(out, base + c, v, mont);
+        }
+    }
+}
+
+// ---- k_cells_assign: assign_integer of `count` values ---------------------------------------------------------
+__global__ void k_cells_assign(const u64* __restrict__ vals, size_t count, int words, int nl, int limb_bits, int lookup, int k,
+                               int cpl, int mont, u64* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per = (size_t)nl * cpl;
+    if (idx >= count * per) return;
+    const size_t u = idx / per; const int cc = (int)(idx - u * per);
+    const int limb = cc / cpl, sub = cc - limb * cpl;
+    W4 x = w4_from128(bits_of(vals + u * words, words, limb * limb_bits, limb_bits));
+    store_cell(out, idx, range_cell(x, sub, limb_bits, lookup, k), mont);
+}
+
+// ---- k_cells_n2: square(n) + refresh, one thread (per key) ------------------------------------------------------
+__global__ void k_cells_n2(const u64* __restrict__ n_words, int words, int kn, int limb_bits, int lookup, int kl, int xl,
+                           const int* __restrict__ inc, int n_out, int mont, u64* __restrict__ out, int* n_written, int* flags) {
+    if (blockIdx.x || threadIdx.x) return;
+    extern __shared__ u64 smx[];
+    W4* x = (W4*)smx;                       // n_out entries
+    const int NC = 2 * kn - 1;
+    const bool wide = limb_bits > 64;
+    size_t cell = 0;
+    for (int i = 0; i < n_out; i++) x[i] = w4_zero();
+    for (int i = 0; i < NC; i++) {          // square: no-carry columns (A.2)
+        W4 acc = w4_zero();
+        const int j0 = i < kn ? 0 : i - kn + 1, j1 = i < kn ? i : kn - 1;
+        for (int j = j0; j <= j1; j++) {
+            u128c aj = bits_of(n_words, words, j * limb_bits, limb_bits), bj = bits_of(n_words, words, (i - j) * limb_bits, limb_bits);
+            w4_mac(acc, (u64)aj, (u64)(aj >> 64), (u64)bj, (u64)(bj >> 64), wide);
+        }
+        x[i] = acc;
+        store_cell(out, cell++, acc, mont);
+    }
+    for (int i = 0; i < NC; i++) {          // refresh (A.3)
+        W4 limb = x[i];
+        for (int j = 0; j <= inc[i]; j++) {
+            W4 qq = w4_shr(limb, limb_bits), rr = w4_low(limb, limb_bits);
+            store_cell(out, cell++, qq, mont);
+            store_cell(out, cell++, rr, mont);
+            if (j == 0) x[i] = rr; else if (i + j < n_out) w4_add(x[i + j], rr);
+            limb = qq;
+        }
+        if (limb.w[0] | limb.w[1] | limb.w[2] | limb.w[3]) atomicOr(flags, 2);
+    }
+    if (lookup) {
+        for (int i = 0; i < n_out; i++)
+            for (int sub = 1; sub <= kl + xl; sub++) store_cell(out, cell++, range_cell(x[i], sub, limb_bits, lookup, kl), mont);
+    }
+    *n_written = (int)cell;
+}
+
+// ---- launchers ----------------------------------------------------------------------------------------------------
+size_t cells_mulmod_smem(const CellLayout& Y) {
+    const size_t L = Y.L, NC = 2 * L - 1;
+    return (5 * 2 * L + 3 * 4 * NC + 2 * 2 * NC) * sizeof(u64);
+}
+cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_a, const u64* d_b, const u64* d_q, const u64* d_rem,
+                         size_t count, int words, int mont, u64* d_out, int* d_flags, int sms, cudaStream_t st) {
+    if (!count) return cudaSuccess;
+    const size_t smem = cells_mulmod_smem(Y);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_cells_mulmod, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    size_t grid = count < (size_t)sms * 8 ? count : (size_t)sms * 8;
+    k_cells_mulmod<<<(unsigned)grid, 128, smem, st>>>(Y, d_consts, d_a, d_b, d_q, d_rem, count, words, mont, d_out, d_flags);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t cells_assign(const u64* d_vals, size_t count, int words, int nl, int limb_bits, int lookup, int k, int cpl, int mont,
+                         u64* d_out, cudaStream_t st) {
+    const size_t total = count * (size_t)nl * cpl;
+    if (!total) return cudaSuccess;
+    k_cells_assign<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_vals, count, words, nl, limb_bits, lookup, k, cpl, mont, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t cells_n2(const u64* d_n_words, int words, int kn, int limb_bits, int lookup, int kl, int xl, const int* d_inc, int n_out,
+                     int mont, u64* d_out, int* d_n_written, int* d_flags, cudaStream_t st) {
+    k_cells_n2<<<1, 1, (size_t)n_out * sizeof(W4), st>>>(d_n_words, words, kn, limb_bits, lookup, kl, xl, d_inc, n_out, mont, d_out,
+                                                        d_n_written, d_flags);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace pb200

@@ -254,3 +254,54 @@ def test_gpu_fed_circuit_is_satisfied(built_lib, enc_bits, limb_bits):
         paillier_enc_add_test(enc_bits, limb_bits, n, g, c1, c2, res[0], lookup_bits=15, witness_source=[(q[0], res[0])])
         with pytest.raises(AssertionError):
             paillier_enc_add_test(enc_bits, limb_bits, n, g, c1, c2, res[0], lookup_bits=15, witness_source=[(q[0], res[0] ^ 2)])
+
+
+# ---- K4: advice cells ------------------------------------------------------------------------------------------
+BN254_FR = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+@pytest.mark.parametrize("enc_bits,limb_bits,lookup_bits", [(128, 64, 15), (264, 88, 15), (128, 64, 13), (128, 64, 0)])
+def test_gpu_cell_stream_equals_chip_cells(built_lib, enc_bits, limb_bits, lookup_bits):
+    """BASELINE.json configs[0] at cell level: every advice value of the reference's encrypt test flow
+    (src/bench.rs:33-75 through PaillierChip::encrypt, src/paillier.rs:32-60) computed on the GPU — witnesses from the
+    (q, rem) stream, cells from the K4 kernels — equals, cell for cell and in order, what the chip restatement assigns."""
+    from oracle.paillier_oracle import paillier_enc_test
+    rng = random.Random(4242 + enc_bits + lookup_bits)
+    n = rng.getrandbits(enc_bits) | (1 << (enc_bits - 1)) | 1
+    g = rng.getrandbits(enc_bits)
+    for m, r in ((rng.getrandbits(enc_bits), rng.getrandbits(enc_bits)), (0, rng.getrandbits(enc_bits)), (5, 1)):
+        with PaillierKey(n, g, enc_bits, limb_bits) as key:
+            c, cells = key.encrypt_cells(m, r, lookup_bits)
+            ctx = paillier_enc_test(enc_bits, limb_bits, n, g, m, r, c, lookup_bits=lookup_bits or None)
+            assert c == paillier_enc_native(n, g, m, r)
+            assert len(cells) == len(ctx.cells)
+            assert cells == ctx.cells
+            if m == 5:
+                c2, mont = key.encrypt_cells(m, r, lookup_bits, montgomery=True)
+                assert mont == [(v << 256) % BN254_FR for v in ctx.cells]
+
+
+@pytest.mark.parametrize("n_bits", [1024, 2048])
+def test_gpu_mulmod_cells_large(built_lib, n_bits):
+    """mul_mod groups at production sizes against the chip restatement: (q, rem) from pb200_add_batch, cells from K4."""
+    from oracle.paillier_oracle import Assigned, BigUintChip, Context, decompose
+    kd = workload.load_key(n_bits)
+    n = kd["n"]; n2 = n * n
+    rng = random.Random(99 + n_bits)
+    L = 2 * n_bits // 64
+    pairs = [(rng.randrange(n2), rng.randrange(n2)) for _ in range(3)] + [(n2 - 1, n2 - 1), (1, 0), (0, 0), (1, 1)]
+    with PaillierKey(n, n + 1, n_bits, 64) as key:
+        res, qs = key.paillier_add_native([p[0] for p in pairs], [p[1] for p in pairs], want_q=True)
+        groups = [(a, b, q, rem) for (a, b), q, rem in zip(pairs, qs, res)]
+        got = key.mulmod_cells(groups, 15)
+        lay = key.cells_layout(15)
+        bad = key.mulmod_cells
+        with pytest.raises(Pb200Error):
+            bad([(pairs[0][0], pairs[0][1], qs[0] ^ 1, res[0])], 15)
+    big = BigUintChip(64, 15)
+    n2_as = Assigned(decompose(n2, L, 64), n2, 64, True)
+    for (a, b, q, rem), cells in zip(groups, got):
+        ctx = Context()
+        out = big.mul_mod(ctx, Assigned(decompose(a, L, 64), a, 64), Assigned(decompose(b, L, 64), b, 64), n2_as)
+        assert out.value == rem and len(cells) == lay["cells_per_mulmod"] == len(ctx.cells)
+        assert cells == ctx.cells
