@@ -237,6 +237,142 @@ __global__ void __launch_bounds__(128) k_cells_mulmod(CellLayout Y, const u64* _
     }
 }
 
+
+// ---- k_cells_mulmod64: the production case, limb_bits = 64 --------------------------------------------------------
+// One WARP per group, four independent warps per CTA (no CTA-wide barrier inside the loop, so the sequential carry chain
+// of one group overlaps the column products and the stores of the others).  Per warp 4L + 3(2L-1) words of shared memory:
+// the limbs of a, b, q, rem and d_i = ab_i - (qn_i + rem_i) + word_max, overwritten in place by (cs_i, carry_(i+1)).
+// Columns: lane l owns the pair (c, c+L), c = l, l+32, ..: for j = 0..L-1 the product a_j * b_((c-j) mod L) belongs to
+// column c when j <= c and to column c+L otherwise — every lane runs exactly L uniform iterations.
+// All stores are one 32-byte cell per lane at consecutive addresses.
+__device__ __forceinline__ void mac3p(u64& c0, u64& c1, u64& c2, u64 lo, u64 hi) {
+    asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u64 %2, %2, 0;" : "+l"(c0), "+l"(c1), "+l"(c2) : "l"(lo), "l"(hi));
+}
+__device__ __forceinline__ W4 chunk_cell(u64 lo, u64 hi, int sub, int pad, int lookup, int k) {    // sub >= 1; pad = lookup - bits % lookup
+    const int idx = sub <= k ? sub - 1 : k - 1;
+    const int sft = idx * lookup;
+    const u64 x = sft >= 64 ? hi >> (sft - 64) : (sft ? (lo >> sft) | (hi << (64 - sft)) : lo);
+    u64 ch = x & ((1ull << lookup) - 1);
+    ch <<= (sub > k ? pad : 0);
+    W4 r = w4_zero(); r.w[0] = ch;
+    return r;
+}
+
+template <bool MONT>
+__global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_cpl, u64 m_eq, const u64* __restrict__ consts,
+                                                           const u64* __restrict__ a, const u64* __restrict__ b,
+                                                           const u64* __restrict__ q, const u64* __restrict__ rem,
+                                                           size_t count, u64* __restrict__ out, int* flags) {
+    extern __shared__ u64 sm[];
+    const int L = Y.L, NC = 2 * L - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64* s_n = sm;
+    u64* s_a = sm + L + (size_t)warp * (4 * L + 3 * NC + 1);
+    u64* s_b = s_a + L; u64* s_q = s_b + L; u64* s_r = s_q + L; u64* s_d = s_r + L;
+    const u64* c_wmax = consts + 2 * L;        // consts: n2 limbs [L][2], word_max (4 words), q_acc [NC][2], mod_acc [NC][2]
+    const u64* c_qacc = c_wmax + 4;
+    const u64* c_macc = c_qacc + 2 * NC;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) s_n[i] = consts[2 * i];
+    __syncthreads();
+    const u64 wm0 = c_wmax[0], wm1 = c_wmax[1], wm2 = c_wmax[2];
+    const int pad_l = Y.lookup_bits ? Y.lookup_bits - 64 % Y.lookup_bits : 0, pad_c = Y.lookup_bits ? Y.lookup_bits - Y.carry_bits % Y.lookup_bits : 0;
+    for (size_t g = (size_t)blockIdx.x * 4 + warp; g < count; g += (size_t)gridDim.x * 4) {
+        for (int i = lane; i < L; i += 32) {
+            s_a[i] = a[g * L + i]; s_b[i] = b[g * L + i]; s_q[i] = q[g * L + i]; s_r[i] = rem[g * L + i];
+        }
+        __syncwarp();
+        const size_t base = g * (size_t)Y.n_cells;
+        // q and rem: limb cells with their range-check chunks
+        for (int c = lane; c < Y.off_ab; c += 32) {
+            const int cc = c < Y.off_rem ? c : c - Y.off_rem;
+            const u64* src = c < Y.off_rem ? s_q : s_r;
+            const int limb = (int)(((u64)cc * m_cpl) >> 32), sub = cc - limb * Y.cpl;
+            const u64 x = src[limb];
+            W4 v;
+            if (sub == 0) { v = w4_zero(); v.w[0] = x; } else v = chunk_cell(x, 0, sub, pad_l, Y.lookup_bits, Y.kl);
+            store_cell(out, base + c, v, MONT);
+        }
+        // no-carry columns ab and q*n^2, the sums, and d
+        for (int c = lane; c < L; c += 32) {
+            // one running accumulator per product; its value when j reaches c + 1 is column c, the rest is column c + L
+            u64 ah0 = 0, ah1 = 0, ah2 = 0, qh0 = 0, qh1 = 0, qh2 = 0, al0 = 0, al1 = 0, al2 = 0, ql0 = 0, ql1 = 0, ql2 = 0;
+            int bi = c;
+#pragma unroll 4
+            for (int j = 0; j < L; j++) {
+                if (j == c + 1) { al0 = ah0; al1 = ah1; al2 = ah2; ql0 = qh0; ql1 = qh1; ql2 = qh2; }
+                const u64 aj = s_a[j], qj = s_q[j], bv = s_b[bi], nv = s_n[bi];
+                mac3p(ah0, ah1, ah2, aj * bv, __umul64hi(aj, bv));
+                mac3p(qh0, qh1, qh2, qj * nv, __umul64hi(qj, nv));
+                bi = bi ? bi - 1 : L - 1;
+            }
+            if (c == L - 1) { al0 = ah0; al1 = ah1; al2 = ah2; ql0 = qh0; ql1 = qh1; ql2 = qh2; }
+            asm("sub.cc.u64 %0, %0, %3; subc.cc.u64 %1, %1, %4; subc.u64 %2, %2, %5;" : "+l"(ah0), "+l"(ah1), "+l"(ah2) : "l"(al0), "l"(al1), "l"(al2));
+            asm("sub.cc.u64 %0, %0, %3; subc.cc.u64 %1, %1, %4; subc.u64 %2, %2, %5;" : "+l"(qh0), "+l"(qh1), "+l"(qh2) : "l"(ql0), "l"(ql1), "l"(ql2));
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int col = c + h * L;
+                if (col < NC) {
+                    W4 ab, qn;
+                    ab.w[0] = h ? ah0 : al0; ab.w[1] = h ? ah1 : al1; ab.w[2] = h ? ah2 : al2; ab.w[3] = 0;
+                    qn.w[0] = h ? qh0 : ql0; qn.w[1] = h ? qh1 : ql1; qn.w[2] = h ? qh2 : ql2; qn.w[3] = 0;
+                    store_cell(out, base + Y.off_ab + col, ab, MONT);
+                    store_cell(out, base + Y.off_qn + col, qn, MONT);
+                    W4 qp = qn;
+                    if (h == 0) mac3p(qp.w[0], qp.w[1], qp.w[2], s_r[c], 0);
+                    store_cell(out, base + Y.off_qnp + col, qp, MONT);
+                    // d = ab - qp + word_max (two's complement over 3 words)
+                    u64 d0, d1, d2;
+                    asm("sub.cc.u64 %0, %3, %6; subc.cc.u64 %1, %4, %7; subc.u64 %2, %5, %8;"
+                        : "=l"(d0), "=l"(d1), "=l"(d2) : "l"(ab.w[0]), "l"(ab.w[1]), "l"(ab.w[2]), "l"(qp.w[0]), "l"(qp.w[1]), "l"(qp.w[2]));
+                    asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u64 %2, %2, %5;" : "+l"(d0), "+l"(d1), "+l"(d2) : "l"(wm0), "l"(wm1), "l"(wm2));
+                    s_d[3 * col] = d0; s_d[3 * col + 1] = d1; s_d[3 * col + 2] = d2;
+                }
+            }
+        }
+        __syncwarp();
+        // is_equal_muled carry chain (A.6): s_i = d_i + carry_i; cs_i = s_i mod 2^64, carry_(i+1) = s_i >> 64, in place
+        int eq = 1;
+        if (lane == 0) {
+            u64 c0 = 0, c1 = 0;
+            int bad = 0;
+            for (int i = 0; i < NC; i++) {
+                u64 s0 = s_d[3 * i], s1 = s_d[3 * i + 1], s2 = s_d[3 * i + 2];
+                asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u64 %2, %2, 0;" : "+l"(s0), "+l"(s1), "+l"(s2) : "l"(c0), "l"(c1));
+                bad |= (int)(s2 >> 63);
+                c0 = s1; c1 = s2;
+                s_d[3 * i + 1] = s1; s_d[3 * i + 2] = s2; s_d[3 * i] = s0;
+            }
+            eq &= (c0 == c_qacc[2 * (NC - 1)] && c1 == c_qacc[2 * (NC - 1) + 1]);
+            if (bad || !eq) atomicOr(flags, 2);
+        }
+        eq = __shfl_sync(0xffffffffu, eq, 0);
+        __syncwarp();
+        {
+            int ok = 1;
+            for (int i = lane; i < NC; i += 32) ok &= (s_d[3 * i] == __ldg(c_macc + 2 * i));
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok && eq && lane == 0) atomicOr(flags, 2);
+            eq &= ok;
+        }
+        const int n_eq = Y.n_cells - Y.off_eq;
+        for (int cc = lane; cc < n_eq; cc += 32) {
+            W4 v = w4_zero();
+            if (cc == n_eq - 1) v.w[0] = (u64)eq;
+            else {
+                const int i = (int)(((u64)cc * m_eq) >> 32), sub = cc - i * Y.eq_stride;
+                const u64 cs = s_d[3 * i], k0 = s_d[3 * i + 1], k1 = s_d[3 * i + 2];
+                if (sub >= 4) v = chunk_cell(k0, k1, sub - 3, pad_c, Y.lookup_bits, Y.kc);
+                else if (sub >= 2) {
+                    const u64* src = sub == 2 ? c_qacc : c_macc;
+                    v.w[0] = __ldg(src + 2 * i); v.w[1] = __ldg(src + 2 * i + 1);
+                } else { v.w[0] = sub ? cs : k0; v.w[1] = sub ? 0 : k1; }
+            }
+            store_cell(out, base + Y.off_eq + cc, v, MONT);
+        }
+        __syncwarp();
+    }
+}
+
 // ---- k_cells_assign: assign_integer of `count` values ---------------------------------------------------------
 __global__ void k_cells_assign(const u64* __restrict__ vals, size_t count, int words, int nl, int limb_bits, int lookup, int k,
                                int cpl, int mont, u64* __restrict__ out) {
@@ -295,6 +431,26 @@ size_t cells_mulmod_smem(const CellLayout& Y) {
 cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_a, const u64* d_b, const u64* d_q, const u64* d_rem,
                          size_t count, int words, int mont, u64* d_out, int* d_flags, int sms, cudaStream_t st) {
     if (!count) return cudaSuccess;
+    if (Y.limb_bits == 64 && Y.n_cells < 65536) {
+        const size_t L = Y.L, NC = 2 * L - 1;
+        const size_t smem64 = (L + 4 * (4 * L + 3 * NC + 1)) * sizeof(u64);
+        static bool attr64 = false;
+        if (!attr64) {
+            cudaError_t e = cudaFuncSetAttribute(k_cells_mulmod64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cells_mulmod64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            if (e != cudaSuccess) return e;
+            attr64 = true;
+        }
+        const u64 m_cpl = (0x100000000ull + Y.cpl - 1) / Y.cpl, m_eq = (0x100000000ull + Y.eq_stride - 1) / Y.eq_stride;
+        size_t ctas = (count + 3) / 4;
+        const size_t per_sm = smem64 ? (200 * 1024) / smem64 : 6;
+        const size_t cap = (size_t)sms * (per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm));
+        if (ctas > cap) ctas = cap;
+        if (mont) k_cells_mulmod64<true><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags);
+        else k_cells_mulmod64<false><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags);
+        count_launch();
+        return cudaGetLastError();
+    }
     const size_t smem = cells_mulmod_smem(Y);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {

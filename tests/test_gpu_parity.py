@@ -294,6 +294,8 @@ def test_gpu_mulmod_cells_large(built_lib, n_bits):
         res, qs = key.paillier_add_native([p[0] for p in pairs], [p[1] for p in pairs], want_q=True)
         groups = [(a, b, q, rem) for (a, b), q, rem in zip(pairs, qs, res)]
         got = key.mulmod_cells(groups, 15)
+        got_mont = key.mulmod_cells(groups[:2], 15, montgomery=True)
+        got_nolookup = key.mulmod_cells(groups[:2], 0)
         lay = key.cells_layout(15)
         bad = key.mulmod_cells
         with pytest.raises(Pb200Error):
@@ -304,4 +306,9 @@ def test_gpu_mulmod_cells_large(built_lib, n_bits):
         ctx = Context()
         out = big.mul_mod(ctx, Assigned(decompose(a, L, 64), a, 64), Assigned(decompose(b, L, 64), b, 64), n2_as)
         assert out.value == rem and len(cells) == lay["cells_per_mulmod"] == len(ctx.cells)
+        assert cells == ctx.cells
+    assert got_mont == [[(v << 256) % BN254_FR for v in cells] for cells in got[:2]]
+    for (a, b, q, rem), cells in zip(groups[:2], got_nolookup):
+        ctx = Context()
+        BigUintChip(64, None).mul_mod(ctx, Assigned(decompose(a, L, 64), a, 64), Assigned(decompose(b, L, 64), b, 64), n2_as)
         assert cells == ctx.cells

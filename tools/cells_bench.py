@@ -33,5 +33,5 @@ def run(n_bits, count, lookup, mont, reps=3):
 if __name__ == "__main__":
     if len(sys.argv) >= 5:
         run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), reps=1); sys.exit(0)
-    res = [run(2048, 16384, 15, 0), run(2048, 16384, 15, 1), run(2048, 16384, 0, 0), run(1024, 32768, 15, 0), run(3072, 8192, 15, 0)]
+    res = [run(2048, 65536, 15, 0), run(2048, 65536, 15, 1), run(2048, 65536, 0, 0), run(1024, 131072, 15, 0), run(3072, 32768, 15, 0), run(4096, 16384, 15, 0)]
     json.dump(res, open("/root/repo/gpurun_out/cells_bench.json", "w"), indent=1)
