@@ -144,6 +144,67 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def hbm_peak():
+    """Measured HBM copy bandwidth of this pool's B200 (driver-written MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def cells_leg(key, kd, n_bits, groups=1 << 16, lookup_bits=15, reps=4):
+    """K4: advice cells of `groups` mul_mod groups, device-resident, CUDA events on the key's stream.
+    Algorithmic bytes per group = cells_per_mulmod x 32 B written + 4 x words_out x 8 B read."""
+    import numpy as np
+    import torch
+    from paillier_halo2_b200 import workload
+    dev = torch.device("cuda", key.device)
+    wo = key.words_out
+    c_w = workload.ciphertexts(n_bits, 2 * groups, kd["n"])
+    d_a = torch.from_numpy(c_w[:groups].view(np.int64)).to(dev)
+    d_b = torch.from_numpy(c_w[groups:].view(np.int64)).to(dev)
+    d_rem, d_q = torch.empty_like(d_a), torch.empty_like(d_a)
+    key.add_dev(d_a.data_ptr(), d_b.data_ptr(), wo, groups, d_rem.data_ptr(), d_q.data_ptr())
+    key.sync()
+    per = key.cells_layout(lookup_bits)["cells_per_mulmod"]
+    d_cells = torch.empty((groups, per, 4), dtype=torch.int64, device=dev)       # 5.3 GB at |n| = 2048: larger than L2
+    stream = torch.cuda.ExternalStream(key.stream, device=dev)
+    peak, src = hbm_peak()
+    out = {"groups": groups, "lookup_bits": lookup_bits, "cells_per_group": per}
+    for mont in (0, 1):
+        for _ in range(3):
+            key.mulmod_cells_dev(d_a.data_ptr(), d_b.data_ptr(), d_q.data_ptr(), d_rem.data_ptr(), groups, lookup_bits, bool(mont), d_cells.data_ptr())
+        key.sync()
+        ms = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            key.mulmod_cells_dev(d_a.data_ptr(), d_b.data_ptr(), d_q.data_ptr(), d_rem.data_ptr(), groups, lookup_bits, bool(mont), d_cells.data_ptr())
+            e1.record(stream)
+            key.sync()
+            ms.append(e0.elapsed_time(e1))
+        t = sum(ms) / len(ms) * 1e-3
+        gbs = groups * (per * 32 + 4 * wo * 8) / t / 1e9
+        out["montgomery" if mont else "canonical"] = {"groups_per_s": groups / t, "ms_per_launch": t * 1e3,
+                                                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                                                   "peak_source": src}}
+    # parity of one group against the chip restatement (checker only)
+    from oracle.paillier_oracle import Assigned, BigUintChip, Context, decompose
+    from paillier_halo2_b200.api import _cells_to_ints, words_to_ints
+    L = 2 * n_bits // 64
+    a0, b0 = words_to_ints(c_w[:1])[0], words_to_ints(c_w[groups:groups + 1])[0]
+    n2 = kd["n"] ** 2
+    key.mulmod_cells_dev(d_a.data_ptr(), d_b.data_ptr(), d_q.data_ptr(), d_rem.data_ptr(), 1, lookup_bits, False, d_cells.data_ptr())
+    key.sync()
+    got = _cells_to_ints(d_cells[0].cpu().numpy().view(np.uint64))
+    ctx = Context()
+    BigUintChip(64, lookup_bits).mul_mod(ctx, Assigned(decompose(a0, L, 64), a0, 64), Assigned(decompose(b0, L, 64), b0, 64),
+                                         Assigned(decompose(n2, L, 64), n2, 64))
+    out["parity"] = bool(got == ctx.cells)
+    del d_cells
+    return out
+
+
 def run_tally(args):
     """BASELINE.json configs[2]: product of 2^20 ciphertexts mod n^2, sharded over the GPUs with one all-gather of
     the per-GPU partials (NCCL) and a final combine.  Strong scaling (total work fixed)."""
@@ -376,6 +437,11 @@ def main():
                                "per step folded into a 64-bit digest per unit on the device; ciphertexts equal the fast chain's; the digests of "
                                "the first and last unit are re-derived from the oracle's (q, rem) stream"}
 
+    # ---- K4: advice-cell expansion of mul_mod groups (HBM-bound writer), rank 0 only
+    cells = None
+    if not args.no_witness and rank == 0:
+        cells = cells_leg(key, kd, N_BITS)
+
     # parity spot check of the last step's output against the CPU port (a checker, never the thing measured)
     parity = None
     if rank == 0:
@@ -404,6 +470,7 @@ def main():
             "clocks": clocks,
             "parity_spot_check": parity,
             "witness": witness,
+            "cells": cells,
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC/s (32x32->64 multiply-accumulate)",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get((N_BITS, units)), "peak_source": peak_src,
                          "note": "algorithmic MACs = units x (mod_sqr x W_sqr + mod_mul x W_mul), W for 32-bit limbs over n^2 "

@@ -385,6 +385,23 @@ __global__ void k_wtab(const u64* __restrict__ g_words, int words_in, const u64*
     }
 }
 
+// per-key g-chain on the witness engine: record i = (q, rem) of (g^(2^i))^2, i < n_bits, and the table entries
+// gtab[i] = strict digits of g^(2^i) * 2^s.  One CTA; every lane computes the same value, lane 0 writes.
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1) k_gchain_w(B28Dev K, WitDev Wd, const u64* __restrict__ g_words, int n_bits,
+                                                            u64* __restrict__ gchain, int4* __restrict__ gtab) {
+    extern __shared__ int4 smem[];
+    Smem<C> S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    load_consts<C>(smem, K);
+    load_value_shl<C>(S.V, g_words, K.words_in, Wd.sh >> 1, role, lane);
+    for (int i = 0; i < n_bits; i++) {
+        if (lane == 0) scatter_entry<C>(gtab + (size_t)i * C::ENTRY4, S.V, role, lane);
+        WStep o; o.rec = lane == 0 ? gchain + (size_t)i * 2 * K.words_out : nullptr; o.rem_out = nullptr;
+        mulmod_w<C>(smem, nullptr, 1, S.V, o, Wd.sh, K.words_out, Wd.inv, Wd.cpow);
+    }
+}
+
 template <class C>
 __device__ __forceinline__ void bcast_entry(int4* buf, const int4* entry, int role, int lane) {
 #pragma unroll
@@ -653,7 +670,7 @@ static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64*
 #define CUW(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
 
 template <class C>
-static cudaError_t witness_prepare_cfg(Block28Key* key, const u64* d_gchain, cudaStream_t st) {
+static cudaError_t witness_prepare_cfg(Block28Key* key, u64* d_gchain, bool gchain_ready, cudaStream_t st) {
     const BigInt& n = key->n;
     BigInt n2 = BigInt::mul(n, n);
     int sh = C::KN - (int)n2.bits();
@@ -684,10 +701,6 @@ static cudaError_t witness_prepare_cfg(Block28Key* key, const u64* d_gchain, cud
     CUW(cudaMalloc(&key->d_nwords, nw.size() * sizeof(u64)));
     CUW(cudaMemcpyAsync(key->d_nwords, nw.data(), nw.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
     CUW(cudaMalloc(&key->d_gtab, (size_t)key->n_bits * C::ENTRY4 * sizeof(int4)));
-    k_wtab<C><<<(key->n_bits + 63) / 64, 64, 0, st>>>(key->d_gwords, wi, d_gchain, wo, (int)key->n_bits, sh / 2, key->d_gtab);
-    count_launch();
-    CUW(cudaGetLastError());
-    CUW(cudaStreamSynchronize(st));                        // the staging vectors above go out of scope
     // 2^(28(L-2)) / Nt_w from the top 52 bits of Nt_w
     BigInt top = BigInt::shr(Nt, (size_t)W * (C::L - 2) - 20);
     double topd = (double)top.bits_at(32, 32) * 4294967296.0 + (double)top.bits_at(0, 32);
@@ -696,6 +709,15 @@ static cudaError_t witness_prepare_cfg(Block28Key* key, const u64* d_gchain, cud
     Wd.gtab = key->d_gtab; Wd.one_s = key->d_one_s; Wd.cpow = key->d_cpow; Wd.n_words = key->d_nwords;
     Wd.exp_bits = (int)n.bits(); Wd.sh = sh; Wd.inv = 1048576.0 / topd;
     CUW(cudaFuncSetAttribute(k_witness<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES));
+    CUW(cudaFuncSetAttribute(k_gchain_w<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES));
+    if (gchain_ready) {        // g-chain records already produced (simple64): only convert them into table entries
+        k_wtab<C><<<(key->n_bits + 63) / 64, 64, 0, st>>>(key->d_gwords, wi, d_gchain, wo, (int)key->n_bits, sh / 2, key->d_gtab);
+    } else {                   // produce records and table entries with the witness engine itself
+        k_gchain_w<C><<<1, C::THREADS, C::SMEM_W_BYTES, st>>>(key->wdev, key->wit, key->d_gwords, (int)key->n_bits, d_gchain, key->d_gtab);
+    }
+    count_launch();
+    CUW(cudaGetLastError());
+    CUW(cudaStreamSynchronize(st));                        // the staging vectors above go out of scope
     key->wit_ready = true;
     return cudaSuccess;
 }
@@ -776,13 +798,13 @@ cudaError_t block28_tally(Block28Key* key, const u64* d_c, size_t count, u64* d_
 // The witness engine needs canonical chain values below n^2 from the first step on: n must fill its declared width
 // (then g, r < 2^n_bits <= 2n <= n^2).  Other keys keep the simple64 witness path.
 bool block28_witness_supported(const Block28Key* key) { return key->use_mma && key->n.bits() == key->n_bits && key->n_bits >= 8; }
-cudaError_t block28_witness_prepare(Block28Key* key, const u64* d_gchain, cudaStream_t st) {
+cudaError_t block28_witness_prepare(Block28Key* key, u64* d_gchain, bool gchain_ready, cudaStream_t st) {
     if (key->wit_ready) return cudaSuccess;
     try {
-        if (key->G == 4) return witness_prepare_cfg<Cfg1024>(key, d_gchain, st);
-        if (key->G == 8) return witness_prepare_cfg<Cfg2048>(key, d_gchain, st);
-        if (key->BL == 14) return witness_prepare_cfg<Cfg3072>(key, d_gchain, st);
-        return witness_prepare_cfg<Cfg4096>(key, d_gchain, st);
+        if (key->G == 4) return witness_prepare_cfg<Cfg1024>(key, d_gchain, gchain_ready, st);
+        if (key->G == 8) return witness_prepare_cfg<Cfg2048>(key, d_gchain, gchain_ready, st);
+        if (key->BL == 14) return witness_prepare_cfg<Cfg3072>(key, d_gchain, gchain_ready, st);
+        return witness_prepare_cfg<Cfg4096>(key, d_gchain, gchain_ready, st);
     } catch (const std::exception&) { return cudaErrorInvalidValue; }
 }
 cudaError_t block28_witness(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, u64* d_records,

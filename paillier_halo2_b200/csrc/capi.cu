@@ -48,7 +48,7 @@ struct pb200_key {
     DevBuf in_a, in_b, out_a, out_b, scratch, offs;
     std::string engine_name;
     // K4 cell expansion: per lookup_bits layout + device constants (n^2 limbs, word_max, q_acc, mod_acc), refresh spill vector
-    struct CellCtx { CellLayout Y; u64* d_consts = nullptr; int* d_inc = nullptr; int n_out = 0; int n2_cells = 0; };
+    struct CellCtx { CellLayout Y; u64* d_consts = nullptr; int* d_inc = nullptr; u64* d_mtab = nullptr; int n_out = 0; int n2_cells = 0; };
     std::map<uint32_t, CellCtx> cells;
     DevBuf cin_a, cin_b, cin_q, cin_r;
     int sms = 148;
@@ -140,7 +140,7 @@ void pb200_key_destroy(pb200_key* k) {
     if (k->d_flags) cudaFree(k->d_flags);
     k->in_a.release(); k->in_b.release(); k->out_a.release(); k->out_b.release(); k->scratch.release(); k->offs.release();
     k->cin_a.release(); k->cin_b.release(); k->cin_q.release(); k->cin_r.release();
-    for (auto& kv : k->cells) { if (kv.second.d_consts) cudaFree(kv.second.d_consts); if (kv.second.d_inc) cudaFree(kv.second.d_inc); }
+    for (auto& kv : k->cells) { if (kv.second.d_consts) cudaFree(kv.second.d_consts); if (kv.second.d_inc) cudaFree(kv.second.d_inc); if (kv.second.d_mtab) cudaFree(kv.second.d_mtab); }
     if (k->stream) cudaStreamDestroy(k->stream);
     delete k;
 }
@@ -189,10 +189,13 @@ static int take_flags(pb200_key* k) {
     return PB200_OK;
 }
 
+// per-key g-chain records: by the witness engine when it serves this key (it builds its table in the same pass), else by
+// simple64 (one thread, the reference's chain)
 static int ensure_gchain(pb200_key* k) {
     if (k->d_gchain) return PB200_OK;
     CU(cudaMalloc(&k->d_gchain, (size_t)k->n_bits * 2 * k->words_out * sizeof(u64)));
-    CU(simple_gchain(k->d_simple, k->d_gchain, (int)k->n_bits, k->stream));
+    if (use_fast(k) && block28_witness_supported(k->fast)) CU(block28_witness_prepare(k->fast, k->d_gchain, false, k->stream));
+    else CU(simple_gchain(k->d_simple, k->d_gchain, (int)k->n_bits, k->stream));
     return PB200_OK;
 }
 
@@ -202,7 +205,7 @@ static int witness_engine(pb200_key* k, bool* fast) {
     *fast = false;
     int rc = ensure_gchain(k); if (rc) return rc;
     if (!use_fast(k) || !block28_witness_supported(k->fast)) return PB200_OK;
-    CU(block28_witness_prepare(k->fast, k->d_gchain, k->stream));
+    CU(block28_witness_prepare(k->fast, k->d_gchain, true, k->stream));
     *fast = true;
     return PB200_OK;
 }
@@ -439,6 +442,18 @@ static int cell_ctx(pb200_key* k, uint32_t lookup_bits, pb200_key::CellCtx** out
         acc = qacc;
     }
     h.insert(h.end(), qa.begin(), qa.end()); h.insert(h.end(), ma.begin(), ma.end());
+    {   // Montgomery forms (x * 2^256 mod p, BN254 Fr) of the per-key q_acc / mod_acc cells; 32-byte aligned in the buffer
+        static const uint64_t FRP[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+        BigInt P = BigInt::from_u64_le(FRP, 4);
+        for (int which = 0; which < 2; which++)
+            for (int i = 0; i < NC; i++) {
+                const std::vector<u64>& src = which ? ma : qa;
+                u64 w2[2] = {src[2 * i], src[2 * i + 1]};
+                BigInt m = BigInt::mod(BigInt::shl(BigInt::from_u64_le(w2, 2), 256), P);
+                u64 w4[4]; m.to_u64_le(w4, 4);
+                h.insert(h.end(), w4, w4 + 4);
+            }
+    }
     // RefreshAux::new(limb_bits, kn, kn) (A.3): how far each column of n*n can spill
     std::vector<BigInt> vals(2 * kn - 1);
     for (int i = 0; i < kn; i++) for (int j = 0; j < kn; j++) vals[i + j] = BigInt::add(vals[i + j], BigInt::mul(B1, B1));
@@ -461,6 +476,11 @@ static int cell_ctx(pb200_key* k, uint32_t lookup_bits, pb200_key::CellCtx** out
     CU(cudaMemcpy(C.d_consts, h.data(), h.size() * sizeof(u64), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&C.d_inc, inc.size() * sizeof(int)));
     CU(cudaMemcpy(C.d_inc, inc.data(), inc.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (lookup_bits >= 1 && lookup_bits <= 16) {       // chunk-value table for the Montgomery output (2 MB at 16 bits)
+        CU(cudaMalloc(&C.d_mtab, ((size_t)32) << lookup_bits));
+        CU(cells_mont_table((int)lookup_bits, C.d_mtab, k->stream));
+        CU(cudaStreamSynchronize(k->stream));
+    }
     k->cells[lookup_bits] = C;
     *out = &k->cells[lookup_bits];
     return PB200_OK;
@@ -486,7 +506,7 @@ int pb200_mulmod_cells_batch_dev(pb200_key* k, const uint64_t* d_a, const uint64
     pb200_key::CellCtx* C = nullptr;
     int rc = cell_ctx(k, lookup_bits, &C); if (rc) return rc;
     CU(cells_mulmod(C->Y, C->d_consts, (const u64*)d_a, (const u64*)d_b, (const u64*)d_q, (const u64*)d_rem, count, (int)k->words_out,
-                    montgomery ? 1 : 0, (u64*)d_cells, k->d_flags, k->sms, k->stream));
+                    montgomery ? 1 : 0, (u64*)d_cells, k->d_flags, k->sms, C->d_mtab, k->stream));
     return PB200_OK;
 }
 

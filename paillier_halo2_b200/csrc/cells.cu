@@ -123,6 +123,85 @@ __device__ __forceinline__ W4 fr_to_mont(const W4& x) {
     return r;
 }
 
+// x * R mod p for a one-word x: x * (R mod p) is 5 words, the quotient by p fits one word and is estimated from the top
+// 128 bits of the product with a 64-bit reciprocal of p's top word (never low, at most one too high: checked over 2*10^5
+// values incl. the extremes), then one conditional correction.  10 word products instead of the 36 of the general path.
+__device__ __constant__ u64 FR_R1[4] = {0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full};
+#define FR_RHO 0xa948e8c4c4740950ull      // floor(2^127 / (p >> 190))
+__device__ __forceinline__ W4 fr_to_mont_u64(u64 x) {
+    u64 t[5];
+    u128c c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { c += (u128c)x * FR_R1[j]; t[j] = (u64)c; c >>= 64; }
+    t[4] = (u64)c;
+    const u64 X0 = (t[2] >> 62) | (t[3] << 2), X1 = (t[3] >> 62) | (t[4] << 2);
+    const u128c e = (u128c)X1 * FR_RHO + __umul64hi(X0, FR_RHO);
+    const u64 qh = (u64)(e >> 63);
+    u64 m[5];
+    c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { c += (u128c)qh * FR_P[j]; m[j] = (u64)c; c >>= 64; }
+    m[4] = (u64)c;
+    u64 borrow = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const u64 d = t[j] - m[j], b1 = t[j] < m[j], d2 = d - borrow, b2 = d < borrow;
+        t[j] = d2; borrow = b1 | b2;
+    }
+    W4 r; r.w[0] = t[0]; r.w[1] = t[1]; r.w[2] = t[2]; r.w[3] = t[3];
+    W4 pp; pp.w[0] = FR_P[0]; pp.w[1] = FR_P[1]; pp.w[2] = FR_P[2]; pp.w[3] = FR_P[3];
+    int guard = 0;
+    while ((t[4] >> 63) && guard++ < 4) {          // negative: add p
+        u128c cc = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { cc += (u128c)r.w[j] + pp.w[j]; r.w[j] = (u64)cc; cc >>= 64; }
+        t[4] += (u64)cc;
+    }
+    for (guard = 0; guard < 4; guard++) {           // >= p: subtract (not expected)
+        bool ge = t[4] != 0;
+        if (!ge) {
+            ge = true;
+#pragma unroll
+            for (int i = 3; i >= 0; i--) if (r.w[i] != pp.w[i]) { ge = r.w[i] > pp.w[i]; break; }
+        }
+        if (!ge) break;
+        u64 bw = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const u64 d = r.w[j] - pp.w[j], b1 = r.w[j] < pp.w[j], d2 = d - bw, b2 = d < bw; r.w[j] = d2; bw = b1 | b2; }
+        t[4] -= bw;
+    }
+    return r;
+}
+
+enum CellKind { CK_RAW = 0, CK_SMALL = 1, CK_WIDE = 2 };   // already in output form / one-word value / up to four words
+template <bool MONT>
+__device__ __forceinline__ void store_cell_k(u64* out, size_t cell, W4 v, int kind) {
+    if (MONT) {
+        if (kind == CK_SMALL) v = fr_to_mont_u64(v.w[0]);
+        else if (kind == CK_WIDE) v = fr_to_mont(v);
+    }
+    ulonglong4 o; o.x = v.w[0]; o.y = v.w[1]; o.z = v.w[2]; o.w = v.w[3];
+    reinterpret_cast<ulonglong4*>(out)[cell] = o;
+}
+
+// Montgomery forms of all lookup-chunk values 0 .. 2^lookup_bits - 1 (most cells are range-check chunks): one 32-byte
+// gather from an L2-resident table replaces the conversion arithmetic
+__global__ void k_mont_table(int n, u64* __restrict__ tab) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const W4 v = fr_to_mont_u64((u64)x);
+    tab[4 * x] = v.w[0]; tab[4 * x + 1] = v.w[1]; tab[4 * x + 2] = v.w[2]; tab[4 * x + 3] = v.w[3];
+}
+template <bool MONT>
+__device__ __forceinline__ void store_chunk(u64* out, size_t cell, W4 v, const u64* __restrict__ mtab) {
+    if (MONT && mtab) {
+        const ulonglong2* t = reinterpret_cast<const ulonglong2*>(mtab) + 2 * v.w[0];
+        const ulonglong2 a = __ldg(t), b = __ldg(t + 1);
+        v.w[0] = a.x; v.w[1] = a.y; v.w[2] = b.x; v.w[3] = b.y;
+        store_cell_k<MONT>(out, cell, v, CK_RAW);
+    } else store_cell_k<MONT>(out, cell, v, CK_SMALL);
+}
+
 __device__ __forceinline__ void store_cell(u64* out, size_t cell, W4 v, int mont) {
     if (mont) v = fr_to_mont(v);
     ulonglong4 o; o.x = v.w[0]; o.y = v.w[1]; o.z = v.w[2]; o.w = v.w[3];
@@ -259,12 +338,13 @@ __device__ __forceinline__ W4 chunk_cell(u64 lo, u64 hi, int sub, int pad, int l
 }
 
 template <bool MONT>
-__global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_cpl, u64 m_eq, const u64* __restrict__ consts,
+__global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_cpl, u64 m_eq, u64 m_eqs, const u64* __restrict__ consts,
                                                            const u64* __restrict__ a, const u64* __restrict__ b,
                                                            const u64* __restrict__ q, const u64* __restrict__ rem,
-                                                           size_t count, u64* __restrict__ out, int* flags) {
+                                                           size_t count, u64* __restrict__ out, int* flags, const u64* __restrict__ mtab) {
     extern __shared__ u64 sm[];
     const int L = Y.L, NC = 2 * L - 1;
+    const u64* c_accm = consts + 2 * L + 4 + 4 * NC;      // Montgomery forms of q_acc, mod_acc: [NC][4] each
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64* s_n = sm;
     u64* s_a = sm + L + (size_t)warp * (4 * L + 3 * NC + 1);
@@ -288,9 +368,8 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
             const u64* src = c < Y.off_rem ? s_q : s_r;
             const int limb = (int)(((u64)cc * m_cpl) >> 32), sub = cc - limb * Y.cpl;
             const u64 x = src[limb];
-            W4 v;
-            if (sub == 0) { v = w4_zero(); v.w[0] = x; } else v = chunk_cell(x, 0, sub, pad_l, Y.lookup_bits, Y.kl);
-            store_cell(out, base + c, v, MONT);
+            if (sub == 0) { W4 v = w4_zero(); v.w[0] = x; store_cell_k<MONT>(out, base + c, v, CK_SMALL); }
+            else store_chunk<MONT>(out, base + c, chunk_cell(x, 0, sub, pad_l, Y.lookup_bits, Y.kl), mtab);
         }
         // no-carry columns ab and q*n^2, the sums, and d
         for (int c = lane; c < L; c += 32) {
@@ -315,11 +394,11 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
                     W4 ab, qn;
                     ab.w[0] = h ? ah0 : al0; ab.w[1] = h ? ah1 : al1; ab.w[2] = h ? ah2 : al2; ab.w[3] = 0;
                     qn.w[0] = h ? qh0 : ql0; qn.w[1] = h ? qh1 : ql1; qn.w[2] = h ? qh2 : ql2; qn.w[3] = 0;
-                    store_cell(out, base + Y.off_ab + col, ab, MONT);
-                    store_cell(out, base + Y.off_qn + col, qn, MONT);
+                    store_cell_k<MONT>(out, base + Y.off_ab + col, ab, CK_WIDE);
+                    store_cell_k<MONT>(out, base + Y.off_qn + col, qn, CK_WIDE);
                     W4 qp = qn;
                     if (h == 0) mac3p(qp.w[0], qp.w[1], qp.w[2], s_r[c], 0);
-                    store_cell(out, base + Y.off_qnp + col, qp, MONT);
+                    store_cell_k<MONT>(out, base + Y.off_qnp + col, qp, CK_WIDE);
                     // d = ab - qp + word_max (two's complement over 3 words)
                     u64 d0, d1, d2;
                     asm("sub.cc.u64 %0, %3, %6; subc.cc.u64 %1, %4, %7; subc.u64 %2, %5, %8;"
@@ -354,21 +433,54 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
             if (!ok && eq && lane == 0) atomicOr(flags, 2);
             eq &= ok;
         }
-        const int n_eq = Y.n_cells - Y.off_eq;
-        for (int cc = lane; cc < n_eq; cc += 32) {
-            W4 v = w4_zero();
-            if (cc == n_eq - 1) v.w[0] = (u64)eq;
-            else {
-                const int i = (int)(((u64)cc * m_eq) >> 32), sub = cc - i * Y.eq_stride;
-                const u64 cs = s_d[3 * i], k0 = s_d[3 * i + 1], k1 = s_d[3 * i + 2];
-                if (sub >= 4) v = chunk_cell(k0, k1, sub - 3, pad_c, Y.lookup_bits, Y.kc);
-                else if (sub >= 2) {
-                    const u64* src = sub == 2 ? c_qacc : c_macc;
-                    v.w[0] = __ldg(src + 2 * i); v.w[1] = __ldg(src + 2 * i + 1);
-                } else { v.w[0] = sub ? cs : k0; v.w[1] = sub ? 0 : k1; }
+        if (!MONT) {
+            // canonical output: one loop over the eq section's cells, lane c writes cell c (contiguous 1 KB per warp store)
+            const int n_eq = Y.n_cells - Y.off_eq;
+            for (int cc = lane; cc < n_eq; cc += 32) {
+                W4 v = w4_zero();
+                if (cc == n_eq - 1) v.w[0] = (u64)eq;
+                else {
+                    const int i = (int)(((u64)cc * m_eqs) >> 32), sub = cc - i * Y.eq_stride;
+                    const u64 cs = s_d[3 * i], k0 = s_d[3 * i + 1], k1 = s_d[3 * i + 2];
+                    if (sub >= 4) v = chunk_cell(k0, k1, sub - 3, pad_c, Y.lookup_bits, Y.kc);
+                    else if (sub >= 2) {
+                        const u64* src = sub == 2 ? c_qacc : c_macc;
+                        v.w[0] = __ldg(src + 2 * i); v.w[1] = __ldg(src + 2 * i + 1);
+                    } else { v.w[0] = sub ? cs : k0; v.w[1] = sub ? 0 : k1; }
+                }
+                store_cell_k<false>(out, base + Y.off_eq + cc, v, CK_RAW);
             }
-            store_cell(out, base + Y.off_eq + cc, v, MONT);
+            __syncwarp();
+            continue;
         }
+        // eq section in passes of uniform cell kind (no divergence between the conversion paths):
+        // per column [carry (wide), cs (one word), q_acc, mod_acc (per-key, pre-converted)], then the carries' chunks
+        for (int i = lane; i < NC; i += 32) {
+            const size_t cell = base + Y.off_eq + (size_t)i * Y.eq_stride;
+            W4 v = w4_zero();
+            v.w[0] = s_d[3 * i + 1]; v.w[1] = s_d[3 * i + 2];
+            store_cell_k<MONT>(out, cell, v, CK_WIDE);
+            v.w[0] = s_d[3 * i]; v.w[1] = 0;
+            store_cell_k<MONT>(out, cell + 1, v, CK_SMALL);
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                if (MONT) {
+                    const u64* m4 = c_accm + 4 * ((size_t)w * NC + i);
+                    v.w[0] = __ldg(m4); v.w[1] = __ldg(m4 + 1); v.w[2] = __ldg(m4 + 2); v.w[3] = __ldg(m4 + 3);
+                } else {
+                    const u64* src = w ? c_macc : c_qacc;
+                    v.w[0] = __ldg(src + 2 * i); v.w[1] = __ldg(src + 2 * i + 1); v.w[2] = v.w[3] = 0;
+                }
+                store_cell_k<MONT>(out, cell + 2 + w, v, CK_RAW);
+            }
+        }
+        const int cpc = Y.kc + Y.xc;
+        for (int idx = lane; idx < (NC - 1) * cpc; idx += 32) {
+            const int i = (int)(((u64)idx * m_eq) >> 32), sub = idx - i * cpc;     // m_eq: magic of cpc
+            store_chunk<MONT>(out, base + Y.off_eq + (size_t)i * Y.eq_stride + 4 + sub,
+                              chunk_cell(s_d[3 * i + 1], s_d[3 * i + 2], sub + 1, pad_c, Y.lookup_bits, Y.kc), mtab);
+        }
+        if (lane == 0) { W4 v = w4_zero(); v.w[0] = (u64)eq; store_cell_k<MONT>(out, base + Y.n_cells - 1, v, CK_SMALL); }
         __syncwarp();
     }
 }
@@ -428,8 +540,14 @@ size_t cells_mulmod_smem(const CellLayout& Y) {
     const size_t L = Y.L, NC = 2 * L - 1;
     return (5 * 2 * L + 3 * 4 * NC + 2 * 2 * NC) * sizeof(u64);
 }
+cudaError_t cells_mont_table(int lookup_bits, u64* d_tab, cudaStream_t st) {
+    const int n = 1 << lookup_bits;
+    k_mont_table<<<(n + 255) / 256, 256, 0, st>>>(n, d_tab);
+    count_launch();
+    return cudaGetLastError();
+}
 cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_a, const u64* d_b, const u64* d_q, const u64* d_rem,
-                         size_t count, int words, int mont, u64* d_out, int* d_flags, int sms, cudaStream_t st) {
+                         size_t count, int words, int mont, u64* d_out, int* d_flags, int sms, const u64* d_mtab, cudaStream_t st) {
     if (!count) return cudaSuccess;
     if (Y.limb_bits == 64 && Y.n_cells < 65536) {
         const size_t L = Y.L, NC = 2 * L - 1;
@@ -441,13 +559,14 @@ cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_
             if (e != cudaSuccess) return e;
             attr64 = true;
         }
-        const u64 m_cpl = (0x100000000ull + Y.cpl - 1) / Y.cpl, m_eq = (0x100000000ull + Y.eq_stride - 1) / Y.eq_stride;
+        const u64 m_eqs = (0x100000000ull + Y.eq_stride - 1) / Y.eq_stride;
+        const u64 m_cpl = (0x100000000ull + Y.cpl - 1) / Y.cpl, m_eq = (Y.kc + Y.xc) ? (0x100000000ull + (Y.kc + Y.xc) - 1) / (Y.kc + Y.xc) : 0;
         size_t ctas = (count + 3) / 4;
         const size_t per_sm = smem64 ? (200 * 1024) / smem64 : 6;
         const size_t cap = (size_t)sms * (per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm));
         if (ctas > cap) ctas = cap;
-        if (mont) k_cells_mulmod64<true><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags);
-        else k_cells_mulmod64<false><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags);
+        if (mont) k_cells_mulmod64<true><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, m_eqs, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags, d_mtab);
+        else k_cells_mulmod64<false><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, m_eqs, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags, nullptr);
         count_launch();
         return cudaGetLastError();
     }

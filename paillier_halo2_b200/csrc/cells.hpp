@@ -22,7 +22,9 @@ struct CellLayout {
 
 size_t cells_mulmod_smem(const CellLayout& Y);
 cudaError_t cells_mulmod(const CellLayout& Y, const uint64_t* d_consts, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_q,
-                         const uint64_t* d_rem, size_t count, int words, int mont, uint64_t* d_out, int* d_flags, int sms, cudaStream_t st);
+                         const uint64_t* d_rem, size_t count, int words, int mont, uint64_t* d_out, int* d_flags, int sms,
+                         const uint64_t* d_mtab /* nullable: Montgomery forms of 0 .. 2^lookup_bits-1 */, cudaStream_t st);
+cudaError_t cells_mont_table(int lookup_bits, uint64_t* d_tab /* 2^lookup_bits * 4 words */, cudaStream_t st);
 cudaError_t cells_assign(const uint64_t* d_vals, size_t count, int words, int nl, int limb_bits, int lookup, int k, int cpl, int mont,
                          uint64_t* d_out, cudaStream_t st);
 cudaError_t cells_n2(const uint64_t* d_n_words, int words, int kn, int limb_bits, int lookup, int kl, int xl, const int* d_inc, int n_out,

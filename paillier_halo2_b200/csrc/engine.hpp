@@ -41,7 +41,8 @@ cudaError_t block28_encrypt(Block28Key*, const u64* d_m, const u64* d_r, size_t 
 cudaError_t block28_tally(Block28Key*, const u64* d_c, size_t count, u64* d_out, cudaStream_t st);
 // witness engine: the reference's chain with exact (q, rem) per mul_mod (block28t arithmetic + exact tail)
 bool block28_witness_supported(const Block28Key*);
-cudaError_t block28_witness_prepare(Block28Key*, const u64* d_gchain /* simple64 g-chain records */, cudaStream_t st);
+// d_gchain: n_bits records (q, rem) of the g-chain squarings; gchain_ready = false lets the witness engine produce them
+cudaError_t block28_witness_prepare(Block28Key*, u64* d_gchain, bool gchain_ready, cudaStream_t st);
 cudaError_t block28_witness(Block28Key*, const u64* d_m, const u64* d_r, size_t count, u64* d_c /*nullable*/,
                             u64* d_records /*nullable*/, const u64* d_offsets /*nullable*/, u64* d_digest /*nullable*/,
                             cudaStream_t st);
