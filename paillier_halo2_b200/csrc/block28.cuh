@@ -707,6 +707,7 @@ template <class C> __device__ __forceinline__ int* west_ptr(Smem<C>& S) { return
 struct WStep {             // per-step outputs of one lane (null = not wanted)
     u64w* rec;             // 2*words_out words: q then rem
     u64w* rem_out;         // words_out words: rem only (the ciphertext of the final step)
+    u64w* q_out = nullptr; // words_out words: q only
 };
 
 template <int L>
@@ -829,6 +830,7 @@ __device__ __noinline__ u64w w_tail(int4* smem_base, int4* next_dst, WStep out, 
             h += wq * cpow[j] + wr * cpow[words_out + j];
             if (out.rec) { out.rec[j] = wq; out.rec[words_out + j] = wr; }
             if (out.rem_out) out.rem_out[j] = wr;
+            if (out.q_out) out.q_out[j] = wq;
         }
     }
     hsum[warp * 32 + lane] = h;

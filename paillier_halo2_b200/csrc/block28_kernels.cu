@@ -489,6 +489,47 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_witness(B28Dev K
     if (role == 0 && active && A.digest) A.digest[unit] = D;
 }
 
+// paillier_add_native / PaillierChip::add (src/paillier.rs:62-85, :94-97) for `count` pairs on the witness engine:
+// one exact mul_mod per lane, rem (and optionally q) as 64-bit words.  Inputs are c_words words each (zero-extended,
+// src/paillier.rs:79-80) and need not be reduced; a quotient that does not fit words_out words raises the range flag.
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_add_w(B28Dev K, WitDev Wd, const u64* __restrict__ c1,
+                                                                      const u64* __restrict__ c2, int c_words, size_t count,
+                                                                      u64* __restrict__ out, u64* __restrict__ q_out, int* flags) {
+    extern __shared__ int4 smem[];
+    Smem<C> S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    load_consts<C>(smem, K);
+    const int wo = K.words_out;
+    for (size_t first = (size_t)blockIdx.x * 32; first < count; first += (size_t)gridDim.x * 32) {
+        size_t unit = first + lane;
+        const bool active = unit < count;
+        if (!active) unit = count - 1;
+        load_value_shl<C>(S.V, c1 + unit * c_words, c_words, Wd.sh >> 1, role, lane);
+        load_value_shl<C>(S.B, c2 + unit * c_words, c_words, Wd.sh >> 1, role, lane);
+        // the record goes through a per-lane staging area only when q is wanted; rem alone is written directly
+        WStep o; o.rec = nullptr; o.rem_out = active ? out + unit * wo : nullptr;
+        o.q_out = (active && q_out) ? q_out + unit * wo : nullptr;
+        mulmod_w<C>(smem, S.B, 0, nullptr, o, Wd.sh, wo, Wd.inv, Wd.cpow);
+        // q must fit words_out words (range check of assign_integer(q, 2*enc_bits)): canonical q digits are in T
+        {
+            const int* Qf = (const int*)S.T + C::L * 32;
+            const int qbits = 64 * wo;
+            int bad = 0;
+#pragma unroll
+            for (int k = 0; k < C::BL; k++) {
+                const int p = role * C::BL + k;
+                const unsigned d = (unsigned)Qf[p * 32 + lane];
+                const int lo = W * p;
+                if (lo >= qbits) bad |= d != 0;
+                else if (lo + W > qbits) bad |= (d >> (qbits - lo)) != 0;
+            }
+            if (bad && active) atomicOr(flags, 1);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 struct Block28Key {
     int G = 0, BL = 0;
@@ -710,6 +751,7 @@ static cudaError_t witness_prepare_cfg(Block28Key* key, u64* d_gchain, bool gcha
     Wd.exp_bits = (int)n.bits(); Wd.sh = sh; Wd.inv = 1048576.0 / topd;
     CUW(cudaFuncSetAttribute(k_witness<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES));
     CUW(cudaFuncSetAttribute(k_gchain_w<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES));
+    CUW(cudaFuncSetAttribute(k_add_w<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES));
     if (gchain_ready) {        // g-chain records already produced (simple64): only convert them into table entries
         k_wtab<C><<<(key->n_bits + 63) / 64, 64, 0, st>>>(key->d_gwords, wi, d_gchain, wo, (int)key->n_bits, sh / 2, key->d_gtab);
     } else {                   // produce records and table entries with the witness engine itself
@@ -795,6 +837,16 @@ cudaError_t block28_tally(Block28Key* key, const u64* d_c, size_t count, u64* d_
 }
 
 
+template <class C>
+static cudaError_t add_cfg(Block28Key* key, const u64* d_c1, const u64* d_c2, int c_words, size_t count, u64* d_out, u64* d_q,
+                           int* d_flags, cudaStream_t st) {
+    size_t ctas = (count + 31) / 32, cap = (size_t)C::CTAS_PER_SM * key->sms;
+    if (ctas > cap) ctas = cap;
+    k_add_w<C><<<(unsigned)ctas, C::THREADS, C::SMEM_W_BYTES, st>>>(key->wdev, key->wit, d_c1, d_c2, c_words, count, d_out, d_q, d_flags);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // The witness engine needs canonical chain values below n^2 from the first step on: n must fill its declared width
 // (then g, r < 2^n_bits <= 2n <= n^2).  Other keys keep the simple64 witness path.
 bool block28_witness_supported(const Block28Key* key) { return key->use_mma && key->n.bits() == key->n_bits && key->n_bits >= 8; }
@@ -814,6 +866,15 @@ cudaError_t block28_witness(Block28Key* key, const u64* d_m, const u64* d_r, siz
     if (key->G == 8) return witness_cfg<Cfg2048>(key, d_m, d_r, count, d_c, d_records, d_offsets, d_digest, st);
     if (key->BL == 14) return witness_cfg<Cfg3072>(key, d_m, d_r, count, d_c, d_records, d_offsets, d_digest, st);
     return witness_cfg<Cfg4096>(key, d_m, d_r, count, d_c, d_records, d_offsets, d_digest, st);
+}
+
+cudaError_t block28_add(Block28Key* key, const u64* d_c1, const u64* d_c2, int c_words, size_t count, u64* d_out, u64* d_q,
+                        int* d_flags, cudaStream_t st) {
+    if (!count) return cudaSuccess;
+    if (key->G == 4) return add_cfg<Cfg1024>(key, d_c1, d_c2, c_words, count, d_out, d_q, d_flags, st);
+    if (key->G == 8) return add_cfg<Cfg2048>(key, d_c1, d_c2, c_words, count, d_out, d_q, d_flags, st);
+    if (key->BL == 14) return add_cfg<Cfg3072>(key, d_c1, d_c2, c_words, count, d_out, d_q, d_flags, st);
+    return add_cfg<Cfg4096>(key, d_c1, d_c2, c_words, count, d_out, d_q, d_flags, st);
 }
 
 }  // namespace pb200

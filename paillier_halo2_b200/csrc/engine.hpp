@@ -47,4 +47,8 @@ cudaError_t block28_witness(Block28Key*, const u64* d_m, const u64* d_r, size_t 
                             u64* d_records /*nullable*/, const u64* d_offsets /*nullable*/, u64* d_digest /*nullable*/,
                             cudaStream_t st);
 
+// one exact mul_mod per pair on the witness engine (requires block28_witness_prepare); range flag bit 0 when q does not fit
+cudaError_t block28_add(Block28Key*, const u64* d_c1, const u64* d_c2, int c_words, size_t count, u64* d_out, u64* d_q /*nullable*/,
+                        int* d_flags, cudaStream_t st);
+
 }  // namespace pb200

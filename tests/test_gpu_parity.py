@@ -312,3 +312,34 @@ def test_gpu_mulmod_cells_large(built_lib, n_bits):
         ctx = Context()
         BigUintChip(64, None).mul_mod(ctx, Assigned(decompose(a, L, 64), a, 64), Assigned(decompose(b, L, 64), b, 64), n2_as)
         assert cells == ctx.cells
+
+
+@pytest.mark.parametrize("n_bits", [128, 1024, 2048, 3072, 4096])
+def test_add_on_witness_engine_vs_oracle(built_lib, n_bits):
+    """pb200_add_batch on block28w (k_add_w): canonical, unreduced and half-width inputs, quotient included; both engines agree;
+    a quotient that does not fit 2*enc_bits raises PB200_ERR_RANGE like the chip's range check would fail."""
+    rng = random.Random(31 + n_bits)
+    if n_bits >= 1024:
+        n = workload.load_key(n_bits)["n"]
+    else:
+        n = rng.getrandbits(n_bits) | (1 << (n_bits - 1)) | 1
+    n2 = n * n
+    top = (1 << (2 * n_bits)) - 1
+    c1s = [rng.randrange(n2) for _ in range(37)] + [0, 1, n2 - 1, n2, n2 + 1, top >> 1, 1, rng.getrandbits(2 * n_bits)]
+    c2s = [rng.randrange(n2) for _ in range(37)] + [5, 1, n2 - 1, n2 - 1, 3, 2, top, rng.getrandbits(2 * n_bits - 3)]
+    want = [divmod(a * b, n2) for a, b in zip(c1s, c2s)]
+    assert all(q <= top for q, _ in want)
+    with PaillierKey(n, n + 1, n_bits, 64) as key:
+        assert key.witness_engine == "block28w"
+        res, qs = key.paillier_add_native(c1s, c2s, want_q=True)
+        assert list(zip(qs, res)) == want
+        assert key.paillier_add_native(c1s[:5], c2s[:5]) == [w[1] for w in want[:5]]
+        half = [rng.getrandbits(n_bits) for _ in range(9)]
+        res_h, q_h = key.paillier_add_native(half, half[::-1], c_bits=n_bits, want_q=True)
+        assert list(zip(q_h, res_h)) == [divmod(a * b, n2) for a, b in zip(half, half[::-1])]
+        with pytest.raises(Pb200Error) as e:
+            key.paillier_add_native([top], [top], want_q=True)
+        assert e.value.status == _lib.PB200_ERR_RANGE
+        key.set_engine(1)
+        res1, qs1 = key.paillier_add_native(c1s, c2s, want_q=True)
+        assert (res1, qs1) == (res, qs)

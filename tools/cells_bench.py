@@ -14,6 +14,15 @@ def run(n_bits, count, lookup, mont, reps=3):
         d_a = torch.from_numpy(c_w[:count].view(np.int64)).to(dev); d_b = torch.from_numpy(c_w[count:].view(np.int64)).to(dev)
         d_rem = torch.empty_like(d_a); d_q = torch.empty_like(d_a)
         key.add_dev(d_a.data_ptr(), d_b.data_ptr(), wo, count, d_rem.data_ptr(), d_q.data_ptr()); key.sync()
+        for eng in (0, 1):
+            key.set_engine(eng)
+            key.add_dev(d_a.data_ptr(), d_b.data_ptr(), wo, min(count, 4096), d_rem.data_ptr(), d_q.data_ptr()); key.sync()
+            t0 = time.perf_counter()
+            key.add_dev(d_a.data_ptr(), d_b.data_ptr(), wo, count, d_rem.data_ptr(), d_q.data_ptr()); key.sync()
+            dt = time.perf_counter() - t0
+            print(json.dumps({"n_bits": n_bits, "add_with_quotient": key.witness_engine, "pairs_per_s": count / dt,
+                              "hbm_GBps": count * 4 * wo * 8 / dt / 1e9}), flush=True)
+        key.set_engine(0)
         per = key.cells_layout(lookup)["cells_per_mulmod"]
         d_cells = torch.empty((count, per, 4), dtype=torch.int64, device=dev)
         stream = torch.cuda.ExternalStream(key.stream, device=dev)
