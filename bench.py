@@ -272,6 +272,93 @@ def run_tally(args):
         dist.destroy_process_group()
 
 
+def run_witness(args):
+    """BASELINE.json configs[3]: batched encrypt + the (q, rem) limb witness of every mul_mod PaillierChip::encrypt issues
+    (|n| = 3072 and 2^18 units over 8 GPUs in the config; --n-bits / --units select others).  Weak scaling: each rank runs
+    `units` units of its own slice; no collective on the data path.  Value = units/s, whole job."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from paillier_halo2_b200 import PaillierKey, _lib, workload
+    from paillier_halo2_b200.api import witness_digest, words_to_ints
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    kd = workload.load_key(N_BITS)
+    units = args.units
+    key = PaillierKey(kd["n"], kd["g_rand"], N_BITS, 64, device=local_rank)
+    m_w, r_w = workload.units(N_BITS, units, seed_offset=1000 * rank)
+    d_m = torch.from_numpy(m_w.view(np.int64)).cuda(); d_r = torch.from_numpy(r_w.view(np.int64)).cuda()
+    d_c = torch.empty((units, key.words_out), dtype=torch.int64, device="cuda")
+    d_dig = torch.empty(units, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.ExternalStream(key.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), min(units, 9472), d_c.data_ptr(), d_dig.data_ptr())
+    for _ in range(max(args.warmup - 1, 0)):
+        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), min(units, 9472), d_c.data_ptr(), d_dig.data_ptr())
+    sampler = ClockSampler(local_rank)
+    launches0 = lib.pb200_kernel_launches()
+    barrier()
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), units, d_c.data_ptr(), d_dig.data_ptr())
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.pb200_kernel_launches() - launches0
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    if rank == 0:
+        from oracle.paillier_oracle import encrypt_steps
+        w_mul, w_sqr = mac_counts(N_BITS)
+        pop_n = bin(kd["n"]).count("1")
+        pop_m = float(np.mean([bin(v).count("1") for v in words_to_ints(m_w[:256])]))
+        n_sqr, n_mul = kd["n"].bit_length(), pop_n + pop_m + 1
+        a_wit = n_sqr * w_sqr + n_mul * w_mul
+        dig = d_dig.cpu().numpy().view(np.uint64)
+        cs = d_c.cpu().numpy().view(np.uint64)
+        ok = True
+        for i in (0, units - 1):
+            mi, ri = words_to_ints(m_w[i:i + 1])[0], words_to_ints(r_w[i:i + 1])[0]
+            c, steps = encrypt_steps(kd["n"], kd["g_rand"], mi, ri)
+            gs = mi.bit_length() + bin(mi).count("1")
+            mine = [(x.q, x.rem) for x in steps[:gs] if x.kind == "mul"] + [(x.q, x.rem) for x in steps[gs:]]
+            ok = ok and int(dig[i]) == witness_digest(mine, key.words_out) and words_to_ints(cs[i:i + 1])[0] == c
+        peak, src = imad_peak()
+        ksec = dev_ms * 1e-3 / args.steps
+        line = {"metric": f"paillier_witness_units_per_s_n{N_BITS}", "value": world * units * args.steps / (dev_ms * 1e-3), "unit": "units/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int64 columns over signed 28-bit digits + s8 IMMA, exact (q, rem) tail",
+                "data": "synthetic",
+                "config": {"workload": f"batched encrypt + (q, rem) limb witness of every mul_mod, |n|={N_BITS}, {units} units per GPU per step "
+                                       "(BASELINE.json configs[3]), witness digested on the device", "engine": key.witness_engine,
+                           "chain": {"mod_sqr": n_sqr, "mod_mul": n_mul, "mac_per_unit": a_wit}},
+                "gpu_launches": int(launches), "clocks": clocks, "parity": ok,
+                "mul_mod_per_s": world * units * args.steps * (n_sqr + n_mul) / (dev_ms * 1e-3),
+                "roofline": {"bound": "imad", "achieved": units * a_wit / ksec / 1e12, "peak": peak / 1e12, "unit": "TMAC/s",
+                             "frac": units * a_wit / ksec / peak, "peak_source": src, "traffic": None}}
+        print(json.dumps(line), flush=True)
+    key.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -284,8 +371,9 @@ def main():
     ap.add_argument("--no-witness", action="store_true", help="skip the witness-mode leg")
     ap.add_argument("--engine", type=int, default=0)
     ap.add_argument("--n-bits", type=int, default=2048, help="key size |n| (default 2048, the BASELINE metric; others are the sweep)")
-    ap.add_argument("--workload", default="encrypt", choices=["encrypt", "tally"],
-                    help="encrypt: the BASELINE metric (default); tally: product of 2^20 ciphertexts sharded over the GPUs (configs[2])")
+    ap.add_argument("--workload", default="encrypt", choices=["encrypt", "tally", "witness"],
+                    help="encrypt: the BASELINE metric (default); tally: product of 2^20 ciphertexts sharded over the GPUs (configs[2]); "
+                         "witness: encrypt + (q, rem) witness of every mul_mod (configs[3]: --n-bits 3072 --units 32768 on 8 GPUs)")
     args = ap.parse_args()
     global N_BITS, METRIC
     N_BITS = args.n_bits
@@ -294,6 +382,8 @@ def main():
         return run_reference(args)
     if args.workload == "tally":
         return run_tally(args)
+    if args.workload == "witness":
+        return run_witness(args)
 
     import numpy as np
     import torch
@@ -481,7 +571,7 @@ def main():
         if not args.no_cpu and world >= 1:
             from oracle import cpu_ref
             threads = cpu_ref.hardware_threads()
-            sample = max(64, min(units, 256 * threads))
+            sample = max(64, min(units, int(256 * threads * (2048 / N_BITS) ** 3)))     # ~3-6 s of CPU work at every key size
             v, dt = cpu_baseline(threads, sample, kd)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"first {sample} units of the same batch, {dt:.1f} s, OpenSSL BIGNUM port of src/paillier.rs:87-92"}
