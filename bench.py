@@ -484,9 +484,11 @@ def main():
     if not args.no_witness:
         d_dig = torch.empty(units, dtype=torch.int64, device="cuda")
         d_cw = torch.empty((units, key.words_out), dtype=torch.int64, device="cuda")
-        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), min(units, 4096), d_cw.data_ptr(), d_dig.data_ptr())
+        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), units, d_cw.data_ptr(), d_dig.data_ptr())     # warm-up at full size
         barrier()
         wl0 = lib.pb200_kernel_launches()
+        w_sampler = ClockSampler(local_rank)
+        w_sampler.start()
         w_evs = []
         for _ in range(2):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -495,6 +497,7 @@ def main():
             e1.record(stream)
             w_evs.append((e0, e1))
         barrier()
+        w_clocks = w_sampler.stop()
         w_ms = sum(a.elapsed_time(b) for a, b in w_evs) / len(w_evs)
         t = torch.tensor([w_ms], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -521,7 +524,8 @@ def main():
                        "witness_stream_GBps": world * units * (w_sqr_n + w_mul_n) * 2 * key.words_out * 8 / (w_ms * 1e-3) / 1e9,
                        "chain": {"mod_sqr": w_sqr_n, "mod_mul": w_mul_n, "mac_per_unit": a_wit},
                        "frac_of_imad_peak": units * a_wit / (w_ms * 1e-3) / peak_w,
-                       "gpu_launches": int(lib.pb200_kernel_launches() - wl0),
+                       "gpu_launches": int(lib.pb200_kernel_launches() - wl0), "clocks": w_clocks,
+                       "ms_each": [a.elapsed_time(b) for a, b in w_evs],
                        "parity": ok,
                        "note": "reference chain (SURVEY.md A.5: bits(n) square_mod + popcount(n) + popcount(m) + 1 mul_mod per unit), exact (q, rem) "
                                "per step folded into a 64-bit digest per unit on the device; ciphertexts equal the fast chain's; the digests of "

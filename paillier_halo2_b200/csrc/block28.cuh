@@ -529,8 +529,11 @@ __device__ __noinline__ void phase_mma(int4* smem_base) {
     int* CA = ca_ptr<C>(S);
 #pragma unroll 1
     for (int q = 0; q < C::NPW; q++) {
-        const int U = warp + q * G;                              // tile pair: columns [P0, P0+16) = digits 4U .. 4U+3
-        if (U >= NP) break;
+        // tile pair: columns [P0, P0+16) = digits 4U .. 4U+3.  Tile pairs are dealt to the warps in serpentine order: the number
+        // of k-steps of a tile grows (phase C) or shrinks (phase B) linearly with U, a plain round-robin gives warp 0 the most
+        // expensive tile of every round (55 against 38 k-steps at |n| = 2048) and the phase ends at a CTA barrier (measured: +0.1 %)
+        const int U = ((q & 1) ? (G - 1 - warp) : warp) + q * G;
+        if (U >= NP) continue;
         const int P0 = P_BASE + 16 * U;
         // k-steps with some (k, p): 0 <= p - k <= K7-1, k in [32ks, 32ks+32), p in [P0, P0+16)
         int ks_lo = (P0 - (K7 - 1) - 31 + 31) / 32; if (P0 - (K7 - 1) - 31 <= 0) ks_lo = 0;

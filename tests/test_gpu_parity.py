@@ -343,3 +343,20 @@ def test_add_on_witness_engine_vs_oracle(built_lib, n_bits):
         key.set_engine(1)
         res1, qs1 = key.paillier_add_native(c1s, c2s, want_q=True)
         assert (res1, qs1) == (res, qs)
+
+
+@pytest.mark.parametrize("n_bits,count", [(1024, 6000), (2048, 2500)])
+def test_witness_engines_agree_at_scale(built_lib, n_bits, count):
+    """block28w against simple64 (independent arithmetic: 64-bit limbs, HAC Barrett, one thread per unit) on a ragged batch:
+    the 64-bit digest of every unit's (q, rem) stream and every ciphertext must agree; ciphertexts also equal the fast chain's."""
+    kd = workload.load_key(n_bits)
+    m_w, r_w = workload.units(n_bits, count, seed_offset=77)
+    ms, rs = words_to_ints(m_w), words_to_ints(r_w)
+    with PaillierKey(kd["n"], kd["g_rand"], n_bits, 64) as key:
+        assert key.witness_engine == "block28w"
+        cs_w, dig_w = key.encrypt_witness_digest(ms, rs)
+        cs_f = words_to_ints(key.encrypt_words(m_w, r_w))
+        key.set_engine(1)
+        cs_s, dig_s = key.encrypt_witness_digest(ms, rs)
+    assert cs_w == cs_s == cs_f
+    assert dig_w == dig_s
