@@ -65,8 +65,16 @@ struct Cfg {
 __device__ __forceinline__ int sgxt28(int x) {
     int r; asm("bfe.s32 %0, %1, 0, 28;" : "=r"(r) : "r"(x)); return r;
 }
+// acc += a * b (signed 32 x 32 -> 64).  Written as a carry pair on the two halves of the accumulator, which ptxas turns into ONE
+// IMAD.WIDE Rd, Ra, Rb, Rd with a 64-bit register addend; the plain `mad.wide.s32 d, a, b, d` is split by ptxas for sm_100a
+// into IMAD.WIDE .., RZ plus IADD3 / IADD3.X (two instructions per product instead of one).
 __device__ __forceinline__ void madw(long long& acc, int a, int b) {
+#ifndef PB200_SPLIT_MAC
+    asm("{ .reg .b32 l, h; mov.b64 {l, h}, %0; mad.lo.cc.s32 l, %1, %2, l; madc.hi.s32 h, %1, %2, h; mov.b64 %0, {l, h}; }"
+        : "+l"(acc) : "r"(a), "r"(b));
+#else
     asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b));
+#endif
 }
 
 enum Mode { M_FULL = 0, M_LT = 1, M_UTG = 2, M_SQ = 3 };

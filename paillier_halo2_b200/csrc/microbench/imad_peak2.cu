@@ -71,8 +71,15 @@ __global__ void __launch_bounds__(512) k_dfma(unsigned long long* out, unsigned 
 }
 
 __device__ __forceinline__ void madw(long long& acc, int a, int b) { asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b)); }
+// the same multiply-accumulate written as a carry pair on the two halves of the accumulator: ptxas turns it into ONE
+// IMAD.WIDE Rd, Ra, Rb, Rd (64-bit register addend) instead of IMAD.WIDE .., RZ + IADD3 + IADD3.X
+__device__ __forceinline__ void madw_fused(long long& acc, int a, int b) {
+    asm("{ .reg .b32 l, h; mov.b64 {l, h}, %0; mad.lo.cc.s32 l, %1, %2, l; madc.hi.s32 h, %1, %2, h; mov.b64 %0, {l, h}; }"
+        : "+l"(acc) : "r"(a), "r"(b));
+}
 
 // the real inner loop: operands from shared memory ([chunk][lane] int4), 37 column accumulators
+template <bool FUSED>
 __global__ void __launch_bounds__(256, 2) k_block19(unsigned long long* out, unsigned seed, int iters) {
     extern __shared__ int4 sm[];
     const int lane = threadIdx.x & 31;
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(256, 2) k_block19(unsigned long long* out, uns
                 const int y = 4 * c + e;
                 if (y < 19) {
 #pragma unroll
-                    for (int x = 0; x < 19; x++) madw(acc[x + y], a[x], b4[e]);
+                    for (int x = 0; x < 19; x++) { if (FUSED) madw_fused(acc[x + y], a[x], b4[e]); else madw(acc[x + y], a[x], b4[e]); }
                 }
             }
         }
@@ -126,7 +133,8 @@ int main() {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
     int sms = p.multiProcessorCount;
     unsigned long long* out; CK(cudaMalloc(&out, (size_t)sms * 16 * 1024 * 8));
-    CK(cudaFuncSetAttribute(k_block19, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 5 * 32 * 16));
+    CK(cudaFuncSetAttribute(k_block19<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 5 * 32 * 16));
+    CK(cudaFuncSetAttribute(k_block19<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 5 * 32 * 16));
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"results\": [\n", p.name, sms);
     bool first = true;
     auto emit = [&](const char* name, int threads, int cps, double ops, double ms) {
@@ -148,13 +156,15 @@ int main() {
         emit("dfma", threads, cps, (double)sms * cps * threads * iters * 64, ms);
     }
     for (int cps : {1, 2}) {
-        double ms = time_ms([&] { k_block19<<<sms * cps, 256, 2 * 8 * 5 * 32 * 16>>>(out, 12345u, 2000); }, 5);
+        double ms = time_ms([&] { k_block19<false><<<sms * cps, 256, 2 * 8 * 5 * 32 * 16>>>(out, 12345u, 2000); }, 5);
         emit("block19_mac", 256, cps, (double)sms * cps * 256 * 2000 * 361, ms);
+        ms = time_ms([&] { k_block19<true><<<sms * cps, 256, 2 * 8 * 5 * 32 * 16>>>(out, 12345u, 2000); }, 5);
+        emit("block19_mac_fused", 256, cps, (double)sms * cps * 256 * 2000 * 361, ms);
     }
     {   // sustained: ~2 s of block19 back to back
         cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         double ops = 0; CK(cudaEventRecord(e0));
-        for (int i = 0; i < 60; i++) { k_block19<<<sms * 2, 256, 2 * 8 * 5 * 32 * 16>>>(out, 7u, 20000); ops += (double)sms * 2 * 256 * 20000 * 361; }
+        for (int i = 0; i < 60; i++) { k_block19<false><<<sms * 2, 256, 2 * 8 * 5 * 32 * 16>>>(out, 7u, 20000); ops += (double)sms * 2 * 256 * 20000 * 361; }
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         emit("block19_mac_sustained", 256, 2, ops, ms);
