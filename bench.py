@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 N_BITS = 2048
 UNITS = 1 << 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_encrypt launch (ncu --set full, profiles/), keyed by (|n|, units)
-TRAFFIC_BYTES = {(2048, 1 << 16): 1524944000 + 797452544}   # profiles/ncu_k_encrypt_r01_final_summary.txt
+TRAFFIC_BYTES = {(2048, 1 << 16): 6121053000 + 806334464}   # profiles/ncu_k_encrypt_r01_fused_summary.txt
 METRIC = "paillier_enc_per_s_n2048"
 UNIT = "enc/s"
 

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpaillier_b200.so")
+LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(HERE, "libpaillier_b200.so")   # PB200_LIB: A/B builds (tools/build_variant.py)
 
 PB200_OK = 0
 PB200_ERR_INVALID_ARG = -1

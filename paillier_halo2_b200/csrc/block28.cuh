@@ -438,6 +438,46 @@ __device__ __noinline__ void phase_product(int4* smem_base, const int4* Y, int s
         const int d = warp + half * G;
         const int i_lo = half ? d - G + 1 : 0;
         const int i_hi = sqr ? d / 2 : (half ? G - 1 : d);
+#ifdef PB200_PHASEA_SINGLE
+        {   // one pass over the block pairs, all 2BL-1 columns live (A/B variant)
+            long long acc[C::NCOL];
+            zero_acc<C>(acc);
+            unsigned aa = v_addr + i_lo * (C::BLK4 * 16), ba = y_addr + (d - i_lo) * (C::BLK4 * 16);
+#pragma unroll 1
+            for (int i = i_lo; i <= i_hi; i++, aa += C::BLK4 * 16, ba -= C::BLK4 * 16) {
+                int a[C::CH * 4];
+#pragma unroll
+                for (int c = 0; c < C::CH; c++) { int4 v = lds128(aa + c * 512); a[4 * c] = v.x; a[4 * c + 1] = v.y; a[4 * c + 2] = v.z; a[4 * c + 3] = v.w; }
+                const bool diag = sqr && 2 * i == d;
+                if (sqr && !diag) {
+#pragma unroll
+                    for (int k = 0; k < C::BL; k++) a[k] += a[k];
+                }
+#pragma unroll
+                for (int c = 0; c < C::CH; c++) {
+                    int4 bv = lds128(ba + c * 512);
+                    int b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int y = 4 * c + e;
+                        if (y < BL) {
+                            if (diag) {
+                                const int by = b4[e], by2 = by + by;
+#pragma unroll
+                                for (int x = 0; x <= y; x++) madw(acc[x + y], a[x], x == y ? by : by2);
+                            } else {
+#pragma unroll
+                                for (int x = 0; x < BL; x++) madw(acc[x + y], a[x], b4[e]);
+                            }
+                        }
+                    }
+                }
+            }
+            int lo[C::CH * 4];
+            pend.spill = normalize<C>(acc, lo, pend.hi);
+            store_block<C>(blk_ptr<C>(S.T, d, lane), lo);
+        }
+#else
         long long carry;
         {   // columns 0 .. BL-1 -> Lo digits
             long long acc[BL];
@@ -462,6 +502,7 @@ __device__ __noinline__ void phase_product(int4* smem_base, const int4* Y, int s
 #pragma unroll
             for (int k = BL; k < C::CH * 4; k++) pend.hi[k] = 0;
         }
+#endif
         pend.carry = 0;
         pend.blk = d;
         if (half == 0 && njobs == 2) {
