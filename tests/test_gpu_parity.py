@@ -360,3 +360,27 @@ def test_witness_engines_agree_at_scale(built_lib, n_bits, count):
         cs_s, dig_s = key.encrypt_witness_digest(ms, rs)
     assert cs_w == cs_s == cs_f
     assert dig_w == dig_s
+
+
+def test_golden_cell_streams_on_gpu(built_lib):
+    """The GPU-produced cell streams against the committed fixtures (tests/golden/cells.json): whole encrypt flows at the
+    reference's sizes and single mul_mod groups at production sizes, by SHA-256 over the 32-byte cells."""
+    import hashlib, json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cells.json")))
+
+    def cell_hash(cells):
+        hh = hashlib.sha256()
+        for c in cells:
+            hh.update(int(c).to_bytes(32, "little"))
+        return hh.hexdigest()
+
+    for f in gold["flows"]:
+        with PaillierKey(h(f["n"]), h(f["g"]), f["enc_bits"], f["limb_bits"]) as key:
+            c, cells = key.encrypt_cells(h(f["m"]), h(f["r"]), f["lookup_bits"])
+        assert c == h(f["c"]) and len(cells) == f["n_cells"] and cell_hash(cells) == f["sha256"]
+        assert [hex(v) for v in cells[:6]] == f["first"] and [hex(v) for v in cells[-6:]] == f["last"]
+    for gq in gold["groups"]:
+        n = workload.load_key(gq["n_bits"])["n"]
+        with PaillierKey(n, n + 1, gq["n_bits"], 64) as key:
+            cells = key.mulmod_cells([(h(gq["a"]), h(gq["b"]), h(gq["q"]), h(gq["rem"]))], gq["lookup_bits"])[0]
+        assert len(cells) == gq["n_cells"] and cell_hash(cells) == gq["sha256"]

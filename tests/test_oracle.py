@@ -134,3 +134,32 @@ def test_zero_modulus_panics_like_num_bigint():
         paillier_enc_native(0, 1, 2, 3)
     with pytest.raises(ZeroDivisionError):
         paillier_add_native(0, 1, 2)
+
+
+def _cell_hash(cells):
+    import hashlib
+    h = hashlib.sha256()
+    for c in cells:
+        h.update(int(c).to_bytes(32, "little"))
+    return h.hexdigest()
+
+
+def test_golden_cell_streams():
+    """tests/golden/cells.json (tools/gen_golden_cells.py): the chip restatement reproduces the committed cell streams."""
+    import json, os
+    from oracle.paillier_oracle import Assigned, BigUintChip, Context, decompose, paillier_enc_test
+    from paillier_halo2_b200 import workload
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cells.json")))
+    for f in gold["flows"]:
+        hx = lambda k: int(f[k], 16)
+        ctx = paillier_enc_test(f["enc_bits"], f["limb_bits"], hx("n"), hx("g"), hx("m"), hx("r"), hx("c"), lookup_bits=f["lookup_bits"])
+        assert len(ctx.cells) == f["n_cells"] and _cell_hash(ctx.cells) == f["sha256"]
+        assert [hex(v) for v in ctx.cells[:6]] == f["first"] and [hex(v) for v in ctx.cells[-6:]] == f["last"]
+    for gq in gold["groups"]:
+        n = workload.load_key(gq["n_bits"])["n"]
+        L = 2 * gq["n_bits"] // 64
+        a, b = int(gq["a"], 16), int(gq["b"], 16)
+        ctx = Context()
+        out = BigUintChip(64, gq["lookup_bits"]).mul_mod(ctx, Assigned(decompose(a, L, 64), a, 64), Assigned(decompose(b, L, 64), b, 64),
+                                                         Assigned(decompose(n * n, L, 64), n * n, 64))
+        assert out.value == int(gq["rem"], 16) and len(ctx.cells) == gq["n_cells"] and _cell_hash(ctx.cells) == gq["sha256"]
