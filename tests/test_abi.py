@@ -68,3 +68,16 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f
+
+
+def test_new_entry_points_reject_null_arguments(built_lib):
+    """argument validation of the witness-digest, add and cell entry points needs no device"""
+    lib = built_lib
+    null = C.c_void_p()
+    assert lib.pb200_encrypt_witness_digest_dev(null, None, None, 1, None, None) == _lib.PB200_ERR_INVALID_ARG
+    assert lib.pb200_mulmod_cells_batch(null, None, None, None, None, 1, 15, 0, None) == _lib.PB200_ERR_INVALID_ARG
+    assert lib.pb200_mulmod_cells_batch_dev(null, None, None, None, None, 1, 15, 0, None) == _lib.PB200_ERR_INVALID_ARG
+    assert lib.pb200_assign_cells_batch(null, None, 1, 128, 15, 0, None) == _lib.PB200_ERR_INVALID_ARG
+    assert lib.pb200_key_n2_cells(null, 15, 0, None) == _lib.PB200_ERR_INVALID_ARG
+    assert lib.pb200_cells_layout(null, 15, None) == _lib.PB200_ERR_INVALID_ARG
+    assert lib.pb200_key_witness_engine(null) == b""
