@@ -545,10 +545,11 @@ __device__ __forceinline__ void mma_s8(int (&d)[4], unsigned a0, unsigned a1, un
 __device__ __forceinline__ int sgxt7(int x) { int r; asm("bfe.s32 %0, %1, 0, 7;" : "=r"(r) : "r"(x)); return r; }
 // one 28-bit digit -> four signed 7-bit digits packed in a word (the top one absorbs the remainder, |.| <= 65)
 __device__ __forceinline__ unsigned split7_pack(int d) {
-    int e0 = sgxt7(d); d = (d - e0) >> 7;
-    int e1 = sgxt7(d); d = (d - e1) >> 7;
-    int e2 = sgxt7(d); d = (d - e2) >> 7;
-    return (unsigned)(e0 & 255) | ((unsigned)(e1 & 255) << 8) | ((unsigned)(e2 & 255) << 16) | ((unsigned)d << 24);
+    // bias every 7-bit field by 64 so that the three low fields can be cut out as unsigned bit fields, then remove the bias
+    // per byte: with f in [0, 127], (f + 0x40) ^ 0x80 == f - 64 (mod 256) and f + 0x40 never carries into the next byte
+    const unsigned dp = (unsigned)d + (64u | (64u << 7) | (64u << 14));
+    const unsigned x = (dp & 0x7Fu) | ((dp << 1) & 0x7F00u) | ((dp << 2) & 0x7F0000u);
+    return ((x + 0x404040u) ^ 0x808080u) | ((unsigned)((int)dp >> 21) << 24);
 }
 
 // A-operand bytes live in the Q buffer: As[lane][RS]; output arrays LO (in T blocks G..2G-1) and CA (in B):
