@@ -25,6 +25,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  NCCL prints its version banner to file descriptor 1 when the first communicator is
+# created, so everything except the result line is sent to stderr: fd 1 is duplicated for the result, then pointed at fd 2.
+_RESULT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _RESULT.write(json.dumps(line) + "\n")
+    _RESULT.flush()
+
+
 N_BITS = 2048
 UNITS = 1 << 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_encrypt launch (ncu --set full, profiles/), keyed by (|n|, units)
@@ -141,7 +152,7 @@ def run_reference(args):
                          "sample": f"{sample} units x {args.steps} steps, OpenSSL BN_mod_exp x2 + BN_mod_mul per unit"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def hbm_peak():
@@ -266,7 +277,7 @@ def run_tally(args):
                              "frac": shard * w_mul / ksec / peak, "peak_source": src,
                              "hbm_gbs_achieved": shard * key.words_out * 8 / ksec / 1e9,
                              "note": "per-GPU shard fold kernel (k_tally x2 launches); one modmul per 512 B read: compute-bound, HBM GB/s reported because north_star asks for it"}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     key.close()
     if world > 1:
         dist.destroy_process_group()
@@ -353,7 +364,7 @@ def run_witness(args):
                 "mul_mod_per_s": world * units * args.steps * (n_sqr + n_mul) / (dev_ms * 1e-3),
                 "roofline": {"bound": "imad", "achieved": units * a_wit / ksec / 1e12, "peak": peak / 1e12, "unit": "TMAC/s",
                              "frac": units * a_wit / ksec / peak, "peak_source": src, "traffic": None}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     key.close()
     if world > 1:
         dist.destroy_process_group()
@@ -579,7 +590,7 @@ def main():
             v, dt = cpu_baseline(threads, sample, kd)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"first {sample} units of the same batch, {dt:.1f} s, OpenSSL BIGNUM port of src/paillier.rs:87-92"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     key.close()
     if world > 1:
         dist.destroy_process_group()
