@@ -341,7 +341,10 @@ int pb200_encrypt_witness_batch(pb200_key* k, const uint64_t* m, const uint64_t*
     const size_t rec_words = 2 * (size_t)k->words_out;
     uint64_t fixed = pb200_witness_records_for(k, m) - popcount_words(m, k->words_in);  // bits(n)+popcount(n)+1
     size_t max_unit_records = (size_t)fixed + k->n_bits;
-    const size_t budget = (size_t)256 << 20;  // bytes of staged records per chunk
+    // bytes of staged records per chunk: a chunk costs one kernel launch whose latency is that of ONE unit's chain (147 ms at
+    // |n| = 2048) however few units it holds, so chunks are made as large as a 2 GiB staging buffer allows when memory is plentiful
+    size_t budget = (size_t)256 << 20;
+    { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr > ((size_t)16 << 30)) budget = (size_t)2 << 30; }
     size_t auto_units = budget / (max_unit_records * rec_words * sizeof(u64));
     if (auto_units < 1) auto_units = 1;
     size_t chunk_units = max_chunk_units ? max_chunk_units : auto_units;
