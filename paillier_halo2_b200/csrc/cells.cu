@@ -337,6 +337,26 @@ __device__ __forceinline__ W4 chunk_cell(u64 lo, u64 hi, int sub, int pad, int l
     return r;
 }
 
+// 192-bit accumulator of 64 x 64 -> 128-bit products on 32-bit words, carry pairs that ptxas fuses into IMAD.WIDE.U32(.X):
+// products at even word offsets (a0 b0 at word 0, a1 b1 at word 2) go to e0..e4, the two cross products (word 1) to o1..o3, kept
+// apart so that every multiply-add lands on an aligned register pair; value = E + (O << 32).  Up to 2^31 products.
+struct Acc192 {
+    unsigned e0, e1, e2, e3, e4, o1, o2, o3;
+    __device__ __forceinline__ void clear() { e0 = e1 = e2 = e3 = e4 = o1 = o2 = o3 = 0; }
+    __device__ __forceinline__ void words(u64& w0, u64& w1, u64& w2) const {
+        w0 = ((u64)e1 << 32) | e0; w1 = ((u64)e3 << 32) | e2; w2 = e4;
+        const u64 x0 = (u64)o1 << 32, x1 = ((u64)o3 << 32) | o2;
+        asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u64 %2, %2, 0;" : "+l"(w0), "+l"(w1), "+l"(w2) : "l"(x0), "l"(x1));
+    }
+};
+__device__ __forceinline__ void mac64(Acc192& A, u64 a, u64 b) {
+    const unsigned a0 = (unsigned)a, a1 = (unsigned)(a >> 32), b0 = (unsigned)b, b1 = (unsigned)(b >> 32);
+    asm("mad.lo.cc.u32 %0, %5, %7, %0; madc.hi.cc.u32 %1, %5, %7, %1; madc.lo.cc.u32 %2, %6, %8, %2; madc.hi.cc.u32 %3, %6, %8, %3; addc.u32 %4, %4, 0;"
+        : "+r"(A.e0), "+r"(A.e1), "+r"(A.e2), "+r"(A.e3), "+r"(A.e4) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;" : "+r"(A.o1), "+r"(A.o2), "+r"(A.o3) : "r"(a0), "r"(b1));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;" : "+r"(A.o1), "+r"(A.o2), "+r"(A.o3) : "r"(a1), "r"(b0));
+}
+
 template <bool MONT>
 __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_cpl, u64 m_eq, u64 m_eqs, const u64* __restrict__ consts,
                                                            const u64* __restrict__ a, const u64* __restrict__ b,
@@ -373,18 +393,25 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
         }
         // no-carry columns ab and q*n^2, the sums, and d
         for (int c = lane; c < L; c += 32) {
-            // one running accumulator per product; its value when j reaches c + 1 is column c, the rest is column c + L
-            u64 ah0 = 0, ah1 = 0, ah2 = 0, qh0 = 0, qh1 = 0, qh2 = 0, al0 = 0, al1 = 0, al2 = 0, ql0 = 0, ql1 = 0, ql2 = 0;
-            int bi = c;
+            // one running accumulator per product; its value when j reaches c + 1 is column c, the rest is column c + L.
+            // The lanes of a warp switch at j = c + 1 in [k0 + 1, k0 + 32] (k0 = c - lane is warp-uniform): only that segment of
+            // the loop carries the snapshot.
+            const int k0 = c - lane;
+            Acc192 A, Q, As, Qs;
+            A.clear(); Q.clear(); As.clear(); Qs.clear();
+            int bi = c, j = 0;
+#define PB200_COL_STEP() { const u64 aj = s_a[j], qj = s_q[j], bv = s_b[bi], nv = s_n[bi]; mac64(A, aj, bv); mac64(Q, qj, nv); bi = bi ? bi - 1 : L - 1; }
 #pragma unroll 4
-            for (int j = 0; j < L; j++) {
-                if (j == c + 1) { al0 = ah0; al1 = ah1; al2 = ah2; ql0 = qh0; ql1 = qh1; ql2 = qh2; }
-                const u64 aj = s_a[j], qj = s_q[j], bv = s_b[bi], nv = s_n[bi];
-                mac3p(ah0, ah1, ah2, aj * bv, __umul64hi(aj, bv));
-                mac3p(qh0, qh1, qh2, qj * nv, __umul64hi(qj, nv));
-                bi = bi ? bi - 1 : L - 1;
-            }
-            if (c == L - 1) { al0 = ah0; al1 = ah1; al2 = ah2; ql0 = qh0; ql1 = qh1; ql2 = qh2; }
+            for (; j <= k0; j++) PB200_COL_STEP()
+            const int j_sw = min(k0 + 32, L - 1);
+#pragma unroll 2
+            for (; j <= j_sw; j++) { if (j == c + 1) { As = A; Qs = Q; } PB200_COL_STEP() }
+#pragma unroll 4
+            for (; j < L; j++) PB200_COL_STEP()
+#undef PB200_COL_STEP
+            if (c == L - 1) { As = A; Qs = Q; }
+            u64 ah0, ah1, ah2, qh0, qh1, qh2, al0, al1, al2, ql0, ql1, ql2;
+            A.words(ah0, ah1, ah2); Q.words(qh0, qh1, qh2); As.words(al0, al1, al2); Qs.words(ql0, ql1, ql2);
             asm("sub.cc.u64 %0, %0, %3; subc.cc.u64 %1, %1, %4; subc.u64 %2, %2, %5;" : "+l"(ah0), "+l"(ah1), "+l"(ah2) : "l"(al0), "l"(al1), "l"(al2));
             asm("sub.cc.u64 %0, %0, %3; subc.cc.u64 %1, %1, %4; subc.u64 %2, %2, %5;" : "+l"(qh0), "+l"(qh1), "+l"(qh2) : "l"(ql0), "l"(ql1), "l"(ql2));
 #pragma unroll
