@@ -663,36 +663,26 @@ __device__ __forceinline__ void q1_to_bytes(Smem<C>& S, int warp, int lane) {
     __syncthreads();
 }
 
-// phase B tail: ripple LO/CA (digits jj = j + 2, two guard digits) into strict q-hat digits, as s8 rows in As
+// phase B tail: q-hat digits (jj = j + 2, two guard digits below) as s8 rows in As.  The digits are NOT rippled: LO + CA is within
+// 2^27 + 2^17 in magnitude, which the s8 split absorbs in its top piece ([-65, 64]); q-hat is the same integer, phase C is exact on
+// any digit representation and the s32 columns stay below 608 * 65 * 64.  Only the two guard digits feed a carry into digit 0.
+// (tests/model_block28.py models exactly this; the rippled version cost a 19-step serial chain and two more CTA barriers.)
 template <class C>
 __device__ __forceinline__ void qhat_to_bytes(Smem<C>& S, int warp, int lane) {
     const int* LO = lo_ptr<C>(S);
     const int* CA = ca_ptr<C>(S);
     int carry = 0;
-    if (warp == 0) {      // the guard digits only feed their carry into digit 0
+    if (warp == 0) {
         int t0 = LO[dl_index(0, lane)];
         carry = (t0 - sgxt28(t0)) >> W;
         int t1 = LO[dl_index(1, lane)] + CA[dl_index(1, lane)] + carry;
         carry = (t1 - sgxt28(t1)) >> W;
     }
-    unsigned w[C::BL];
+    unsigned* row = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + warp * C::BL;      // As (Q buffer) is dead since phase B's MMAs ended
 #pragma unroll
     for (int k = 0; k < C::BL; k++) {
         const int jj = warp * C::BL + k + 2;
-        int tt = (LO[dl_index(jj, lane)] + CA[dl_index(jj, lane)] + (1 << (W - 1))) + carry;
-        carry = tt >> W;
-        w[k] = split7_pack((tt & ((1 << W) - 1)) - (1 << (W - 1)));
-    }
-    __syncthreads();                                              // every warp has read LO/CA of its block
-    unsigned* row = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + warp * C::BL;
-#pragma unroll
-    for (int k = 0; k < C::BL; k++) row[k] = w[k];
-    __syncthreads();
-    if (warp + 1 < C::G) {                                        // carry out of this block into the lowest 7-bit digit of the next
-        unsigned* nx = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + (warp + 1) * C::BL;
-        unsigned v = *nx;
-        int e0 = (int)(signed char)(v & 255) + carry;
-        *nx = (v & ~255u) | ((unsigned)e0 & 255u);
+        row[k] = split7_pack(LO[dl_index(jj, lane)] + CA[dl_index(jj, lane)] + (k == 0 ? carry : 0));
     }
     __syncthreads();
 }

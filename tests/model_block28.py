@@ -283,14 +283,17 @@ def mulmod_imma(P, keyc, A, B, sqr=False):
     # phase B: digits j >= L of q1*mu, two guard digits below
     cols = conv_columns(digits7(q1), digits7(mu_d), 4 * (L - 2), 4 * 2 * L)
     lo, carry = fold28(cols)                      # index jj = j - (L-2)
+    # q-hat digits are NOT rippled: lo + carry-in of the fold is already within the range the s8 split absorbs
+    # (|d| <= 2^27 + 2^17, top 7-bit piece within [-65, 64]); only the two guard digits feed a carry into digit 0
     qh = []
     c = 0
-    for jj in range(len(lo)):
+    for jj in range(2):
         t = lo[jj] + (carry[jj - 1] if jj else 0) + c
-        d = sgxt(t)
-        c = (t - d) >> W
-        if jj >= 2:
-            qh.append(d)
+        c = (t - sgxt(t)) >> W
+    for jj in range(2, len(lo)):
+        d = lo[jj] + carry[jj - 1] + (c if jj == 2 else 0)
+        assert abs(d) < (1 << W) - (1 << 21)
+        qh.append(d)
     # phase C: low L digits of qh*Nt (exact)
     cols = conv_columns(digits7(qh), digits7(Nt_d), 0, 4 * L)
     lo, carry = fold28(cols)
@@ -330,12 +333,11 @@ def _imma_parts(P, keyc, A, B, sqr):
     cols = conv_columns(digits7(q1), digits7(mu_d), 4 * (L - 2), 4 * 2 * L)
     lo, carry = fold28(cols)
     qh, c = [], 0
-    for jj in range(len(lo)):
+    for jj in range(2):
         t = lo[jj] + (carry[jj - 1] if jj else 0) + c
-        d = sgxt(t)
-        c = (t - d) >> W
-        if jj >= 2:
-            qh.append(d)
+        c = (t - sgxt(t)) >> W
+    for jj in range(2, len(lo)):
+        qh.append(lo[jj] + carry[jj - 1] + (c if jj == 2 else 0))      # not rippled (see mulmod_imma)
     qh = qh[:L]
     cols = conv_columns(digits7(qh), digits7(Nt_d), 0, 4 * L)
     lo, carry = fold28(cols)
