@@ -66,6 +66,41 @@ __device__ __forceinline__ void load_value(int4* buf, const u64* src, int nwords
     __syncthreads();
 }
 
+// The 32 inputs of a CTA step are contiguous in global memory: copy them with coalesced loads into a word-major staging area
+// ([word][lane], row stride 33 to spread the transposing stores over the banks) and cut the digits out of shared memory
+// (a lane reading its own 512-byte ciphertext word by word touches 32 different lines per instruction).
+template <class C>
+__device__ __forceinline__ void stage_words(u64* stage, const u64* src, int units_avail, int nwords) {
+    const int total = 32 * nwords;
+    for (int idx = threadIdx.x; idx < total; idx += C::THREADS) {
+        const int l = idx / nwords, wi = idx - l * nwords;
+        stage[wi * 33 + l] = l < units_avail ? src[(size_t)l * nwords + wi] : 0;
+    }
+    __syncthreads();
+}
+template <class C>
+__device__ __forceinline__ void load_value_staged(int4* buf, const u64* stage, int nwords, int role, int lane) {
+    int a[C::CH * 4];
+    int carry = 0;
+#pragma unroll
+    for (int k = 0; k < C::BL; k++) {
+        int bit = W * (role * C::BL + k);
+        int wi = bit >> 6, sh = bit & 63;
+        u64 lo = wi < nwords ? stage[wi * 33 + lane] : 0, hi = wi + 1 < nwords ? stage[(wi + 1) * 33 + lane] : 0;
+        u64 v = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+        int t = (int)(v & ((1u << W) - 1)) + carry;
+        int d = sgxt28(t);
+        carry = (t - d) >> W;
+        a[k] = d;
+    }
+#pragma unroll
+    for (int k = C::BL; k < C::CH * 4; k++) a[k] = 0;
+    store_block<C>(blk_ptr<C>(buf, role, lane), a);
+    __syncthreads();
+    if (role + 1 < C::G) *(int*)blk_ptr<C>(buf, role + 1, lane) += carry;
+    __syncthreads();
+}
+
 template <class C>
 __device__ __forceinline__ void set_one(int4* buf, int role, int lane) {
     int a[C::CH * 4];
@@ -287,7 +322,9 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, 
     for (size_t it = 0; it < max_iters; it++) {
         size_t u = first + it * stride;
         const bool have = u < count;
-        load_value<C>(S.B, c + (have ? u : count - 1) * K.words_out, K.words_out, role, lane);
+        const size_t base = (size_t)blockIdx.x * 32 + it * stride;                  // first unit of this CTA step
+        stage_words<C>((u64*)S.T, c + base * K.words_out, base < count ? (int)(count - base < 32 ? count - base : 32) : 0, K.words_out);
+        load_value_staged<C>(S.B, (const u64*)S.T, K.words_out, role, lane);
         if (!have) {                                   // lanes without an input multiply by one
             int a[C::CH * 4];
 #pragma unroll
