@@ -367,8 +367,8 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
     const u64* c_accm = consts + 2 * L + 4 + 4 * NC;      // Montgomery forms of q_acc, mod_acc: [NC][4] each
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64* s_n = sm;
-    u64* s_a = sm + L + (size_t)warp * (4 * L + 3 * NC + 1);
-    u64* s_b = s_a + L; u64* s_q = s_b + L; u64* s_r = s_q + L; u64* s_d = s_r + L;
+    u64* s_w = sm + L + (size_t)warp * (8 * L + 3 * NC + 1);      // per warp: two limb sets (double buffer), then d
+    u64* s_d = s_w + 8 * L;
     const u64* c_wmax = consts + 2 * L;        // consts: n2 limbs [L][2], word_max (4 words), q_acc [NC][2], mod_acc [NC][2]
     const u64* c_qacc = c_wmax + 4;
     const u64* c_macc = c_qacc + 2 * NC;
@@ -376,11 +376,27 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
     __syncthreads();
     const u64 wm0 = c_wmax[0], wm1 = c_wmax[1], wm2 = c_wmax[2];
     const int pad_l = Y.lookup_bits ? Y.lookup_bits - 64 % Y.lookup_bits : 0, pad_c = Y.lookup_bits ? Y.lookup_bits - Y.carry_bits % Y.lookup_bits : 0;
-    for (size_t g = (size_t)blockIdx.x * 4 + warp; g < count; g += (size_t)gridDim.x * 4) {
+    // the limbs of the NEXT group travel global -> shared with cp.async while the current group is expanded
+    auto prefetch = [&](size_t g, int buf) {
+        u64* dst = s_w + buf * 4 * L;
         for (int i = lane; i < L; i += 32) {
-            s_a[i] = a[g * L + i]; s_b[i] = b[g * L + i]; s_q[i] = q[g * L + i]; s_r[i] = rem[g * L + i];
+            const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst + i);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d0), "l"(a + g * L + i));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d0 + 8 * L), "l"(b + g * L + i));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d0 + 16 * L), "l"(q + g * L + i));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d0 + 24 * L), "l"(rem + g * L + i));
         }
+        asm volatile("cp.async.commit_group;");
+    };
+    const size_t g_first = (size_t)blockIdx.x * 4 + warp, g_step = (size_t)gridDim.x * 4;
+    int buf = 0;
+    if (g_first < count) prefetch(g_first, 0);
+    for (size_t g = g_first; g < count; g += g_step, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;");
         __syncwarp();
+        if (g + g_step < count) prefetch(g + g_step, buf ^ 1);
+        u64* s_a = s_w + buf * 4 * L;
+        u64* s_b = s_a + L; u64* s_q = s_b + L; u64* s_r = s_q + L;
         const size_t base = g * (size_t)Y.n_cells;
         // q and rem: limb cells with their range-check chunks
         for (int c = lane; c < Y.off_ab; c += 32) {
@@ -578,7 +594,7 @@ cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_
     if (!count) return cudaSuccess;
     if (Y.limb_bits == 64 && Y.n_cells < 65536) {
         const size_t L = Y.L, NC = 2 * L - 1;
-        const size_t smem64 = (L + 4 * (4 * L + 3 * NC + 1)) * sizeof(u64);
+        const size_t smem64 = (L + 4 * (8 * L + 3 * NC + 1)) * sizeof(u64);
         static bool attr64 = false;
         if (!attr64) {
             cudaError_t e = cudaFuncSetAttribute(k_cells_mulmod64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
