@@ -87,11 +87,11 @@ static void paillier_enc_add(Context* ctx, const RangeChip* range, size_t enc_bi
 
 static BigUint odd(BigUint v) { if (v.is_zero()) v = BigUint(1); v.w[0] |= 1; return v; }     // the GPU path's contract: odd, non-zero n
 
-static void test_paillier_encryption(size_t ENC_BIT_LEN, size_t LIMB_BIT_LEN, int rounds) {
+static void test_paillier_encryption(size_t ENC_BIT_LEN, size_t LIMB_BIT_LEN, int rounds, uint32_t K = 16, uint32_t LOOKUP = 15) {
     for (int it = 0; it < rounds; it++) {
         std::vector<std::string> why; Context kept;
         BigUint n, g, m, r;
-        bool ok = base_test().k(16).lookup_bits(15).expect_satisfied(true).run((uint32_t)LIMB_BIT_LEN, [&](Context* ctx, const RangeChip* range) {
+        bool ok = base_test().k(K).lookup_bits(LOOKUP).expect_satisfied(true).run((uint32_t)LIMB_BIT_LEN, [&](Context* ctx, const RangeChip* range) {
             n = odd(gen_biguint(ENC_BIT_LEN)); g = gen_biguint(ENC_BIT_LEN); m = gen_biguint(ENC_BIT_LEN); r = gen_biguint(ENC_BIT_LEN);
             if (it == 1) m = BigUint();                                  // empty g-chain
             if (it == 2) { r = BigUint(1); m = BigUint(1); }
@@ -107,10 +107,10 @@ static void test_paillier_encryption(size_t ENC_BIT_LEN, size_t LIMB_BIT_LEN, in
             CHECK(!bad.mul_mods.empty());
             size_t victim = bad.mul_mods[bad.mul_mods.size() / 2].first_cell;
             bad.cells[victim][0] ^= 1;       // lowest limb of q of one mul_mod
-            CHECK(!check_constraints(bad, (uint32_t)LIMB_BIT_LEN, 15).empty());
+            CHECK(!check_constraints(bad, (uint32_t)LIMB_BIT_LEN, LOOKUP).empty());
             Context bad2 = kept;
             bad2.cells[bad2.mul_mods.back().first_cell + 3][0] += 1;     // a range-check chunk
-            CHECK(!check_constraints(bad2, (uint32_t)LIMB_BIT_LEN, 15).empty());
+            CHECK(!check_constraints(bad2, (uint32_t)LIMB_BIT_LEN, LOOKUP).empty());
         }
         printf("test_paillier_encryption[%zu/%zu] round %d ok: %zu cells, %zu mul_mod groups\n", ENC_BIT_LEN, LIMB_BIT_LEN, it, kept.cells.size(), kept.mul_mods.size());
     }
@@ -162,6 +162,7 @@ int main(int argc, char** argv) {
     test_encryption_addition(264, 88, 2);
     test_paillier_encryption(264, 88, 1);       // the reference's second limb shape on the encrypt flow
     test_encryption_addition(128, 64, 1);
+    test_paillier_encryption(128, 64, 1, 14, 13);   // the shape of src/bench.rs:161-164 (k = 14, lookup_bits = 13)
     printf("all host tests passed\n");
     return 0;
 }
