@@ -173,6 +173,22 @@ __device__ __forceinline__ W4 fr_to_mont_u64(u64 x) {
     return r;
 }
 
+// (a + b) mod p for a, b < p, branch-free
+__device__ __forceinline__ W4 fr_add(W4 a, const W4& b) {
+    w4_add(a, b);                                   // < 2p < 2^255: no carry out of 256 bits
+    W4 d = a, pp;
+    pp.w[0] = FR_P[0]; pp.w[1] = FR_P[1]; pp.w[2] = FR_P[2]; pp.w[3] = FR_P[3];
+    u64 borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const u64 x = d.w[i], y = pp.w[i], t = x - y, b1 = x < y, t2 = t - borrow, b2 = t < borrow;
+        d.w[i] = t2; borrow = b1 | b2;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) a.w[i] = borrow ? a.w[i] : d.w[i];
+    return a;
+}
+
 enum CellKind { CK_RAW = 0, CK_SMALL = 1, CK_WIDE = 2 };   // already in output form / one-word value / up to four words
 template <bool MONT>
 __device__ __forceinline__ void store_cell_k(u64* out, size_t cell, W4 v, int kind) {
@@ -438,10 +454,18 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
                     ab.w[0] = h ? ah0 : al0; ab.w[1] = h ? ah1 : al1; ab.w[2] = h ? ah2 : al2; ab.w[3] = 0;
                     qn.w[0] = h ? qh0 : ql0; qn.w[1] = h ? qh1 : ql1; qn.w[2] = h ? qh2 : ql2; qn.w[3] = 0;
                     store_cell_k<MONT>(out, base + Y.off_ab + col, ab, CK_WIDE);
-                    store_cell_k<MONT>(out, base + Y.off_qn + col, qn, CK_WIDE);
                     W4 qp = qn;
                     if (h == 0) mac3p(qp.w[0], qp.w[1], qp.w[2], s_r[c], 0);
-                    store_cell_k<MONT>(out, base + Y.off_qnp + col, qp, CK_WIDE);
+                    if (MONT) {
+                        // Montgomery form is linear: the cell of qn + rem is the cell of qn plus the (one-word) cell of rem, and for the
+                        // upper columns it IS the cell of qn: one general conversion serves two cells
+                        const W4 qn_m = fr_to_mont(qn);
+                        store_cell_k<true>(out, base + Y.off_qn + col, qn_m, CK_RAW);
+                        store_cell_k<true>(out, base + Y.off_qnp + col, h == 0 ? fr_add(qn_m, fr_to_mont_u64(s_r[c])) : qn_m, CK_RAW);
+                    } else {
+                        store_cell_k<false>(out, base + Y.off_qn + col, qn, CK_RAW);
+                        store_cell_k<false>(out, base + Y.off_qnp + col, qp, CK_RAW);
+                    }
                     // d = ab - qp + word_max (two's complement over 3 words)
                     u64 d0, d1, d2;
                     asm("sub.cc.u64 %0, %3, %6; subc.cc.u64 %1, %4, %7; subc.u64 %2, %5, %8;"
