@@ -686,12 +686,10 @@ cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_
     if (Y.limb_bits == 64 && Y.n_cells < 65536) {
         const size_t L = Y.L, NC = 2 * L - 1;
         const size_t smem64 = (L + 4 * (8 * L + 3 * NC + 1)) * sizeof(u64);
-        static bool attr64 = false;
-        if (!attr64) {
-            cudaError_t e = cudaFuncSetAttribute(k_cells_mulmod64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cells_mulmod64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        {   // per device (a function attribute belongs to the current context): set on every launch, it is a host-side table write
+            cudaError_t e = mont ? cudaFuncSetAttribute(k_cells_mulmod64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)
+                                 : cudaFuncSetAttribute(k_cells_mulmod64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             if (e != cudaSuccess) return e;
-            attr64 = true;
         }
         const u64 m_eqs = (0x100000000ull + Y.eq_stride - 1) / Y.eq_stride;
         const u64 m_cpl = (0x100000000ull + Y.cpl - 1) / Y.cpl, m_eq = (Y.kc + Y.xc) ? (0x100000000ull + (Y.kc + Y.xc) - 1) / (Y.kc + Y.xc) : 0;
@@ -705,11 +703,9 @@ cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_
         return cudaGetLastError();
     }
     const size_t smem = cells_mulmod_smem(Y);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_cells_mulmod, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     size_t grid = count < (size_t)sms * 8 ? count : (size_t)sms * 8;
     k_cells_mulmod<<<(unsigned)grid, 128, smem, st>>>(Y, d_consts, d_a, d_b, d_q, d_rem, count, words, mont, d_out, d_flags);
