@@ -17,7 +17,7 @@
 namespace pb200 {
 using namespace b28;
 
-constexpr int WIN = 5;                 // sliding window of the r-chain
+constexpr int WIN = 6;                 // sliding window of the r-chain (6: 293 + 31 multiplications at |n| = 2048; 5: 341 + 15)
 constexpr int TABN = 1 << (WIN - 1);   // odd powers r^1, r^3, ..., r^(2*TABN-1)
 constexpr int SCRATCH_ENTRIES = TABN + 2;   // + r^2 (table build) + rn (kept while g^m is computed)
 
