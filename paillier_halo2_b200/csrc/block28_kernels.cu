@@ -3,7 +3,7 @@
 // Replaces, for `count` independent units: g.modpow(m, n2), r.modpow(n, n2) and the final product of
 // paillier_enc_native (/root/reference/src/paillier.rs:87-92), and the fold of paillier_add_native
 // (:94-97).  Chain per unit (all modulo Nt, a multiple of n^2):
-//   r^n : left-to-right sliding window (w = 5) over the per-key exponent n; the 16 odd powers of r live in
+//   r^n : left-to-right sliding window (w = 6) over the per-key exponent n; the 32 odd powers of r live in
 //         a per-CTA global scratch table (L2-resident), the window schedule is computed once per key;
 //   g^m : fixed-base comb, w-bit windows (w = 12 for |n| >= 1024, else 8): product of TG[i][digit_i(m)],
 //         TG[i][d] = g^(d * 2^(w i)) mod Nt, built once per key by this engine (k_gtable_*);
