@@ -29,6 +29,7 @@ struct B28Dev {            // per-key device-side descriptor (same for every con
     const int4* tg;        // comb table: [window][2^comb_bits][ENTRY4]
     int n_windows;
     int comb_bits;         // window width of the fixed-base comb for g^m
+    const int4* n_entry;   // g == n + 1 (the standard Paillier generator): strict digits of n, g^m = 1 + m n (mod n^2); else null
     int words_in, words_out;
     int sh;                // Nt = n2 << sh
     unsigned nt_top;       // floor(Nt / 2^(28(L-2)))
@@ -297,10 +298,18 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K
         if (sft + cb > 64 && w + 1 < K.words_in) v |= mw[w + 1] << (64 - sft);
         return (int)(v & ((1u << cb) - 1));
     };
-    gather_entry<C>(S.V, K.tg + (size_t)comb_digit(0) * C::ENTRY4, role, lane);
-    for (int i = 1; i < K.n_windows; i++) {
-        gather_entry<C>(S.B, K.tg + (((size_t)i << cb) + comb_digit(i)) * C::ENTRY4, role, lane);
-        mulmod<C, false, MMA>(S, S.B, role, lane);
+    if (K.n_entry) {
+        // g = n + 1: (1 + n)^m = 1 + m n (mod n^2) — one multiplication by the per-key constant n instead of the comb
+        load_value<C>(S.V, mw, K.words_in, role, lane);
+        mulmod_const<C, MMA>(S, K.n_entry, role, lane);
+        if (role == 0) ((int*)blk_ptr<C>(S.V, 0, lane))[0] += 1;
+        __syncthreads();
+    } else {
+        gather_entry<C>(S.V, K.tg + (size_t)comb_digit(0) * C::ENTRY4, role, lane);
+        for (int i = 1; i < K.n_windows; i++) {
+            gather_entry<C>(S.B, K.tg + (((size_t)i << cb) + comb_digit(i)) * C::ENTRY4, role, lane);
+            mulmod<C, false, MMA>(S, S.B, role, lane);
+        }
     }
     // ---- c = gm * rn, canonical
     copy_from_global<C>(S.B, tab + (size_t)(TABN + 1) * C::VAL4, role, lane);
@@ -572,7 +581,7 @@ struct Block28Key {
     int G = 0, BL = 0;
     std::string name;
     B28Dev dev{};
-    int4* d_consts = nullptr; int2* d_ops = nullptr; int4* d_tg = nullptr; u64* d_gwords = nullptr;
+    int4* d_consts = nullptr; int2* d_ops = nullptr; int4* d_tg = nullptr; u64* d_gwords = nullptr; int4* d_nentry = nullptr;
     int4* d_scratch = nullptr; size_t scratch_ctas = 0;
     u64* d_partials = nullptr; size_t partials_cap = 0;
     int sms = 148;
@@ -665,7 +674,8 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     int comb_bits = n_bits >= 1024 ? 12 : 8;
     if (const char* e = getenv("PB200_COMB_BITS")) { int v = atoi(e); if (v >= 4 && v <= 16) comb_bits = v; }
     const int n_windows = (int)((n_bits + comb_bits - 1) / comb_bits);
-    key->n_sqr = 1; key->n_mul = (TABN - 1) + (uint64_t)(n_windows - 1) + 1;   // r^2; table; comb; gm*rn
+    const bool g_std = g == BigInt::add(n, BigInt(1)) && !getenv("PB200_NO_GSTD");
+    key->n_sqr = 1; key->n_mul = (TABN - 1) + (g_std ? 1 : (uint64_t)(n_windows - 1)) + 1;   // r^2; table; comb (or m*n); gm*rn
     for (auto& o : ops) { key->n_sqr += (uint64_t)o.x; if (o.y >= 0) key->n_mul += 1; }
     CUK(cudaMalloc(&key->d_ops, (ops.size() + 1) * sizeof(int2)));
     if (!ops.empty()) CUK(cudaMemcpyAsync(key->d_ops, ops.data(), ops.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
@@ -674,8 +684,16 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     g.to_u64_le(gw.data(), win);
     CUK(cudaMalloc(&key->d_gwords, win * sizeof(u64)));
     CUK(cudaMemcpyAsync(key->d_gwords, gw.data(), win * sizeof(u64), cudaMemcpyHostToDevice, st));
-    CUK(cudaMalloc(&key->d_tg, ((size_t)n_windows << comb_bits) * C::ENTRY4 * sizeof(int4)));
+    if (!g_std) CUK(cudaMalloc(&key->d_tg, ((size_t)n_windows << comb_bits) * C::ENTRY4 * sizeof(int4)));
+    if (g_std) {
+        std::vector<int> e_n;
+        to_entry<C>(n, e_n);
+        CUK(cudaMalloc(&key->d_nentry, e_n.size() * sizeof(int)));
+        CUK(cudaMemcpyAsync(key->d_nentry, e_n.data(), e_n.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CUK(cudaStreamSynchronize(st));
+    }
     B28Dev& K = key->dev;
+    K.n_entry = key->d_nentry;
     K.consts = key->d_consts; K.ops = key->d_ops; K.n_ops = (int)ops.size(); K.first_idx = first_idx;
     K.tg = key->d_tg; K.n_windows = n_windows; K.comb_bits = comb_bits; K.words_in = (int)win; K.words_out = (int)((2 * n_bits + 63) / 64);
     K.sh = sh;
@@ -689,11 +707,13 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     CUK((cudaFuncSetAttribute(k_tally<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
     CUK((cudaFuncSetAttribute(k_tally<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
     int4* d_bases = nullptr;
-    CUK(cudaMalloc(&d_bases, (size_t)n_windows * C::ENTRY4 * sizeof(int4)));
-    k_gtable_bases<C><<<1, C::THREADS, C::SMEM_BYTES, st>>>(K, key->d_gwords, d_bases); count_launch();
-    k_gtable_fill<C><<<(n_windows + 31) / 32, C::THREADS, C::SMEM_BYTES, st>>>(K, d_bases, key->d_tg); count_launch();
+    if (!g_std) {      // the comb table is only needed for a general g
+        CUK(cudaMalloc(&d_bases, (size_t)n_windows * C::ENTRY4 * sizeof(int4)));
+        k_gtable_bases<C><<<1, C::THREADS, C::SMEM_BYTES, st>>>(K, key->d_gwords, d_bases); count_launch();
+        k_gtable_fill<C><<<(n_windows + 31) / 32, C::THREADS, C::SMEM_BYTES, st>>>(K, d_bases, key->d_tg); count_launch();
+    }
     cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(d_bases);
+    if (d_bases) cudaFree(d_bases);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { *cuda_err = e; block28_destroy(key); return nullptr; }
     return key;
@@ -843,6 +863,7 @@ void block28_destroy(Block28Key* key) {
     if (key->d_consts) cudaFree(key->d_consts);
     if (key->d_ops) cudaFree(key->d_ops);
     if (key->d_tg) cudaFree(key->d_tg);
+    if (key->d_nentry) cudaFree(key->d_nentry);
     if (key->d_gwords) cudaFree(key->d_gwords);
     if (key->d_scratch) cudaFree(key->d_scratch);
     if (key->d_partials) cudaFree(key->d_partials);

@@ -392,3 +392,29 @@ def test_golden_cell_streams_on_gpu(built_lib):
         with PaillierKey(n, n + 1, gq["n_bits"], 64) as key:
             cells = key.mulmod_cells([(h(gq["a"]), h(gq["b"]), h(gq["q"]), h(gq["rem"]))], gq["lookup_bits"])[0]
         assert len(cells) == gq["n_cells"] and cell_hash(cells) == gq["sha256"]
+
+
+@pytest.mark.parametrize("n_bits", [1024, 2048])
+def test_standard_generator_fast_path(built_lib, n_bits):
+    """g = n + 1: g^m = 1 + m n (mod n^2) is one multiplication by a per-key constant; same ciphertexts as the general comb path
+    (PB200_NO_GSTD=1 keeps the comb for g = n + 1) and as the oracle, edge plaintexts included."""
+    import os
+    kd = workload.load_key(n_bits)
+    n = kd["n"]
+    m_w, r_w = workload.units(n_bits, 40, seed_offset=5)
+    ms, rs = words_to_ints(m_w), words_to_ints(r_w)
+    ms[:4] = [0, 1, n - 1, (1 << n_bits) - 1]
+    with PaillierKey(n, n + 1, n_bits, 64) as key:
+        fast = key.paillier_enc_native(ms, rs)
+        n_sqr, n_mul = key.chain_counts()
+    os.environ["PB200_NO_GSTD"] = "1"
+    try:
+        with PaillierKey(n, n + 1, n_bits, 64) as key:
+            comb = key.paillier_enc_native(ms, rs)
+            assert key.chain_counts()[1] > n_mul
+    finally:
+        del os.environ["PB200_NO_GSTD"]
+    assert fast == comb
+    assert fast[:6] == [paillier_enc_native(n, n + 1, m, r) for m, r in zip(ms[:6], rs[:6])]
+    n2 = n * n
+    assert all(pow(n + 1, m, n2) == (1 + m * n) % n2 for m in ms[:6])
