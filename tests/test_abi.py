@@ -81,3 +81,24 @@ def test_new_entry_points_reject_null_arguments(built_lib):
     assert lib.pb200_key_n2_cells(null, 15, 0, None) == _lib.PB200_ERR_INVALID_ARG
     assert lib.pb200_cells_layout(null, 15, None) == _lib.PB200_ERR_INVALID_ARG
     assert lib.pb200_key_witness_engine(null) == b""
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/paillier-b200-sys cannot be compiled here (no Rust toolchain); at least its extern block must list exactly the symbols of
+    the header, with the same number of parameters."""
+    header = open(os.path.join(ROOT, "include", "paillier_b200.h")).read()
+    rust = open(os.path.join(ROOT, "rust", "paillier-b200-sys", "src", "lib.rs")).read()
+    decl_h = {}
+    for mm in re.finditer(r"\b(pb200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, re.S):
+        name, args = mm.group(1), mm.group(2).strip()
+        if name == "pb200_witness_sink_fn":
+            continue
+        decl_h[name] = 0 if args in ("", "void") else args.count(",") + 1
+    ext = rust[rust.index('extern "C" {'):]
+    ext = ext[:ext.index("\n}\n")]
+    decl_r = {}
+    for mm in re.finditer(r"pub fn (pb200_[a-z0-9_]+)\s*\(([^;]*?)\)\s*(->[^;]*)?;", ext, re.S):
+        args = mm.group(2).strip()
+        decl_r[mm.group(1)] = 0 if not args else args.count(":")
+    assert set(decl_h) == set(decl_r), set(decl_h) ^ set(decl_r)
+    assert decl_h == decl_r, {k: (decl_h[k], decl_r[k]) for k in decl_h if decl_h[k] != decl_r[k]}
