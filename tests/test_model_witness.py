@@ -37,3 +37,51 @@ def test_witness_step_exact(G, BL, n_bits, n_keys, n_rand):
                 assert (q, rem) == divmod(a * b, N)
                 assert nxt == mb.to_digits(rem << s, P.L)
     assert stats["passes"] <= 2
+
+
+def test_witness_chain_model_matches_oracle_stream():
+    """The whole k_witness chain on the limb model (128-bit key, Cfg<4,19>): g-chain multiplications over the set bits of m against
+    the per-key table g^(2^i) 2^s, r-chain with the multiplication of an iteration computed BEFORE its squaring but emitted after
+    it, final gm*rn — the emitted (q, rem) stream must be the oracle's, record for record."""
+    from oracle.paillier_oracle import encrypt_steps
+    rng = random.Random(2026)
+    n_bits = 128
+    P = mb.Params(4, 19)
+    wo = (2 * n_bits + 63) // 64
+    n = rng.getrandbits(n_bits) | (1 << (n_bits - 1)) | 1
+    g = rng.getrandbits(n_bits)
+    N = n * n
+    keyw, inv = mb.witness_key(P, N)
+    s = keyw[0] >> 1
+    mb._cache.clear()
+    D = lambda v: mb.to_digits(v << s, P.L)
+    step = lambda A, B, sqr=False: mb.witness_step(P, keyw, inv, A, B, wo, sqr)
+    # per-key table (k_gchain_w): gtab[i] = g^(2^i) 2^s, with the g-chain squaring records
+    gtab, cur = [], D(g)
+    for _ in range(n_bits):
+        gtab.append(cur)
+        _, _, cur = step(cur, cur, True)
+    for m, r in ((rng.getrandbits(n_bits), rng.getrandbits(n_bits)), (0, 1), ((1 << n_bits) - 1, n + 1)):
+        stream = []
+        acc = D(1)
+        for i in range(m.bit_length()):
+            if (m >> i) & 1:
+                q, rem, acc = step(acc, gtab[i])
+                stream.append((q, rem))
+        gm = acc
+        cur, acc = D(r), D(1)
+        for i in range(n.bit_length()):
+            pending = None
+            if (n >> i) & 1:
+                q, rem, acc = step(cur, acc)          # mul first: cur stays in V
+                pending = (q, rem)
+            q, rem, cur = step(cur, cur, True)
+            stream.append((q, rem))
+            if pending:
+                stream.append(pending)
+        q, rem, _ = step(gm, acc)
+        stream.append((q, rem))
+        c, steps = encrypt_steps(n, g, m, r)
+        gs = m.bit_length() + bin(m).count("1")
+        want = [(x.q, x.rem) for x in steps[:gs] if x.kind == "mul"] + [(x.q, x.rem) for x in steps[gs:]]
+        assert rem == c and stream == want
