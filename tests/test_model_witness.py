@@ -85,3 +85,9 @@ def test_witness_chain_model_matches_oracle_stream():
         gs = m.bit_length() + bin(m).count("1")
         want = [(x.q, x.rem) for x in steps[:gs] if x.kind == "mul"] + [(x.q, x.rem) for x in steps[gs:]]
         assert rem == c and stream == want
+
+
+def test_montgomery_cios32_model():
+    """the 32-bit-word CIOS of the K4 Montgomery output (cells.cu: fr_to_mont32), word for word, against (x << 256) % p"""
+    import model_cios32
+    assert model_cios32.self_test(3000) > 3000
