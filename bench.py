@@ -590,6 +590,16 @@ def main():
             v, dt = cpu_baseline(threads, sample, kd)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"first {sample} units of the same batch, {dt:.1f} s, OpenSSL BIGNUM port of src/paillier.rs:87-92"}
+            try:        # second line of SURVEY.md 8d: the Python-int restatement on one core, two units
+                from oracle.paillier_oracle import paillier_enc_native as _py_enc
+                from paillier_halo2_b200.api import words_to_ints as _w2i
+                _ms, _rs = _w2i(m_w[:2]), _w2i(r_w[:2])
+                _t0 = time.perf_counter()
+                for _m, _r in zip(_ms, _rs):
+                    _py_enc(kd["n"], g, _m, _r)
+                line["cpu_baseline"]["python_int_enc_per_s_one_core"] = 2 / (time.perf_counter() - _t0)
+            except Exception as _e:     # a reporting extra must never cost the bench line
+                line["cpu_baseline"]["python_int_enc_per_s_one_core"] = None
         emit(line)
     key.close()
     if world > 1:
