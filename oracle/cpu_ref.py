@@ -34,6 +34,8 @@ def load() -> C.CDLL:
         lib.cpu_paillier_add_batch.argtypes = [u64p, C.c_int, u64p, u64p, C.c_int, C.c_size_t, u64p, C.c_int]
         lib.cpu_paillier_tally.restype = C.c_int
         lib.cpu_paillier_tally.argtypes = [u64p, C.c_int, u64p, C.c_size_t, u64p, C.c_int]
+        lib.cpu_witness_digest_batch.restype = C.c_int
+        lib.cpu_witness_digest_batch.argtypes = [u64p, u64p, C.c_int, u64p, u64p, C.c_size_t, u64p, u64p, C.c_int, C.c_int]
         _lib = lib
     return _lib
 
@@ -77,3 +79,27 @@ def tally(n: int, words_in: int, c_w: np.ndarray, threads: int = 1) -> np.ndarra
     out = np.empty(2 * words_in, dtype="<u8")
     lib.cpu_paillier_tally(_p(_w(n, words_in)), words_in, _p(c_w), c_w.shape[0], _p(out), threads)
     return out
+
+
+
+def witness_digest_batch(n: int, g: int, words_in: int, m_w: np.ndarray, r_w: np.ndarray, threads: int = 1, backend: str = "auto"):
+    """(ciphertexts, digests, backend used) of the reference's mul_mod chain per unit (src/paillier.rs:51,55,57; SURVEY.md
+    A.4-A.5): full product + div_rem per step, digest as defined in include/paillier_b200.h.  backend: "openssl" (BN_div),
+    "gmp" (mpz_tdiv_qr, 2.5x faster) or "auto" (gmp when libgmp.so.10 loads).  Raises if some quotient overflows words_out."""
+    lib = load()
+    m_w = np.ascontiguousarray(m_w, dtype="<u8")
+    r_w = np.ascontiguousarray(r_w, dtype="<u8")
+    count = m_w.shape[0]
+    c = np.empty((count, 2 * words_in), dtype="<u8")
+    dig = np.empty(count, dtype="<u8")
+    args = (_p(_w(n, words_in)), _p(_w(g, words_in)), words_in, _p(m_w), _p(r_w), count, _p(c), _p(dig), threads)
+    rc, used = -1, "openssl"
+    if backend in ("auto", "gmp"):
+        rc, used = lib.cpu_witness_digest_batch(*args, 1), "gmp"
+        if rc == -1 and backend == "gmp":
+            raise RuntimeError("libgmp.so.10 not loadable")
+    if rc == -1:
+        rc, used = lib.cpu_witness_digest_batch(*args, 0), "openssl"
+    if rc != 0:
+        raise OverflowError("a mul_mod quotient does not fit 2*enc_bits (range check on q fails)")
+    return c, dig, used

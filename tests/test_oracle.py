@@ -163,3 +163,35 @@ def test_golden_cell_streams():
         out = BigUintChip(64, gq["lookup_bits"]).mul_mod(ctx, Assigned(decompose(a, L, 64), a, 64), Assigned(decompose(b, L, 64), b, 64),
                                                          Assigned(decompose(n * n, L, 64), n * n, 64))
         assert out.value == int(gq["rem"], 16) and len(ctx.cells) == gq["n_cells"] and _cell_hash(ctx.cells) == gq["sha256"]
+
+
+@pytest.mark.parametrize("backend", ["openssl", "gmp"])
+def test_cpu_witness_digest_batch_matches_python_chain(backend):
+    """oracle/paillier_cpu.cpp cpu_witness_digest_batch (the full-batch checker of bench.py and the GPU tests) against the
+    Python restatement of the chain, both backends: the reference's default sizes with even / short n
+    (the reference draws n = gen_biguint(bits)), edge units, and a production size."""
+    rng = random.Random(20261018)
+    cases = []
+    for n_bits in (128, 264):
+        wi = (n_bits + 63) // 64
+        for _ in range(3):
+            n = rng.getrandbits(n_bits) | (1 << (n_bits - 1))          # full width so that q fits 2*enc_bits
+            g = rng.getrandbits(n_bits)
+            ms = [0, 1, (1 << n_bits) - 1] + [rng.getrandbits(n_bits) for _ in range(5)]
+            rs = [1, 0, (1 << n_bits) - 1] + [rng.getrandbits(n_bits) for _ in range(5)]
+            cases.append((n_bits, wi, n, g, ms, rs))
+    key = workload.load_key(1024)
+    m_w, r_w = workload.units(1024, 3)
+    cases.append((1024, 16, key["n"], key["g_rand"], words_to_ints(m_w), words_to_ints(r_w)))
+    for n_bits, wi, n, g, ms, rs in cases:
+        try:
+            c, dig, used = cpu_ref.witness_digest_batch(n, g, wi, ints_to_words(ms, wi), ints_to_words(rs, wi), threads=2, backend=backend)
+        except RuntimeError:
+            pytest.skip("libgmp.so.10 not loadable")
+        assert used == backend
+        for i, (m, r) in enumerate(zip(ms, rs)):
+            cc, steps = encrypt_steps(n, g, m, r)
+            ng = m.bit_length() + bin(m).count("1")
+            mine = [(s.q, s.rem) for s in steps[:ng] if s.kind == "mul"] + [(s.q, s.rem) for s in steps[ng:]]
+            assert words_to_ints(c[i:i + 1])[0] == cc
+            assert int(dig[i]) == witness_digest(mine, 2 * wi)
