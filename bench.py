@@ -216,158 +216,361 @@ def cells_leg(key, kd, n_bits, groups=1 << 16, lookup_bits=15, reps=4):
     return out
 
 
-def run_tally(args):
-    """BASELINE.json configs[2]: product of 2^20 ciphertexts mod n^2, sharded over the GPUs with one all-gather of
-    the per-GPU partials (NCCL) and a final combine.  Strong scaling (total work fixed)."""
+class Ctx:
+    """Per-process bench context: rank / world, torch + NCCL, the loaded library."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        from paillier_halo2_b200 import _lib
+
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the Paillier hot path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.lib = _lib.load()
+        self.dev = torch.device("cuda", self.local_rank)
+        self.flush_buf = None
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def flush_l2(self):
+        if self.flush_buf is None:
+            self.flush_buf = self.torch.empty(256 << 20, dtype=self.torch.uint8, device=self.dev)      # > 126 MB L2
+        self.flush_buf.fill_(1)
+        self.torch.cuda.synchronize()
+
+    def stream_of(self, key):
+        return self.torch.cuda.ExternalStream(key.stream, device=self.dev)
+
+    def launches(self):
+        return int(self.lib.pb200_kernel_launches())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def unit_stream(kd, g, m_row, r_row):
+    """(q, rem) records of one unit's stream from the Python oracle (checker)."""
+    from oracle.paillier_oracle import encrypt_steps
+    from paillier_halo2_b200.api import words_to_ints
+    mi, ri = words_to_ints(m_row)[0], words_to_ints(r_row)[0]
+    c, steps = encrypt_steps(kd["n"], g, mi, ri)
+    gs = mi.bit_length() + bin(mi).count("1")
+    return c, [(x.q, x.rem) for x in steps[:gs] if x.kind == "mul"] + [(x.q, x.rem) for x in steps[gs:]]
+
+
+def witness_chain_macs(kd, m_w, n_bits):
     import numpy as np
-    import torch
-    import torch.distributed as dist
+    from paillier_halo2_b200.api import words_to_ints
+    w_mul, w_sqr = mac_counts(n_bits)
+    pop_n = bin(kd["n"]).count("1")
+    pop_m = float(np.mean([bin(v).count("1") for v in words_to_ints(m_w[:256])]))
+    n_sqr, n_mul = kd["n"].bit_length(), pop_n + pop_m + 1
+    return n_sqr, n_mul, n_sqr * w_sqr + n_mul * w_mul
 
-    from paillier_halo2_b200 import PaillierKey, _lib, workload
-    from paillier_halo2_b200.shard import shard_range, tally_sharded_gpu
 
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = _lib.load()
-    kd = workload.load_key(N_BITS)
-    total = 1 << 20
-    key = PaillierKey(kd["n"], kd["g_std"], N_BITS, 64, device=local_rank)
-    lo, hi = shard_range(total, rank, world)
-    c_all = workload.ciphertexts(N_BITS, total, kd["n"]) if total <= (1 << 20) else None
-    d_c = torch.from_numpy(c_all[lo:hi].view(np.int64)).cuda()
-    stream = torch.cuda.ExternalStream(key.stream, device=torch.device("cuda", local_rank))
-    partial = torch.empty(key.words_out, dtype=torch.int64, device="cuda")
-    for _ in range(args.warmup):
-        out = tally_sharded_gpu(key, d_c, hi - lo, world)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches0 = lib.pb200_kernel_launches()
-    kern_ms = 0.0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+class ParityJob:
+    """Full-batch witness parity on the host cores, in the background: the CPU chain (oracle/paillier_cpu.cpp: full product +
+    div_rem per mul_mod) over the units in index order, in slices, until every unit is done or the time budget is spent.
+    A checker: it never feeds the product path."""
+
+    def __init__(self, kd, g, n_bits, m_w, r_w, budget_s, threads):
+        self.args = (kd["n"], g, n_bits // 64, m_w, r_w)
+        self.budget, self.threads = budget_s, threads
+        self.dig, self.cs, self.done, self.backend, self.secs = [], [], 0, None, 0.0
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def start(self):
+        self.t.start()
+        return self
+
+    def _run(self):
+        import numpy as np
+        from oracle import cpu_ref
+        n, g, wi, m_w, r_w = self.args
+        t0 = time.perf_counter()
+        step = max(64, 48 * self.threads)
+        rate = None
+        while self.done < len(m_w):
+            left = self.budget - (time.perf_counter() - t0)
+            if left <= 0 or (rate and step / rate > left):
+                break
+            e = min(len(m_w), self.done + step)
+            t1 = time.perf_counter()
+            c, d, self.backend = cpu_ref.witness_digest_batch(n, g, wi, m_w[self.done:e], r_w[self.done:e], threads=self.threads)
+            rate = (e - self.done) / (time.perf_counter() - t1)
+            self.cs.append(c); self.dig.append(d); self.done = e
+        self.secs = time.perf_counter() - t0
+        self.dig = np.concatenate(self.dig) if self.dig else np.empty(0, dtype="<u8")
+        self.cs = np.concatenate(self.cs) if self.cs else np.empty((0, 2 * wi), dtype="<u8")
+
+    def join(self):
+        self.t.join()
+        return self
+
+
+def leg_witness(cx, key, kd, g, n_bits, m_w, r_w, d_m, d_r, reps=2):
+    """Witness mode, device-resident: the reference's own LSB-first chain with the exact (q, rem) of every mul_mod, digested on the
+    device (pb200_encrypt_witness_digest_dev).  Returns (result dict, device digests, device ciphertexts)."""
+    torch = cx.torch
+    units = m_w.shape[0]
+    d_dig = torch.empty(units, dtype=torch.int64, device=cx.dev)
+    d_cw = torch.empty((units, key.words_out), dtype=torch.int64, device=cx.dev)
+    stream = cx.stream_of(key)
+    key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), units, d_cw.data_ptr(), d_dig.data_ptr())     # warm-up at full size
+    cx.barrier()
+    wl0 = cx.launches()
+    sampler = ClockSampler(cx.local_rank)
+    sampler.start()
+    evs = []
+    for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream); key.tally_dev(d_c.data_ptr(), hi - lo, partial.data_ptr()); e1.record(stream)
-        key.sync(); kern_ms += e0.elapsed_time(e1)
-        out = tally_sharded_gpu(key, d_c, hi - lo, world)
-    torch.cuda.synchronize()
+        e0.record(stream)
+        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), units, d_cw.data_ptr(), d_dig.data_ptr())
+        e1.record(stream)
+        evs.append((e0, e1))
+    cx.barrier()
+    clocks = sampler.stop()
+    (w_ms,) = cx.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / len(evs))
+    n_sqr, n_mul, a_wit = witness_chain_macs(kd, m_w, n_bits)
+    peak_w, _ = imad_peak()
+    out = {"value": cx.world * units / (w_ms * 1e-3), "unit": "units/s", "engine": key.witness_engine, "ms_per_launch": w_ms,
+           "units_per_gpu": units, "records_per_unit": n_sqr + n_mul, "mul_mod_per_s": cx.world * units * (n_sqr + n_mul) / (w_ms * 1e-3),
+           "witness_stream_GBps": cx.world * units * (n_sqr + n_mul) * 2 * key.words_out * 8 / (w_ms * 1e-3) / 1e9,
+           "chain": {"mod_sqr": n_sqr, "mod_mul": n_mul, "mac_per_unit": a_wit},
+           "frac_of_imad_peak": units * a_wit / (w_ms * 1e-3) / peak_w,
+           "gpu_launches": int(cx.launches() - wl0), "clocks": clocks, "ms_each": [a.elapsed_time(b) for a, b in evs]}
+    return out, d_dig, d_cw
+
+
+def pcie_d2h_gbs(cx, nbytes=1 << 30):
+    """Measured device -> pinned host copy bandwidth of this box (the roof of the witness delivery), best of 3."""
+    torch = cx.torch
+    src = torch.empty(nbytes, dtype=torch.uint8, device=cx.dev)
+    dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); dst.copy_(src, non_blocking=True); e1.record()
+        torch.cuda.synchronize()
+        best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
+def leg_witness_e2e(cx, key, kd, g, n_bits, m_w, r_w, units, dig_ref=None):
+    """The witness DELIVERED: pb200_encrypt_witness_batch with host inputs, every (q, rem) record landing in pinned host memory
+    and handed to a sink callback (here: counts bytes, re-hashes the first unit of every 4th piece and compares it with the
+    device digest).  Wall clock around the blocking C-ABI call; the roof is the measured device -> host copy bandwidth."""
+    import ctypes as C
+    import numpy as np
+    from paillier_halo2_b200 import _lib
+    from paillier_halo2_b200.api import DIGEST_C, DIGEST_INIT, DIGEST_PRIME, MASK64
+    wo = key.words_out
+    units = min(units, m_w.shape[0])
+    cpow = np.empty(2 * wo, dtype=np.uint64)
+    c = DIGEST_C
+    for j in range(2 * wo):
+        cpow[j] = c; c = (c * DIGEST_C) & MASK64
+    state = {"bytes": 0, "units": 0, "pieces": 0, "checked": 0, "ok": True}
+
+    def sink(_user, chp):
+        ch = chp.contents
+        nu = ch.n_units
+        offs = np.ctypeslib.as_array(ch.offsets, shape=(nu + 1,))
+        total = int(offs[nu])
+        state["bytes"] += total * 2 * wo * 8; state["units"] += nu; state["pieces"] += 1
+        if dig_ref is not None and state["pieces"] % 4 == 1:
+            recs = np.ctypeslib.as_array(ch.records, shape=(total, 2 * wo))[: int(offs[1])]
+            with np.errstate(over="ignore"):
+                hs = (recs * cpow).sum(axis=1, dtype=np.uint64)
+            d = DIGEST_INIT
+            for hv in hs.tolist():
+                d = ((d ^ hv) * DIGEST_PRIME) & MASK64
+            state["checked"] += 1
+            state["ok"] = state["ok"] and d == int(dig_ref[ch.first_unit])
+        return 0
+
+    cb = _lib.SINK_FN(sink)
+    m_h, r_h = np.ascontiguousarray(m_w[:units]), np.ascontiguousarray(r_w[:units])
+    c_h = np.empty((units, wo), dtype="<u8")
+    p = lambda a: a.ctypes.data_as(_lib.u64p)
+    # warm-up: pinned ring, device record buffers and per-key tables are allocated on first use
+    _lib.check(cx.lib.pb200_encrypt_witness_batch(key.handle, p(m_h), p(r_h), units, p(c_h), 0, cb, None), "pb200_encrypt_witness_batch")
+    d2h = pcie_d2h_gbs(cx)
+    for k_ in state:
+        state[k_] = True if k_ == "ok" else 0
+    cx.barrier()
+    t0 = time.perf_counter()
+    _lib.check(cx.lib.pb200_encrypt_witness_batch(key.handle, p(m_h), p(r_h), units, p(c_h), 0, cb, None), "pb200_encrypt_witness_batch")
     dt = time.perf_counter() - t0
-    launches = lib.pb200_kernel_launches() - launches0
-    t = torch.tensor([dt, kern_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt, kern_ms = float(t[0]), float(t[1])
+    dt, d2h_min = cx.max_over_ranks(dt, -d2h)
+    gbs = state["bytes"] / dt / 1e9
+    return {"value": cx.world * units / dt, "unit": "units/s", "units_per_gpu": units, "seconds": dt, "pieces": state["pieces"],
+            "d2h_bytes_per_step": int(state["bytes"] + c_h.nbytes), "h2d_bytes_per_step": int(m_h.nbytes + r_h.nbytes),
+            "roofline": {"bound": "pcie_d2h", "achieved": gbs, "peak": -d2h_min, "unit": "GB/s", "frac": gbs / -d2h_min,
+                         "peak_source": "device -> pinned host copy of 1 GiB measured in this run (best of 4)"},
+            "sink_rehashed_units": state["checked"], "parity": bool(state["ok"] and state["units"] == units)}
+
+
+TALLY_TOTAL = 1 << 20
+TALLY_PARTS = 8            # the 2^20 ciphertexts are 8 fixed Philox streams, so the SET is the same for every GPU count
+
+
+def leg_tally(cx, kd, n_bits, steps, warmup):
+    """BASELINE.json configs[2]: product of 2^20 ciphertexts mod n^2 sharded over the GPUs.  Strong scaling (total fixed).  One
+    launch per GPU per tally (pb200_tally_peer_dev): shard fold, partials exchanged through peer-mapped memory inside the kernel,
+    combine — or, when the peers cannot be mapped, fold + NCCL all-gather + combine."""
+    import numpy as np
+    from paillier_halo2_b200 import PaillierKey
+    from paillier_halo2_b200.shard import connect_tally_peers, tally_sharded_gpu
+    torch = cx.torch
+    world, rank = cx.world, cx.rank
+    key = PaillierKey(kd["n"], kd["g_std"], n_bits, 64, device=cx.local_rank)
+    per_part = TALLY_TOTAL // TALLY_PARTS
+    from paillier_halo2_b200 import workload
+    mine = range(rank * TALLY_PARTS // world, (rank + 1) * TALLY_PARTS // world)
+    parts = {s_: workload.ciphertexts(n_bits, per_part, kd["n"], seed_offset=100 + s_) for s_ in (range(TALLY_PARTS) if rank == 0 else mine)}
+    shard = np.concatenate([parts[s_] for s_ in mine])
+    count = shard.shape[0]
+    d_c = torch.from_numpy(shard.view(np.int64)).to(cx.dev)
+    out = torch.empty(key.words_out, dtype=torch.int64, device=cx.dev)
+    exchange = connect_tally_peers(key, rank, world) if world > 1 else "peer-memory"
+    if world == 1:
+        key.tally_peer_connect(0, 1, [key.tally_peer_export()])
+    stream = cx.stream_of(key)
+    for _ in range(max(warmup, 1)):
+        tally_sharded_gpu(key, d_c, count, world, exchange=exchange, out=out)
+    cx.barrier()
+    l0 = cx.launches()
+    ms = []
+    for _ in range(steps):
+        cx.flush_l2()
+        cx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        tally_sharded_gpu(key, d_c, count, world, exchange=exchange, out=out)
+        e1.record(stream)
+        key.sync()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms.append(cx.max_over_ranks(e0.elapsed_time(e1) if exchange == "peer-memory" else wall)[0])
+    launches = cx.launches() - l0
+    flags = key.take_flags()
+    t = sum(ms) / len(ms) * 1e-3
+    res = {"value": TALLY_TOTAL / t, "unit": "ciphertexts/s", "ciphertexts": TALLY_TOTAL, "n_gpus": world, "scaling": "strong",
+           "ms_per_tally": t * 1e3, "ms_each": ms, "exchange": exchange, "engine": key.engine, "gpu_launches_per_tally": launches / steps,
+           "timing": "CUDA events on the launching stream, max over ranks" if exchange == "peer-memory" else "wall clock around the call, max over ranks",
+           "l2": "flushed between tallies (256 MiB write)", "flags": flags}
     if rank == 0:
         from oracle import cpu_ref
-        want = cpu_ref.tally(kd["n"], N_BITS // 64, c_all, threads=cpu_ref.hardware_threads())
-        ok = bool((out.cpu().numpy().view(np.uint64) == want).all())
-        w_mul, _ = mac_counts(N_BITS)
+        c_all = np.concatenate([parts[s_] for s_ in range(TALLY_PARTS)])
+        want = cpu_ref.tally(kd["n"], n_bits // 64, c_all, threads=cpu_ref.hardware_threads())
+        res["parity_vs_cpu_fold"] = bool((out.cpu().numpy().view(np.uint64) == want).all())
+        w_mul, _ = mac_counts(n_bits)
         peak, src = imad_peak()
-        shard = hi - lo
-        ksec = kern_ms * 1e-3 / args.steps
-        line = {"metric": f"paillier_tally_ciphertexts_per_s_n{N_BITS}", "value": total * 2 * args.steps / dt, "unit": "ciphertexts/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / (2 * args.steps),
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64 accumulators over signed 28-bit digits",
-                "data": "synthetic", "config": {"workload": f"product of 2^20 ciphertexts mod n^2, |n|={N_BITS}, sharded over {world} GPU(s), "
-                                                            "NCCL all-gather of partials + combine (BASELINE.json configs[2])", "engine": key.engine},
-                "gpu_launches": int(launches), "parity_vs_cpu_fold": ok,
-                "roofline": {"bound": "imad", "achieved": shard * w_mul / ksec / 1e12, "peak": peak / 1e12, "unit": "TMAC/s",
-                             "frac": shard * w_mul / ksec / peak, "peak_source": src,
-                             "hbm_gbs_achieved": shard * key.words_out * 8 / ksec / 1e9,
-                             "note": "per-GPU shard fold kernel (k_tally x2 launches); one modmul per 512 B read: compute-bound, HBM GB/s reported because north_star asks for it"}}
-        emit(line)
+        res["roofline"] = {"bound": "imad", "achieved": TALLY_TOTAL * w_mul / t / 1e12, "peak": world * peak / 1e12, "unit": "TMAC/s",
+                           "frac": TALLY_TOTAL * w_mul / t / (world * peak), "peak_source": src,
+                           "hbm_gbs_achieved": TALLY_TOTAL * key.words_out * 8 / t / 1e9,
+                           "note": "whole tally (fold + exchange + combine) against world x P_imad; one modmul per 512 B read (64 MAC/B): "
+                                   "compute-bound, HBM GB/s reported because north_star asks for it"}
     key.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return res
+
+
+def leg_witness_cfg3(cx, steps_units, parity_units=1024):
+    """BASELINE.json configs[3]: batched encrypt + full (q, rem) limb witness at |n| = 3072, 2^18 units over 8 GPUs = 32768 units
+    per GPU (weak scaling, no collective).  Device digest for every unit; parity: `parity_units` units spread evenly over the
+    batch re-derived by the CPU chain; plus the delivery (pb200_encrypt_witness_batch) of a bounded sample."""
+    import numpy as np
+    from paillier_halo2_b200 import PaillierKey, workload
+    torch = cx.torch
+    n_bits = 3072
+    kd = workload.load_key(n_bits)
+    g = kd["g_rand"]
+    units = steps_units
+    key = PaillierKey(kd["n"], g, n_bits, 64, device=cx.local_rank)
+    m_w, r_w = workload.units(n_bits, units, seed_offset=3000 + 1000 * cx.rank)
+    d_m = torch.from_numpy(m_w.view(np.int64)).to(cx.dev); d_r = torch.from_numpy(r_w.view(np.int64)).to(cx.dev)
+    res, d_dig, d_cw = leg_witness(cx, key, kd, g, n_bits, m_w, r_w, d_m, d_r, reps=2)
+    res["config"] = f"|n|=3072, {units} units per GPU ({cx.world * units} in total), (q, rem) of every mul_mod, digested on the device"
+    dig = d_dig.cpu().numpy().view(np.uint64)
+    res["e2e"] = leg_witness_e2e(cx, key, kd, g, n_bits, m_w, r_w, min(units, 6144), dig)
+    if cx.rank == 0:
+        from oracle import cpu_ref
+        idx = np.unique(np.linspace(0, units - 1, min(parity_units, units)).astype(np.int64))
+        t0 = time.perf_counter()
+        c, d, backend = cpu_ref.witness_digest_batch(kd["n"], g, n_bits // 64, m_w[idx], r_w[idx], threads=cpu_ref.hardware_threads())
+        res["parity"] = bool((d == dig[idx]).all() and (c == d_cw.cpu().numpy().view(np.uint64)[idx]).all())
+        res["parity_units"] = int(len(idx))
+        res["parity_note"] = f"{len(idx)} units spread evenly over rank 0's batch, CPU chain ({backend}), {time.perf_counter() - t0:.0f} s"
+    del d_dig, d_cw, d_m, d_r
+    key.close()
+    return res
+
+
+def run_tally(args):
+    cx = Ctx()
+    from paillier_halo2_b200 import workload
+    kd = workload.load_key(N_BITS)
+    res = leg_tally(cx, kd, N_BITS, args.steps, args.warmup)
+    if cx.rank == 0:
+        line = {"metric": f"paillier_tally_ciphertexts_per_s_n{N_BITS}", "value": res["value"], "unit": "ciphertexts/s", "n_gpus": cx.world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_tally"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "int64 accumulators over signed 28-bit digits", "data": "synthetic",
+                "config": {"workload": f"product of 2^20 ciphertexts mod n^2, |n|={N_BITS}, sharded over {cx.world} GPU(s) (BASELINE.json configs[2])"},
+                "gpu_launches": int(res["gpu_launches_per_tally"] * args.steps), "tally": res, "roofline": res.get("roofline")}
+        emit(line)
+    cx.close()
 
 
 def run_witness(args):
-    """BASELINE.json configs[3]: batched encrypt + the (q, rem) limb witness of every mul_mod PaillierChip::encrypt issues
-    (|n| = 3072 and 2^18 units over 8 GPUs in the config; --n-bits / --units select others).  Weak scaling: each rank runs
-    `units` units of its own slice; no collective on the data path.  Value = units/s, whole job."""
+    """`--workload witness`: the witness leg alone at --n-bits / --units (key-size sweep of the witness engine)."""
     import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    from paillier_halo2_b200 import PaillierKey, _lib, workload
-    from paillier_halo2_b200.api import witness_digest, words_to_ints
-
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = _lib.load()
+    from paillier_halo2_b200 import PaillierKey, workload
+    cx = Ctx()
+    torch = cx.torch
     kd = workload.load_key(N_BITS)
+    g = kd["g_rand"]
     units = args.units
-    key = PaillierKey(kd["n"], kd["g_rand"], N_BITS, 64, device=local_rank)
-    m_w, r_w = workload.units(N_BITS, units, seed_offset=1000 * rank)
-    d_m = torch.from_numpy(m_w.view(np.int64)).cuda(); d_r = torch.from_numpy(r_w.view(np.int64)).cuda()
-    d_c = torch.empty((units, key.words_out), dtype=torch.int64, device="cuda")
-    d_dig = torch.empty(units, dtype=torch.int64, device="cuda")
-    stream = torch.cuda.ExternalStream(key.stream, device=torch.device("cuda", local_rank))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), min(units, 9472), d_c.data_ptr(), d_dig.data_ptr())
-    for _ in range(max(args.warmup - 1, 0)):
-        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), min(units, 9472), d_c.data_ptr(), d_dig.data_ptr())
-    sampler = ClockSampler(local_rank)
-    launches0 = lib.pb200_kernel_launches()
-    barrier()
-    sampler.start()
-    evs = []
-    for _ in range(args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), units, d_c.data_ptr(), d_dig.data_ptr())
-        e1.record(stream)
-        evs.append((e0, e1))
-    barrier()
-    clocks = sampler.stop()
-    launches = lib.pb200_kernel_launches() - launches0
-    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    if rank == 0:
-        from oracle.paillier_oracle import encrypt_steps
-        w_mul, w_sqr = mac_counts(N_BITS)
-        pop_n = bin(kd["n"]).count("1")
-        pop_m = float(np.mean([bin(v).count("1") for v in words_to_ints(m_w[:256])]))
-        n_sqr, n_mul = kd["n"].bit_length(), pop_n + pop_m + 1
-        a_wit = n_sqr * w_sqr + n_mul * w_mul
-        dig = d_dig.cpu().numpy().view(np.uint64)
-        cs = d_c.cpu().numpy().view(np.uint64)
-        ok = True
-        for i in sorted({0, units - 1} | {(units * t) // 16 for t in range(16)}):       # 17 units spread over the batch
-            mi, ri = words_to_ints(m_w[i:i + 1])[0], words_to_ints(r_w[i:i + 1])[0]
-            c, steps = encrypt_steps(kd["n"], kd["g_rand"], mi, ri)
-            gs = mi.bit_length() + bin(mi).count("1")
-            mine = [(x.q, x.rem) for x in steps[:gs] if x.kind == "mul"] + [(x.q, x.rem) for x in steps[gs:]]
-            ok = ok and int(dig[i]) == witness_digest(mine, key.words_out) and words_to_ints(cs[i:i + 1])[0] == c
+    key = PaillierKey(kd["n"], g, N_BITS, 64, device=cx.local_rank)
+    m_w, r_w = workload.units(N_BITS, units, seed_offset=1000 * cx.rank)
+    d_m = torch.from_numpy(m_w.view(np.int64)).to(cx.dev); d_r = torch.from_numpy(r_w.view(np.int64)).to(cx.dev)
+    res, d_dig, d_cw = leg_witness(cx, key, kd, g, N_BITS, m_w, r_w, d_m, d_r, reps=max(args.steps, 1))
+    if cx.rank == 0:
+        from oracle import cpu_ref
+        idx = np.unique(np.linspace(0, units - 1, min(512, units)).astype(np.int64))
+        c, d, backend = cpu_ref.witness_digest_batch(kd["n"], g, N_BITS // 64, m_w[idx], r_w[idx], threads=cpu_ref.hardware_threads())
+        res["parity"] = bool((d == d_dig.cpu().numpy().view(np.uint64)[idx]).all() and (c == d_cw.cpu().numpy().view(np.uint64)[idx]).all())
+        res["parity_units"] = int(len(idx))
         peak, src = imad_peak()
-        ksec = dev_ms * 1e-3 / args.steps
-        line = {"metric": f"paillier_witness_units_per_s_n{N_BITS}", "value": world * units * args.steps / (dev_ms * 1e-3), "unit": "units/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "int64 columns over signed 28-bit digits + s8 IMMA, exact (q, rem) tail",
-                "data": "synthetic",
-                "config": {"workload": f"batched encrypt + (q, rem) limb witness of every mul_mod, |n|={N_BITS}, {units} units per GPU per step "
-                                       "(BASELINE.json configs[3]), witness digested on the device", "engine": key.witness_engine,
-                           "chain": {"mod_sqr": n_sqr, "mod_mul": n_mul, "mac_per_unit": a_wit}},
-                "gpu_launches": int(launches), "clocks": clocks, "parity": ok,
-                "mul_mod_per_s": world * units * args.steps * (n_sqr + n_mul) / (dev_ms * 1e-3),
-                "roofline": {"bound": "imad", "achieved": units * a_wit / ksec / 1e12, "peak": peak / 1e12, "unit": "TMAC/s",
-                             "frac": units * a_wit / ksec / peak, "peak_source": src, "traffic": None}}
+        line = {"metric": f"paillier_witness_units_per_s_n{N_BITS}", "value": res["value"], "unit": "units/s", "n_gpus": cx.world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_launch"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int64 columns over signed 28-bit digits + s8 IMMA, exact (q, rem) tail", "data": "synthetic",
+                "config": {"workload": f"batched encrypt + (q, rem) limb witness of every mul_mod, |n|={N_BITS}, {units} units per GPU per step"},
+                "gpu_launches": res["gpu_launches"], "clocks": res["clocks"], "parity": res["parity"], "witness": res,
+                "roofline": {"bound": "imad", "achieved": res["frac_of_imad_peak"] * peak / 1e12, "peak": peak / 1e12, "unit": "TMAC/s",
+                             "frac": res["frac_of_imad_peak"], "peak_source": src, "traffic": None}}
         emit(line)
     key.close()
-    if world > 1:
-        dist.destroy_process_group()
+    cx.close()
 
 
 def main():
@@ -378,13 +581,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--units", type=int, default=UNITS, help="units per GPU per step (default: the BASELINE config, 2^16)")
     ap.add_argument("--g", default="rand", choices=["rand", "std"], help="rand: random g (headline); std: g = n+1")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-witness", action="store_true", help="skip the witness-mode leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the full-batch CPU witness parity")
+    ap.add_argument("--no-witness", action="store_true", help="only the headline encrypt leg (used for ncu captures)")
+    ap.add_argument("--skip", default="", help="comma-separated legs to skip: witness,witness_e2e,tally,cells,witness3072")
+    ap.add_argument("--parity-budget", type=float, default=float(os.environ.get("PB200_PARITY_BUDGET_S", "240")),
+                    help="seconds of host time the full-batch CPU witness parity may take (units are checked in index order)")
     ap.add_argument("--engine", type=int, default=0)
     ap.add_argument("--n-bits", type=int, default=2048, help="key size |n| (default 2048, the BASELINE metric; others are the sweep)")
     ap.add_argument("--workload", default="encrypt", choices=["encrypt", "tally", "witness"],
-                    help="encrypt: the BASELINE metric (default); tally: product of 2^20 ciphertexts sharded over the GPUs (configs[2]); "
-                         "witness: encrypt + (q, rem) witness of every mul_mod (configs[3]: --n-bits 3072 --units 32768 on 8 GPUs)")
+                    help="encrypt: the BASELINE metric with every leg (default); tally: configs[2] alone; witness: the witness leg alone "
+                         "at --n-bits / --units")
     args = ap.parse_args()
     global N_BITS, METRIC
     N_BITS = args.n_bits
@@ -397,20 +603,14 @@ def main():
         return run_witness(args)
 
     import numpy as np
-    import torch
-    import torch.distributed as dist
 
     from paillier_halo2_b200 import PaillierKey, _lib, workload
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the Paillier hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = _lib.load()
+    cx = Ctx()
+    torch, lib, world, rank, local_rank = cx.torch, cx.lib, cx.world, cx.rank, cx.local_rank
+    skip = set(x for x in args.skip.split(",") if x)
+    if args.no_witness:
+        skip |= {"witness", "witness_e2e", "tally", "cells", "witness3072"}
     kd = workload.load_key(N_BITS)
     g = kd["g_rand"] if args.g == "rand" else kd["g_std"]
     units = args.units
@@ -429,17 +629,11 @@ def main():
     d_m = m_pin.cuda(non_blocking=False)
     d_r = r_pin.cuda(non_blocking=False)
     d_c = torch.empty((units, key.words_out), dtype=torch.int64, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
-    stream = torch.cuda.ExternalStream(key.stream, device=torch.device("cuda", local_rank))
+    stream = cx.stream_of(key)
+    barrier = cx.barrier
 
     def step_dev():
         key.encrypt_dev(d_m.data_ptr(), d_r.data_ptr(), units, d_c.data_ptr())
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 0)):
         step_dev()
@@ -452,8 +646,7 @@ def main():
     sampler.start()
     evs = []
     for _ in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
+        cx.flush_l2()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         step_dev()
@@ -462,11 +655,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = lib.pb200_kernel_launches() - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
+    (dev_ms,) = cx.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
     value = world * units * args.steps / (dev_ms * 1e-3)
 
     # ---- e2e: the host-buffer C-ABI call, pinned host memory, H2D + kernel + D2H inside the timed region
@@ -482,80 +671,57 @@ def main():
     for _ in range(args.steps):
         step_host()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    (e2e_s,) = cx.max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * units * args.steps / e2e_s
 
-    # ---- witness mode (BASELINE.json configs[1]: "witnesses checked bit-exact"): the reference's own LSB-first chain with the
-    # exact (q, rem) of every mul_mod, digested on the device (pb200_encrypt_witness_digest_dev), same units, inputs in HBM
-    witness = None
-    if not args.no_witness:
-        d_dig = torch.empty(units, dtype=torch.int64, device="cuda")
-        d_cw = torch.empty((units, key.words_out), dtype=torch.int64, device="cuda")
-        key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), units, d_cw.data_ptr(), d_dig.data_ptr())     # warm-up at full size
-        barrier()
-        wl0 = lib.pb200_kernel_launches()
-        w_sampler = ClockSampler(local_rank)
-        w_sampler.start()
-        w_evs = []
-        for _ in range(2):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            key.encrypt_witness_digest_dev(d_m.data_ptr(), d_r.data_ptr(), units, d_cw.data_ptr(), d_dig.data_ptr())
-            e1.record(stream)
-            w_evs.append((e0, e1))
-        barrier()
-        w_clocks = w_sampler.stop()
-        w_ms = sum(a.elapsed_time(b) for a, b in w_evs) / len(w_evs)
-        t = torch.tensor([w_ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        w_ms = float(t.item())
-        if rank == 0:
-            from oracle.paillier_oracle import encrypt_steps
-            from paillier_halo2_b200.api import witness_digest, words_to_ints
-            pop_n = bin(kd["n"]).count("1")
-            pop_m = float(np.mean([bin(v).count("1") for v in words_to_ints(m_w[:256])]))
-            w_sqr_n, w_mul_n = kd["n"].bit_length(), pop_n + pop_m + 1
-            a_wit = w_sqr_n * w_sqr + w_mul_n * w_mul
-            ok = bool((d_cw.cpu().numpy().view(np.uint64) == d_c.cpu().numpy().view(np.uint64)).all())
-            dig = d_dig.cpu().numpy().view(np.uint64)
-            for i in sorted({0, units - 1} | {(units * t) // 16 for t in range(16)}):       # 17 units spread over the batch
-                mi, ri = words_to_ints(m_w[i:i + 1])[0], words_to_ints(r_w[i:i + 1])[0]
-                _, steps = encrypt_steps(kd["n"], g, mi, ri)
-                gs = mi.bit_length() + bin(mi).count("1")
-                mine = [(x.q, x.rem) for x in steps[:gs] if x.kind == "mul"] + [(x.q, x.rem) for x in steps[gs:]]
-                ok = ok and int(dig[i]) == witness_digest(mine, key.words_out)
-            peak_w, _ = imad_peak()
-            witness = {"value": world * units / (w_ms * 1e-3), "unit": "units/s", "engine": key.witness_engine, "ms_per_launch": w_ms,
-                       "records_per_unit": w_sqr_n + w_mul_n, "mul_mod_per_s": world * units * (w_sqr_n + w_mul_n) / (w_ms * 1e-3),
-                       "witness_stream_GBps": world * units * (w_sqr_n + w_mul_n) * 2 * key.words_out * 8 / (w_ms * 1e-3) / 1e9,
-                       "chain": {"mod_sqr": w_sqr_n, "mod_mul": w_mul_n, "mac_per_unit": a_wit},
-                       "frac_of_imad_peak": units * a_wit / (w_ms * 1e-3) / peak_w,
-                       "gpu_launches": int(lib.pb200_kernel_launches() - wl0), "clocks": w_clocks,
-                       "ms_each": [a.elapsed_time(b) for a, b in w_evs],
-                       "parity": ok,
-                       "note": "reference chain (SURVEY.md A.5: bits(n) square_mod + popcount(n) + popcount(m) + 1 mul_mod per unit), exact (q, rem) "
-                               "per step folded into a 64-bit digest per unit on the device; ciphertexts equal the fast chain's; the digests of "
-                               "17 units spread over the batch are re-derived from the oracle's (q, rem) stream"}
-
+    # ---- witness mode (BASELINE.json configs[1]: "witnesses checked bit-exact"), device digests, then the witness delivered
+    witness, dig, cw_host, parity_job = None, None, None, None
+    if "witness" not in skip:
+        witness, d_dig, d_cw = leg_witness(cx, key, kd, g, N_BITS, m_w, r_w, d_m, d_r)
+        dig = d_dig.cpu().numpy().view(np.uint64)
+        cw_host = d_cw.cpu().numpy().view(np.uint64)
+        del d_dig, d_cw
+        if "witness_e2e" not in skip:
+            witness["e2e"] = leg_witness_e2e(cx, key, kd, g, N_BITS, m_w, r_w, 16384, dig)
+    # ---- tally (configs[2]) before the host cores get busy with the parity job: its launches are sub-millisecond
+    tally = leg_tally(cx, kd, N_BITS, 10, 3) if "tally" not in skip else None
+    # ---- full-batch witness parity on the host cores, in the background while the remaining GPU legs run
+    if witness is not None and rank == 0 and not args.no_cpu:
+        from oracle import cpu_ref
+        parity_job = ParityJob(kd, g, N_BITS, m_w, r_w, args.parity_budget, cpu_ref.hardware_threads()).start()
     # ---- K4: advice-cell expansion of mul_mod groups (HBM-bound writer), rank 0 only
-    cells = None
-    if not args.no_witness and rank == 0:
-        cells = cells_leg(key, kd, N_BITS)
+    cells = cells_leg(key, kd, N_BITS) if ("cells" not in skip and rank == 0) else None
+    # ---- configs[3]: |n| = 3072 witness, 32768 units per GPU
+    witness3072 = leg_witness_cfg3(cx, 32768) if "witness3072" not in skip else None
 
     # parity spot check of the last step's output against the CPU port (a checker, never the thing measured)
     parity = None
     if rank == 0:
         from oracle import cpu_ref
+        got_dev_all = d_c.cpu().numpy().view(np.uint64)
+        if parity_job is not None:
+            parity_job.join()
+            nd = parity_job.done
+            w_ok = bool((parity_job.dig == dig[:nd]).all() and (parity_job.cs == cw_host[:nd]).all())
+            fast_ok = bool((parity_job.cs == got_dev_all[:nd]).all() and (cw_host == got_dev_all).all())
+            witness["parity"] = w_ok and fast_ok
+            witness["parity_units"] = int(nd)
+            witness["parity_note"] = (f"digests and ciphertexts of the first {nd} of {units} units re-derived by the CPU chain "
+                                      f"(oracle/paillier_cpu.cpp, {parity_job.backend} backend, full product + div_rem per mul_mod, "
+                                      f"{parity_job.threads} threads, {parity_job.secs:.0f} s, budget {args.parity_budget:.0f} s); the fast chain's "
+                                      f"ciphertexts (k_encrypt) equal them too; all {units} fast-chain and witness-chain ciphertexts agree")
+        elif witness is not None:
+            idx17 = sorted({0, units - 1} | {(units * t) // 16 for t in range(16)})
+            from paillier_halo2_b200.api import witness_digest
+            ok = bool((cw_host == got_dev_all).all())
+            for i in idx17:
+                _, mine = unit_stream(kd, g, m_w[i:i + 1], r_w[i:i + 1])
+                ok = ok and int(dig[i]) == witness_digest(mine, key.words_out)
+            witness["parity"], witness["parity_units"] = ok, len(idx17)
         idx = [0, 1, units // 2, units - 1]
         want = cpu_ref.enc_batch(kd["n"], g, N_BITS // 64, m_w[idx], r_w[idx], threads=4)
-        got_dev = d_c.cpu().numpy().view(np.uint64)[idx]
         got_host = c_pin.numpy().view(np.uint64)[idx]
-        parity = bool((want == got_dev).all() and (want == got_host).all())
+        parity = bool((want == got_dev_all[idx]).all() and (want == got_host).all())
 
     if rank == 0:
         peak, peak_src = imad_peak()
@@ -575,6 +741,8 @@ def main():
             "clocks": clocks,
             "parity_spot_check": parity,
             "witness": witness,
+            "tally": tally,
+            "witness3072": witness3072,
             "cells": cells,
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC/s (32x32->64 multiply-accumulate)",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get((N_BITS, units)), "peak_source": peak_src,
@@ -602,8 +770,7 @@ def main():
                 line["cpu_baseline"]["python_int_enc_per_s_one_core"] = None
         emit(line)
     key.close()
-    if world > 1:
-        dist.destroy_process_group()
+    cx.close()
 
 
 if __name__ == "__main__":

@@ -13,7 +13,8 @@
  *   - a value of b bits occupies  PB200_WORDS(b) = ceil(b/64) words; unused high bits are zero;
  *   - batches are unit-major and contiguous: unit u starts at word u * words_per_value;
  *   - every function returns 0 (PB200_OK) or a negative pb200_status; nothing throws or aborts
- *     across the ABI (maps to Result<_, Error> on the Rust side, src/paillier.rs:38,68);
+ *     across the ABI (maps to Result<_, Error> on the Rust side, src/paillier.rs:38,68); entry points
+ *     run on the key's device and restore the caller's current CUDA device before returning;
  *   - the caller owns every buffer it passes; the library owns a pb200_key until
  *     pb200_key_destroy;  a key is bound to one CUDA device and one internal stream; calls on one
  *     key are serialised by the caller (mirrors &mut Context<F>), different keys may be used from
@@ -40,13 +41,21 @@ typedef enum pb200_status {
     PB200_OK = 0,
     PB200_ERR_INVALID_ARG = -1,   /* null pointer, zero sizes, n_bits % limb_bits != 0 (assign_integer's assert) */
     PB200_ERR_ZERO_MODULUS = -2,  /* n == 0: num-bigint modpow / % panic (src/paillier.rs:89-91,96) */
-    PB200_ERR_EVEN_MODULUS = -3,  /* n even: outside the GPU path's contract (a Paillier n = p*q is odd) */
+    PB200_ERR_EVEN_MODULUS = -3,  /* reserved (never returned): even n is accepted, as in the reference, whose tests draw
+                                     n = rng.gen_biguint(bits) (src/paillier.rs:173,251) */
     PB200_ERR_RANGE = -4,         /* an input does not fit its declared bit width (range check would fail) */
     PB200_ERR_UNSUPPORTED = -5,   /* key size larger than the largest compiled engine */
     PB200_ERR_CUDA = -6,          /* CUDA runtime failure; pb200_last_cuda_error() has the text */
     PB200_ERR_NOMEM = -7,
-    PB200_ERR_SINK = -8           /* the witness sink callback returned non-zero */
+    PB200_ERR_SINK = -8,          /* the witness sink callback returned non-zero */
+    PB200_ERR_CONSTRAINT = -9,    /* a supplied (q, rem) does not satisfy a*b = q*n^2 + rem (mul_mod's equality would fail) */
+    PB200_ERR_PEER = -10          /* multi-GPU tally: a peer's partial did not arrive within the kernel's time-out */
 } pb200_status;
+
+/* bits of the per-key device flag word (pb200_key_take_flags) */
+#define PB200_FLAG_RANGE 1u       /* -> PB200_ERR_RANGE */
+#define PB200_FLAG_CONSTRAINT 2u  /* -> PB200_ERR_CONSTRAINT */
+#define PB200_FLAG_PEER_TIMEOUT 4u /* a peer GPU's tally partial did not arrive (pb200_tally_peer_dev / pb200_tally_multi) */
 
 typedef struct pb200_key pb200_key;
 
@@ -84,6 +93,10 @@ void* pb200_key_stream(const pb200_key* key);        /* cudaStream_t the key enq
  * roofline's algorithmic work is counted on; excludes the engine's internal canonicalisation) */
 int pb200_key_chain_counts(const pb200_key* key, uint64_t* n_sqr, uint64_t* n_mul);
 int pb200_key_sync(pb200_key* key);                  /* cudaStreamSynchronize on that stream */
+/* _dev entry points report range / constraint failures only through a per-key flag word on the device.  This call synchronises
+ * the key's stream, returns the word (PB200_FLAG_*) and clears it.  Host entry points clear it when they start and map it to
+ * their return status, so a _dev failure never leaks into a later host call. */
+int pb200_key_take_flags(pb200_key* key, uint32_t* flags_out);
 
 /* ---- encrypt --------------------------------------------------------------------------------
  * Replaces: paillier_enc_native (src/paillier.rs:87-92) for `count` independent (m, r) pairs, and
@@ -113,9 +126,30 @@ int pb200_add_batch_dev(pb200_key* key, const uint64_t* d_c1_le, const uint64_t*
  * _dev: d_c on the key's device, d_partial_out receives one words_out-word value on the device. */
 int pb200_tally(pb200_key* key, const uint64_t* c_le, size_t count, uint64_t* out_le);
 int pb200_tally_dev(pb200_key* key, const uint64_t* d_c_le, size_t count, uint64_t* d_partial_out_le);
-/* combine `n_partials` per-shard partial products (host memory, e.g. gathered from the other
- * ranks with NCCL all-gather or a host gather) into the final product on the key's device */
+/* combine `n_partials` per-shard partial products (host memory, e.g. gathered by the caller) into the final product on the
+ * key's device: the same fold on the key's own engine */
 int pb200_tally_combine(pb200_key* key, const uint64_t* partials_le, size_t n_partials, uint64_t* out_le);
+
+/* ---- multi-GPU tally (BASELINE.json configs[2]; SURVEY.md 8b pb200_tally(keys[], n_gpus, ..)) --------------------------------
+ * Replaces: the fold of paillier_add_native (src/paillier.rs:94-97) over ciphertexts that are sharded across the GPUs of one
+ * NVLink/NVSwitch domain.  ONE kernel launch per GPU: every GPU folds its shard, stores its 2|n|/8-byte partial into every
+ * peer's mailbox through peer-mapped memory, waits for the peers' partials in its own mailbox and combines them — no NCCL call,
+ * no host hop, no second launch; every GPU ends with the full product (bit-identical: the product is commutative).
+ *
+ * Single process, one key per device: keys[i] must hold the same n; d_c[i] is the shard resident on keys[i]'s device
+ * (counts[i] ciphertexts of words_out words); out_le (host) receives the product.  Peer access is enabled on first use; when
+ * the devices cannot reach each other the partials are gathered through the host and combined on keys[0] instead. */
+int pb200_tally_multi(pb200_key* const* keys, int n_gpus, const uint64_t* const* d_c, const size_t* counts, uint64_t* out_le);
+
+/* One process per GPU (torchrun / MPI): each rank exports a handle to its mailbox, the ranks exchange the 64-byte handles by
+ * any means (e.g. an all-gather on the host), each rank connects, and from then on pb200_tally_peer_dev is a COLLECTIVE call:
+ * every rank calls it once per tally, in the same order, on its own shard.  d_out (device, words_out words) receives the full
+ * product on every rank; enqueued on the key's stream, no synchronise.  A rank whose peers never arrive gives up after a few
+ * seconds and raises PB200_FLAG_PEER_TIMEOUT in the key's flag word.  world <= 8. */
+typedef struct pb200_ipc_handle { unsigned char bytes[64]; } pb200_ipc_handle;
+int pb200_tally_peer_export(pb200_key* key, pb200_ipc_handle* out);
+int pb200_tally_peer_connect(pb200_key* key, int rank, int world, const pb200_ipc_handle* handles /* world entries */);
+int pb200_tally_peer_dev(pb200_key* key, const uint64_t* d_c_le, size_t count, uint64_t* d_out_le);
 
 /* ---- witness --------------------------------------------------------------------------------
  * Replaces: the witness generation inside BigUintChip::pow_mod_fixed_exp / mul_mod that
@@ -138,10 +172,16 @@ typedef struct pb200_witness_chunk {
     const uint32_t* g_mul_counts;  /* n_units: number of g-chain mul records at the head of each unit */
 } pb200_witness_chunk;
 
-/* called on the calling thread, chunk memory is valid only during the call; return 0 to continue */
+/* called on the calling thread; chunk memory (pinned host memory owned by the library) is valid only during the call;
+ * return 0 to continue */
 typedef int (*pb200_witness_sink_fn)(void* user, const pb200_witness_chunk* chunk);
 
-/* max_chunk_units == 0 lets the library size chunks to its staging buffers */
+/* Delivery: the stream does not fit anywhere whole (4 MB per unit at |n| = 2048), so it is produced on the device in chunks
+ * (two record buffers sized from the free device memory: the kernel of the next chunk runs while this one drains) and handed
+ * to the sink in pieces of whole units through a ring of four pinned staging slots filled by a second stream — while the sink
+ * works on one piece the next three are crossing PCIe.  max_chunk_units bounds the units per sink call (0: as many as fit a
+ * staging slot, 256 MiB unless PB200_WITNESS_SLOT_BYTES says otherwise; PB200_WITNESS_CHUNK_BYTES bounds a device chunk).
+ * c_out (nullable) receives the ciphertexts of a chunk before its first piece is delivered. */
 int pb200_encrypt_witness_batch(pb200_key* key, const uint64_t* m_le, const uint64_t* r_le, size_t count,
                                 uint64_t* c_out_le /* nullable */, size_t max_chunk_units,
                                 pb200_witness_sink_fn sink, void* user);
@@ -204,7 +244,7 @@ typedef struct pb200_cell_layout {
 } pb200_cell_layout;
 int pb200_cells_layout(pb200_key* key, uint32_t lookup_bits, pb200_cell_layout* out);
 /* a, b, q, rem: count * words_out words each (q, rem as produced by the witness stream / pb200_add_batch);
- * cells_out: count * cells_per_mulmod * 4 words.  PB200_ERR_RANGE if some (q, rem) does not satisfy
+ * cells_out: count * cells_per_mulmod * 4 words.  PB200_ERR_CONSTRAINT if some (q, rem) does not satisfy
  * a*b = q*n^2 + rem (the chip's equality constraint would fail).  _dev: device pointers, no synchronise,
  * no check. */
 int pb200_mulmod_cells_batch(pb200_key* key, const uint64_t* a_le, const uint64_t* b_le, const uint64_t* q_le,

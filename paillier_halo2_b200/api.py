@@ -226,6 +226,41 @@ class PaillierKey(CellMixin):
     def sync(self) -> None:
         check(self._lib.pb200_key_sync(self._h), "pb200_key_sync")
 
+    def take_flags(self) -> int:
+        """Synchronise, return and clear the per-key device flag word (PB200_FLAG_*): how _dev callers learn of a failure."""
+        f = C.c_uint32()
+        check(self._lib.pb200_key_take_flags(self._h, C.byref(f)), "pb200_key_take_flags")
+        return int(f.value)
+
+    # -- multi-GPU tally: one process per GPU (pb200_tally_peer_*), or one process driving several keys (tally_multi) ------
+    def tally_peer_export(self) -> bytes:
+        """64-byte handle of this key's mailbox; the ranks exchange these and pass the list to tally_peer_connect."""
+        buf = (C.c_ubyte * 64)()
+        check(self._lib.pb200_tally_peer_export(self._h, buf), "pb200_tally_peer_export")
+        return bytes(buf)
+
+    def tally_peer_connect(self, rank: int, world: int, handles: Sequence[bytes]) -> None:
+        raw = b"".join(handles) if world > 1 else bytes(64)
+        assert len(raw) == 64 * max(world, 1)
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        check(self._lib.pb200_tally_peer_connect(self._h, rank, world, buf), "pb200_tally_peer_connect")
+
+    def tally_peer_dev(self, d_c: int, count: int, d_out: int) -> None:
+        """Collective: every rank of the connected group calls it once per tally; d_out receives the full product."""
+        check(self._lib.pb200_tally_peer_dev(self._h, d_c, count, d_out), "pb200_tally_peer_dev")
+
+    @staticmethod
+    def tally_multi(keys: Sequence["PaillierKey"], d_cs: Sequence[int], counts: Sequence[int]) -> int:
+        """pb200_tally_multi: keys[i] on distinct devices of one process, d_cs[i] the device pointer of shard i."""
+        n = len(keys)
+        lib = keys[0]._lib
+        hk = (C.c_void_p * n)(*[k._h for k in keys])
+        hp = (C.c_void_p * n)(*[C.c_void_p(p) for p in d_cs])
+        hc = (C.c_size_t * n)(*counts)
+        out = np.empty(keys[0].words_out, dtype="<u8")
+        check(lib.pb200_tally_multi(hk, n, hp, hc, _p(out)), "pb200_tally_multi")
+        return words_to_ints(out)[0]
+
     # -- raw array API (uint64 little-endian words, unit-major) -----------------------------
     def encrypt_words(self, m_w: np.ndarray, r_w: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         m_w = np.ascontiguousarray(m_w, dtype="<u8")

@@ -254,17 +254,41 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_gtable_fill(B28Dev K, const i
     }
 }
 
+// Per-CTA global scratch is sized by the CTAs that can be RESIDENT, not by the grid: a CTA takes one of the `per_sm` slots of the
+// SM it runs on (a bit of masks[%smid], atomicCAS) and gives it back when it ends.  per_sm is the occupancy the runtime reports
+// for the kernel, so a free bit always exists; the loop still re-reads the mask should that ever not hold.
+struct SlotPool { unsigned* masks; int per_sm; };
+__device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+__device__ __forceinline__ int slot_acquire(const SlotPool& P) {
+    unsigned* mk = P.masks + smid();
+    const unsigned full = P.per_sm >= 32 ? 0xffffffffu : ((1u << P.per_sm) - 1u);
+    for (;;) {
+        const unsigned cur = *(volatile unsigned*)mk;
+        const unsigned free_bits = ~cur & full;
+        if (!free_bits) { __nanosleep(100); continue; }
+        const int b = __ffs((int)free_bits) - 1;
+        if (atomicCAS(mk, cur, cur | (1u << b)) == cur) return (int)smid() * P.per_sm + b;
+    }
+}
+__device__ __forceinline__ void slot_release(const SlotPool& P, int slot) {
+    atomicAnd(P.masks + slot / P.per_sm, ~(1u << (slot % P.per_sm)));
+}
+__global__ void k_nsmid(unsigned* out) { unsigned v; asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v)); *out = v; }
+
 template <class C, bool MMA>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K, const u64* __restrict__ m, const u64* __restrict__ r,
-                                                            size_t count, u64* __restrict__ c_out, int4* scratch) {
+                                                            size_t count, u64* __restrict__ c_out, int4* scratch, SlotPool pool) {
     extern __shared__ int4 smem[];
+    __shared__ int s_slot;
     Smem<C> S(smem);
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_slot = slot_acquire(pool);
     load_consts<C>(smem, K);
+    const int slot = s_slot;
     size_t unit = (size_t)blockIdx.x * 32 + lane;
     const bool active = unit < count;
     if (!active) unit = count - 1;
-    int4* tab = scratch + (size_t)blockIdx.x * SCRATCH_ENTRIES * C::VAL4;
+    int4* tab = scratch + (size_t)slot * SCRATCH_ENTRIES * C::VAL4;
     // ---- r^n: odd powers table, then the per-key window schedule
     load_value<C>(S.V, r + unit * K.words_in, K.words_in, role, lane);
     copy_to_global<C>(tab, S.V, role, lane);                                   // tab[0] = r
@@ -315,43 +339,159 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K
     copy_from_global<C>(S.B, tab + (size_t)(TABN + 1) * C::VAL4, role, lane);
     mulmod<C, false, MMA>(S, S.B, role, lane);
     finalize<C, MMA>(S, K, c_out + unit * K.words_out, active, role, lane);
+    if (threadIdx.x == 0) slot_release(pool, slot);
 }
 
-// out[b] = product of the inputs assigned to CTA b (lane l of CTA b folds units b*32+l, +stride, ...), canonical
-template <class C, bool MMA>
-__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, const u64* __restrict__ c, size_t count, u64* __restrict__ out) {
-    extern __shared__ int4 smem[];
-    Smem<C> S(smem);
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    load_consts<C>(smem, K);
-    const size_t stride = (size_t)gridDim.x * 32;
-    size_t first = (size_t)blockIdx.x * 32 + lane;
-    size_t max_iters = (count + stride - 1) / stride;
-    set_one<C>(S.V, role, lane);
-    for (size_t it = 0; it < max_iters; it++) {
-        size_t u = first + it * stride;
-        const bool have = u < count;
-        const size_t base = (size_t)blockIdx.x * 32 + it * stride;                  // first unit of this CTA step
-        stage_words<C>((u64*)S.T, c + base * K.words_out, base < count ? (int)(count - base < 32 ? count - base : 32) : 0, K.words_out);
-        load_value_staged<C>(S.B, (const u64*)S.T, K.words_out, role, lane);
-        if (!have) {                                   // lanes without an input multiply by one
-            int a[C::CH * 4];
+// ---- tally: the N-ary fold of paillier_add_native (/root/reference/src/paillier.rs:94-97) in ONE launch per GPU -------------------
+// 1. every lane of every CTA folds a strided subset of the inputs (main loop, all lanes useful);
+// 2. the CTAs fold pairwise up a binary tree by "last arriver continues": a CTA stores its 32 lane values in its node slot, bumps
+//    the node counter and leaves if its sibling has not arrived yet; the one that arrives second loads the sibling's values and
+//    multiplies (32 useful lanes per multiplication, no spinning, no co-residency assumption);
+// 3. the one surviving CTA folds its 32 lanes (5 steps) and canonicalises;
+// 4. multi-GPU (world > 1): it stores the canonical partial into every peer's mailbox over NVLink (plain stores to mapped peer
+//    memory, then a release flag at system scope), waits for the peers' partials in its own mailbox, folds the `world` partials
+//    (3 steps at 8 GPUs) and canonicalises again — every GPU ends with the full product, no host hop and no second launch.
+constexpr int TALLY_MAXW = 8;                          // GPUs of one NVSwitch domain
+constexpr int MAIL_WORDS = 128;                        // one partial: up to 2*4096/64 words
+constexpr size_t MAIL_FLAG_OFF = (size_t)2 * TALLY_MAXW * MAIL_WORDS;      // u64 index of flags[parity][src]
+constexpr size_t MAIL_U64 = MAIL_FLAG_OFF + 2 * TALLY_MAXW;
+struct TallyPeer {
+    int world, rank;
+    unsigned long long epoch;          // sequence number of this collective call (>= 1); parity selects the mailbox half
+    u64* mail[TALLY_MAXW];             // every rank's mailbox as mapped on THIS device (mail[rank] is the local one)
+    int* flags;                        // the key's flag word (bit 2: a peer's partial did not arrive)
+};
+
+template <class C>
+__device__ __forceinline__ void copy_from_global_cg(int4* buf, const int4* g, int role, int lane) {     // written by another SM: L2 only
 #pragma unroll
-            for (int k = 0; k < C::CH * 4; k++) a[k] = 0;
-            if (role == 0) a[0] = 1;
-            store_block<C>(blk_ptr<C>(S.B, role, lane), a);
-        }
-        __syncthreads();
-        mulmod<C, false, MMA>(S, S.B, role, lane);
+    for (int c = 0; c < C::CH; c++) buf[(role * C::CH + c) * 32 + lane] = __ldcg(g + (role * C::CH + c) * 32 + lane);
+    __syncthreads();
+}
+template <class C>
+__device__ __forceinline__ void set_one_where(int4* buf, bool cond, int role, int lane) {
+    if (cond) {
+        int a[C::CH * 4];
+#pragma unroll
+        for (int k = 0; k < C::CH * 4; k++) a[k] = 0;
+        if (role == 0) a[0] = 1;
+        store_block<C>(blk_ptr<C>(buf, role, lane), a);
     }
-    // fold the 32 lanes: B[lane] = V[lane ^ off]
-    for (int off = 16; off >= 1; off >>= 1) {
+    __syncthreads();
+}
+// V[lane] <- product over the lanes of its aligned group of `width` lanes (width a power of two <= 32)
+template <class C, bool MMA>
+__device__ __forceinline__ void fold_lanes(Smem<C>& S, int width, int role, int lane) {
+    for (int off = width >> 1; off >= 1; off >>= 1) {
 #pragma unroll
         for (int ch = 0; ch < C::CH; ch++) S.B[(role * C::CH + ch) * 32 + lane] = S.V[(role * C::CH + ch) * 32 + (lane ^ off)];
         __syncthreads();
         mulmod<C, false, MMA>(S, S.B, role, lane);
     }
-    finalize<C, MMA>(S, K, out + (size_t)blockIdx.x * K.words_out, lane == 0, role, lane);
+}
+
+template <class C, bool MMA>
+__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, const u64* __restrict__ c, size_t count, u64* __restrict__ out,
+                                                                      int4* nodes, unsigned* node_cnt, TallyPeer P) {
+    extern __shared__ int4 smem[];
+    __shared__ int s_first;
+    Smem<C> S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    load_consts<C>(smem, K);
+    // ---- 1. main loop
+    const size_t stride = (size_t)gridDim.x * 32;
+    const size_t first = (size_t)blockIdx.x * 32 + lane;
+    const size_t max_iters = (count + stride - 1) / stride;
+    set_one<C>(S.V, role, lane);
+    for (size_t it = 0; it < max_iters; it++) {
+        const size_t u = first + it * stride;
+        const size_t base = (size_t)blockIdx.x * 32 + it * stride;                  // first unit of this CTA step
+        stage_words<C>((u64*)S.T, c + base * K.words_out, base < count ? (int)(count - base < 32 ? count - base : 32) : 0, K.words_out);
+        load_value_staged<C>(S.B, (const u64*)S.T, K.words_out, role, lane);
+        set_one_where<C>(S.B, u >= count, role, lane);                               // lanes without an input multiply by one
+        mulmod<C, false, MMA>(S, S.B, role, lane);
+    }
+    // ---- 2. tree over the CTAs
+    {
+        int idx = blockIdx.x, n = gridDim.x;
+        size_t node_base = 0;
+        while (n > 1) {
+            const int j = idx >> 1;
+            if ((idx ^ 1) < n) {
+                int4* slot = nodes + (node_base + j) * 2 * (size_t)C::VAL4;
+                copy_to_global<C>(slot + (size_t)(idx & 1) * C::VAL4, S.V, role, lane);
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) s_first = atomicAdd(node_cnt + node_base + j, 1u) == 0u;
+                __syncthreads();
+                if (s_first) return;                                                 // the sibling will pick this value up
+                if (threadIdx.x == 0) node_cnt[node_base + j] = 0;                   // both arrived: ready for the next launch
+                __threadfence();
+                copy_from_global_cg<C>(S.B, slot + (size_t)((idx & 1) ^ 1) * C::VAL4, role, lane);
+                mulmod<C, false, MMA>(S, S.B, role, lane);
+            }
+            node_base += (size_t)((n + 1) >> 1);
+            idx = j; n = (n + 1) >> 1;
+        }
+    }
+    // ---- 3. the surviving CTA: fold its lanes, canonical partial
+    fold_lanes<C, MMA>(S, 32, role, lane);
+    if (P.world <= 1) { finalize<C, MMA>(S, K, out, lane == 0, role, lane); return; }
+    // ---- 4. exchange over peer memory and combine
+    const int par = (int)(P.epoch & 1);
+    u64* mine = P.mail[P.rank] + ((size_t)par * TALLY_MAXW + P.rank) * MAIL_WORDS;
+    finalize<C, MMA>(S, K, mine, lane == 0, role, lane);
+    __threadfence();
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (P.world - 1) * K.words_out; idx += C::THREADS) {
+        int peer = idx / K.words_out; const int w = idx - peer * K.words_out;
+        if (peer >= P.rank) peer++;
+        P.mail[peer][((size_t)par * TALLY_MAXW + P.rank) * MAIL_WORDS + w] = __ldcg(mine + w);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
+        // publish: my partial is in peer t's mailbox;   then wait for peer t's partial in mine
+        u64* theirs = P.mail[threadIdx.x] + MAIL_FLAG_OFF + (size_t)par * TALLY_MAXW + P.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(theirs), "l"(P.epoch) : "memory");
+        const u64* flag = P.mail[P.rank] + MAIL_FLAG_OFF + (size_t)par * TALLY_MAXW + threadIdx.x;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            if (v >= P.epoch) break;
+            if (clock64() - t0 > 6000000000ll) { atomicOr(P.flags, 4); break; }      // ~3 s: a peer never called
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    {
+        const int src = lane < P.world ? lane : P.world - 1;
+        const u64* w = P.mail[P.rank] + ((size_t)par * TALLY_MAXW + src) * MAIL_WORDS;
+        int a[C::CH * 4];
+        int carry = 0;
+#pragma unroll
+        for (int k = 0; k < C::BL; k++) {
+            const int bit = W * (role * C::BL + k);
+            const int wi = bit >> 6, sh = bit & 63;
+            const u64 lo = wi < K.words_out ? __ldcg(w + wi) : 0, hi = wi + 1 < K.words_out ? __ldcg(w + wi + 1) : 0;
+            const u64 v = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+            const int t = (int)(v & ((1u << W) - 1)) + carry;
+            const int d = sgxt28(t);
+            carry = (t - d) >> W;
+            a[k] = d;
+        }
+#pragma unroll
+        for (int k = C::BL; k < C::CH * 4; k++) a[k] = 0;
+        store_block<C>(blk_ptr<C>(S.V, role, lane), a);
+        __syncthreads();
+        if (role + 1 < C::G) ((int*)blk_ptr<C>(S.V, role + 1, lane))[0] += carry;
+        __syncthreads();
+    }
+    set_one_where<C>(S.V, lane >= P.world, role, lane);
+    int width = 1; while (width < P.world) width <<= 1;
+    fold_lanes<C, MMA>(S, width, role, lane);
+    finalize<C, MMA>(S, K, out, lane == 0, role, lane);
 }
 
 
@@ -582,8 +722,13 @@ struct Block28Key {
     std::string name;
     B28Dev dev{};
     int4* d_consts = nullptr; int2* d_ops = nullptr; int4* d_tg = nullptr; u64* d_gwords = nullptr; int4* d_nentry = nullptr;
-    int4* d_scratch = nullptr; size_t scratch_ctas = 0;
-    u64* d_partials = nullptr; size_t partials_cap = 0;
+    int4* d_scratch = nullptr; size_t scratch_slots = 0;     // r-power tables, one per resident-CTA slot (SlotPool)
+    unsigned* d_slot_masks = nullptr; int nsmid = 0, enc_per_sm = 0;
+    int4* d_nodes = nullptr; unsigned* d_node_cnt = nullptr; size_t node_ctas = 0;   // tally tree: 2 values per node, arrival counters
+    u64* d_mail = nullptr;                                   // tally mailbox (peer-visible), MAIL_U64 words
+    TallyPeer peer{};                                        // world <= 1 until block28_tally_peer_connect
+    void* ipc_opened[TALLY_MAXW] = {};                       // peer mailboxes opened with cudaIpcOpenMemHandle
+    int device = 0;
     int sms = 148;
     uint64_t n_sqr = 0, n_mul = 0;   // modular squarings / multiplications per encryption
     bool use_mma = true;             // constant-operand phases on the tensor pipe (engine 3) or on IMAD (engine 2)
@@ -633,7 +778,7 @@ template <class C>
 static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits, int device, cudaStream_t st, cudaError_t* cuda_err) {
     Block28Key* key = new Block28Key();
     key->G = C::G; key->BL = C::BL;
-    key->n = n; key->n_bits = n_bits;
+    key->n = n; key->n_bits = n_bits; key->device = device;
     key->name = "block28t<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">";
     cudaDeviceProp prop;
     CUK(cudaGetDeviceProperties(&prop, device));
@@ -719,53 +864,63 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     return key;
 }
 
+#define CUW(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+
 template <class C>
 static cudaError_t encrypt_cfg(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st) {
-    size_t ctas = (count + 31) / 32;
-    if (ctas > key->scratch_ctas) {
-        if (key->d_scratch) cudaFree(key->d_scratch);
-        key->d_scratch = nullptr; key->scratch_ctas = 0;
-        cudaError_t e = cudaMalloc(&key->d_scratch, ctas * SCRATCH_ENTRIES * C::VAL4 * sizeof(int4));
-        if (e != cudaSuccess) return e;
-        key->scratch_ctas = ctas;
+    if (!key->d_scratch) {
+        // slots = SM ids x resident CTAs per SM (occupancy of the kernel as compiled), independent of the batch size
+        unsigned* d_n = nullptr; unsigned h_n = 0;
+        CUW(cudaMalloc(&d_n, sizeof(unsigned)));
+        k_nsmid<<<1, 1, 0, st>>>(d_n); count_launch();
+        CUW(cudaMemcpyAsync(&h_n, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CUW(cudaStreamSynchronize(st));
+        cudaFree(d_n);
+        int per_sm = 0;
+        CUW((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encrypt<C, true>, C::THREADS, C::SMEM_BYTES)));
+        if (per_sm < 1 || per_sm > 32 || h_n == 0) return cudaErrorLaunchOutOfResources;
+        key->nsmid = (int)h_n; key->enc_per_sm = per_sm;
+        CUW(cudaMalloc(&key->d_slot_masks, h_n * sizeof(unsigned)));
+        CUW(cudaMemsetAsync(key->d_slot_masks, 0, h_n * sizeof(unsigned), st));
+        const size_t slots = (size_t)h_n * per_sm;
+        CUW(cudaMalloc(&key->d_scratch, slots * SCRATCH_ENTRIES * C::VAL4 * sizeof(int4)));
+        key->scratch_slots = slots;
     }
-    if (key->use_mma) k_encrypt<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch);
-    else k_encrypt<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch);
+    const SlotPool pool{key->d_slot_masks, key->enc_per_sm};
+    const size_t ctas = (count + 31) / 32;
+    if (key->use_mma) k_encrypt<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
+    else k_encrypt<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
     count_launch();
     return cudaGetLastError();
 }
 
+// nodes of the CTA tree over `n` leaves: sum of ceil(n / 2^l) for l >= 1
+static size_t tree_nodes(size_t n) { size_t t = 0; while (n > 1) { n = (n + 1) >> 1; t += n; } return t; }
+
 template <class C>
-static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64* d_out, cudaStream_t st) {
-    const int wo = key->dev.words_out;
-    size_t cap = (size_t)C::CTAS_PER_SM * key->sms + 8;
-    if (!key->d_partials) {
-        cudaError_t e = cudaMalloc(&key->d_partials, cap * wo * sizeof(u64));
-        if (e != cudaSuccess) return e;
-        key->partials_cap = cap;
-    }
+static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64* d_out, bool collective, cudaStream_t st) {
+    const size_t cap = (size_t)C::CTAS_PER_SM * key->sms;
     size_t ctas = (count + 31) / 32;
-    if (ctas > (size_t)C::CTAS_PER_SM * key->sms) ctas = (size_t)C::CTAS_PER_SM * key->sms;
-    if (ctas <= 1) {
-        if (key->use_mma) k_tally<C, true><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out);
-        else k_tally<C, false><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out);
-        count_launch();
-        return cudaGetLastError();
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    if (!key->d_nodes) {
+        const size_t nodes = tree_nodes(cap) + 1;
+        CUW(cudaMalloc(&key->d_nodes, nodes * 2 * C::VAL4 * sizeof(int4)));
+        CUW(cudaMalloc(&key->d_node_cnt, nodes * sizeof(unsigned)));
+        CUW(cudaMemsetAsync(key->d_node_cnt, 0, nodes * sizeof(unsigned), st));
+        key->node_ctas = cap;
     }
-    if (key->use_mma) {
-        k_tally<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, key->d_partials);
-        k_tally<C, true><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->d_partials, ctas, d_out);
-    } else {
-        k_tally<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, key->d_partials);
-        k_tally<C, false><<<1, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->d_partials, ctas, d_out);
-    }
-    count_launch(2);
+    TallyPeer P = key->peer;
+    if (!collective || P.world <= 1) { P.world = 1; P.rank = 0; }
+    else { key->peer.epoch += 1; P.epoch = key->peer.epoch; }
+    if (key->use_mma) k_tally<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
+    else k_tally<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
+    count_launch();
     return cudaGetLastError();
 }
 
 
 // ---- witness engine: per-key constants and launcher ------------------------------------------------------
-#define CUW(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
 
 template <class C>
 static cudaError_t witness_prepare_cfg(Block28Key* key, u64* d_gchain, bool gchain_ready, cudaStream_t st) {
@@ -866,7 +1021,11 @@ void block28_destroy(Block28Key* key) {
     if (key->d_nentry) cudaFree(key->d_nentry);
     if (key->d_gwords) cudaFree(key->d_gwords);
     if (key->d_scratch) cudaFree(key->d_scratch);
-    if (key->d_partials) cudaFree(key->d_partials);
+    if (key->d_slot_masks) cudaFree(key->d_slot_masks);
+    if (key->d_nodes) cudaFree(key->d_nodes);
+    if (key->d_node_cnt) cudaFree(key->d_node_cnt);
+    for (int i = 0; i < TALLY_MAXW; i++) if (key->ipc_opened[i]) cudaIpcCloseMemHandle(key->ipc_opened[i]);
+    if (key->d_mail) cudaFree(key->d_mail);
     if (key->d_wconsts) cudaFree(key->d_wconsts);
     if (key->d_gtab) cudaFree(key->d_gtab);
     if (key->d_one_s) cudaFree(key->d_one_s);
@@ -887,13 +1046,47 @@ cudaError_t block28_encrypt(Block28Key* key, const u64* d_m, const u64* d_r, siz
     if (key->BL == 14) return encrypt_cfg<Cfg3072>(key, d_m, d_r, count, d_c, st);
     return encrypt_cfg<Cfg4096>(key, d_m, d_r, count, d_c, st);
 }
-cudaError_t block28_tally(Block28Key* key, const u64* d_c, size_t count, u64* d_out, cudaStream_t st) {
-    if (key->G == 4) return tally_cfg<Cfg1024>(key, d_c, count, d_out, st);
-    if (key->G == 8) return tally_cfg<Cfg2048>(key, d_c, count, d_out, st);
-    if (key->BL == 14) return tally_cfg<Cfg3072>(key, d_c, count, d_out, st);
-    return tally_cfg<Cfg4096>(key, d_c, count, d_out, st);
+static cudaError_t tally_dispatch(Block28Key* key, const u64* d_c, size_t count, u64* d_out, bool collective, cudaStream_t st) {
+    if (key->G == 4) return tally_cfg<Cfg1024>(key, d_c, count, d_out, collective, st);
+    if (key->G == 8) return tally_cfg<Cfg2048>(key, d_c, count, d_out, collective, st);
+    if (key->BL == 14) return tally_cfg<Cfg3072>(key, d_c, count, d_out, collective, st);
+    return tally_cfg<Cfg4096>(key, d_c, count, d_out, collective, st);
 }
+cudaError_t block28_tally(Block28Key* key, const u64* d_c, size_t count, u64* d_out, cudaStream_t st) {
+    return tally_dispatch(key, d_c, count, d_out, false, st);
+}
+// collective over the connected peer group: every rank calls it once per tally, in the same order
+cudaError_t block28_tally_peer(Block28Key* key, const u64* d_c, size_t count, u64* d_out, cudaStream_t st) {
+    return tally_dispatch(key, d_c, count, d_out, true, st);
+}
+int block28_peer_world(const Block28Key* key) { return key->peer.world; }
 
+// the peer-visible mailbox of this key (allocated on first use, zeroed)
+cudaError_t block28_mailbox(Block28Key* key, u64** d_mail, cudaStream_t st) {
+    if (!key->d_mail) {
+        CUW(cudaMalloc(&key->d_mail, MAIL_U64 * sizeof(u64)));
+        CUW(cudaMemsetAsync(key->d_mail, 0, MAIL_U64 * sizeof(u64), st));
+        CUW(cudaStreamSynchronize(st));
+    }
+    *d_mail = key->d_mail;
+    return cudaSuccess;
+}
+size_t block28_mailbox_bytes() { return MAIL_U64 * sizeof(u64); }
+int block28_max_world() { return TALLY_MAXW; }
+// mail[i]: rank i's mailbox as addressable from this key's device (mail[rank] must be this key's own); opened[i]: non-null when
+// the pointer came from cudaIpcOpenMemHandle and must be closed with the key
+cudaError_t block28_tally_peer_connect(Block28Key* key, int rank, int world, u64* const* mail, void* const* opened, int* d_flags) {
+    if (world < 1 || world > TALLY_MAXW || rank < 0 || rank >= world) return cudaErrorInvalidValue;
+    for (int i = 0; i < TALLY_MAXW; i++) {
+        if (key->ipc_opened[i]) { cudaIpcCloseMemHandle(key->ipc_opened[i]); key->ipc_opened[i] = nullptr; }
+        key->peer.mail[i] = i < world ? mail[i] : nullptr;
+        if (opened && i < world) key->ipc_opened[i] = opened[i];
+    }
+    key->peer.world = world; key->peer.rank = rank; key->peer.epoch = 0; key->peer.flags = d_flags;
+    // a reconnect restarts the epochs: the local mailbox flags must restart with them
+    if (key->d_mail) CUW(cudaMemset(key->d_mail + MAIL_FLAG_OFF, 0, 2 * TALLY_MAXW * sizeof(u64)));
+    return cudaSuccess;
+}
 
 template <class C>
 static cudaError_t add_cfg(Block28Key* key, const u64* d_c1, const u64* d_c2, int c_words, size_t count, u64* d_out, u64* d_q,

@@ -7,6 +7,7 @@
 #include "engine.hpp"
 #include "cells.hpp"
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <new>
@@ -17,9 +18,30 @@ static thread_local std::string t_cuda_error;
 
 static int cuda_fail(cudaError_t e, const char* where) {
     t_cuda_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return PB200_ERR_NOMEM; }
     return PB200_ERR_CUDA;
 }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+// Nothing may unwind through an extern "C" frame: every entry point is a function-try-block ending in PB200_CATCH.
+#define PB200_CATCH \
+    catch (const std::bad_alloc&) { t_cuda_error = "host allocation failed"; return PB200_ERR_NOMEM; } \
+    catch (const std::exception& ex_) { t_cuda_error = std::string("internal: ") + ex_.what(); return PB200_ERR_UNSUPPORTED; } \
+    catch (...) { t_cuda_error = "internal: unknown exception"; return PB200_ERR_UNSUPPORTED; }
+
+// Entry points run on the key's device and put the caller's current device back when they return.
+struct DevGuard {
+    int prev = -1; bool changed = false;
+    cudaError_t set(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev == dev) return cudaSuccess;
+        cudaError_t e = cudaSetDevice(dev);
+        changed = e == cudaSuccess;
+        return e;
+    }
+    ~DevGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
+};
+#define USE_DEVICE(k) DevGuard dev_guard_; CU(dev_guard_.set((k)->device))
 
 struct DevBuf {  // grow-only device buffer
     void* p = nullptr; size_t cap = 0;
@@ -52,6 +74,16 @@ struct pb200_key {
     std::map<uint32_t, CellCtx> cells;
     DevBuf cin_a, cin_b, cin_q, cin_r;
     int sms = 148;
+    std::vector<pb200_key*> group;          // pb200_tally_multi: the peer group this key is connected to (single process)
+    // witness delivery pipeline (pb200_encrypt_witness_batch): created on first use
+    struct Pipe {
+        static const int NS = 4;             // pinned staging slots
+        cudaStream_t copy = nullptr;
+        cudaEvent_t kern_done[2] = {}, buf_free[2] = {}, slot_done[NS] = {};
+        void* pinned[NS] = {}; size_t slot_bytes = 0;
+        DevBuf rec[2], cbuf[2], offs[2], m_in[2], r_in[2];
+        bool ready = false;
+    } pipe;
 };
 
 static bool use_fast(const pb200_key* k) { return k->fast && k->engine != 1; }
@@ -63,12 +95,14 @@ const char* pb200_strerror(int s) {
         case PB200_OK: return "ok";
         case PB200_ERR_INVALID_ARG: return "invalid argument";
         case PB200_ERR_ZERO_MODULUS: return "modulus n is zero (num-bigint would panic)";
-        case PB200_ERR_EVEN_MODULUS: return "modulus n is even (GPU path requires odd n)";
+        case PB200_ERR_EVEN_MODULUS: return "modulus n is even (reserved; even n is accepted)";
         case PB200_ERR_RANGE: return "input does not fit its declared bit width (range check fails)";
         case PB200_ERR_UNSUPPORTED: return "key size not supported by any compiled engine";
         case PB200_ERR_CUDA: return "CUDA failure";
         case PB200_ERR_NOMEM: return "out of memory";
         case PB200_ERR_SINK: return "witness sink aborted";
+        case PB200_ERR_PEER: return "a peer GPU's tally partial did not arrive (every rank of the group must make the same call)";
+        case PB200_ERR_CONSTRAINT: return "(q, rem) do not satisfy a*b = q*n^2 + rem (the chip's equality constraint fails)";
         default: return "unknown status";
     }
 }
@@ -87,7 +121,7 @@ static bool fits(const uint64_t* v, uint32_t words, uint32_t bits) {
 }
 
 int pb200_key_create(int device, uint32_t n_bits, uint32_t limb_bits, const uint64_t* n_le, const uint64_t* g_le,
-                     pb200_key** out) {
+                     pb200_key** out) try {
     if (!out) return PB200_ERR_INVALID_ARG;
     *out = nullptr;
     if (!n_le || !g_le || n_bits == 0 || limb_bits == 0 || limb_bits > 128) return PB200_ERR_INVALID_ARG;
@@ -97,12 +131,14 @@ int pb200_key_create(int device, uint32_t n_bits, uint32_t limb_bits, const uint
     if (!fits(n_le, win, n_bits) || !fits(g_le, win, n_bits)) return PB200_ERR_RANGE;
     BigInt n = BigInt::from_u64_le(n_le, win), g = BigInt::from_u64_le(g_le, win);
     if (n.is_zero()) return PB200_ERR_ZERO_MODULUS;
-    if (!n.is_odd()) return PB200_ERR_EVEN_MODULUS;
+    // even n is accepted: the reference's own tests draw n = rng.gen_biguint(bits) (src/paillier.rs:173,251) and nothing in the
+    // Barrett engines needs an odd modulus (PB200_ERR_EVEN_MODULUS stays in the enum for ABI stability, never returned)
     int ndev = pb200_device_count();
     if (device < 0 || device >= ndev) { t_cuda_error = "no such CUDA device"; return PB200_ERR_CUDA; }
-    CU(cudaSetDevice(device));
+    DevGuard dev_guard_; CU(dev_guard_.set(device));
     pb200_key* k = new (std::nothrow) pb200_key();
     if (!k) return PB200_ERR_NOMEM;
+    struct KeyOwner { pb200_key* k; ~KeyOwner() { if (k) pb200_key_destroy(k); } } owner{k};   // released on success
     k->device = device; k->n_bits = n_bits; k->limb_bits = limb_bits; k->words_in = win; k->words_out = wout;
     k->n = n; k->g = g; k->n2 = BigInt::mul(n, n);
     SimpleConsts* h = new SimpleConsts();
@@ -120,19 +156,20 @@ int pb200_key_create(int device, uint32_t n_bits, uint32_t limb_bits, const uint
     if (e == cudaSuccess) e = cudaMemsetAsync(k->d_flags, 0, sizeof(int), k->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(k->stream);
     delete h;
-    if (e != cudaSuccess) { int rc = cuda_fail(e, "pb200_key_create"); pb200_key_destroy(k); return rc; }
+    if (e != cudaSuccess) return cuda_fail(e, "pb200_key_create");
     cudaError_t fe = cudaSuccess;
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) k->sms = prop.multiProcessorCount; }
     k->fast = block28_create(n, g, n_bits, device, k->stream, &k->fast_why, &fe);
-    if (fe != cudaSuccess) { int rc = cuda_fail(fe, "block28_create"); pb200_key_destroy(k); return rc; }
+    if (fe != cudaSuccess) return cuda_fail(fe, "block28_create");
     k->engine_name = k->fast ? block28_name(k->fast) : "simple64";
+    owner.k = nullptr;
     *out = k;
     return PB200_OK;
-}
+} PB200_CATCH
 
 void pb200_key_destroy(pb200_key* k) {
     if (!k) return;
-    cudaSetDevice(k->device);
+    DevGuard dev_guard_; dev_guard_.set(k->device);
     if (k->stream) cudaStreamSynchronize(k->stream);
     if (k->fast) block28_destroy(k->fast);
     if (k->d_simple) cudaFree(k->d_simple);
@@ -140,6 +177,18 @@ void pb200_key_destroy(pb200_key* k) {
     if (k->d_flags) cudaFree(k->d_flags);
     k->in_a.release(); k->in_b.release(); k->out_a.release(); k->out_b.release(); k->scratch.release(); k->offs.release();
     k->cin_a.release(); k->cin_b.release(); k->cin_q.release(); k->cin_r.release();
+    if (k->pipe.ready) {
+        if (k->pipe.copy) { cudaStreamSynchronize(k->pipe.copy); cudaStreamDestroy(k->pipe.copy); }
+        for (int i = 0; i < 2; i++) {
+            if (k->pipe.kern_done[i]) cudaEventDestroy(k->pipe.kern_done[i]);
+            if (k->pipe.buf_free[i]) cudaEventDestroy(k->pipe.buf_free[i]);
+            k->pipe.rec[i].release(); k->pipe.cbuf[i].release(); k->pipe.offs[i].release(); k->pipe.m_in[i].release(); k->pipe.r_in[i].release();
+        }
+        for (int i = 0; i < pb200_key::Pipe::NS; i++) {
+            if (k->pipe.slot_done[i]) cudaEventDestroy(k->pipe.slot_done[i]);
+            if (k->pipe.pinned[i]) cudaFreeHost(k->pipe.pinned[i]);
+        }
+    }
     for (auto& kv : k->cells) { if (kv.second.d_consts) cudaFree(kv.second.d_consts); if (kv.second.d_inc) cudaFree(kv.second.d_inc); if (kv.second.d_mtab) cudaFree(kv.second.d_mtab); }
     if (k->stream) cudaStreamDestroy(k->stream);
     delete k;
@@ -148,46 +197,67 @@ uint32_t pb200_key_n_bits(const pb200_key* k) { return k ? k->n_bits : 0; }
 uint32_t pb200_key_words_in(const pb200_key* k) { return k ? k->words_in : 0; }
 uint32_t pb200_key_words_out(const pb200_key* k) { return k ? k->words_out : 0; }
 int pb200_key_device(const pb200_key* k) { return k ? k->device : -1; }
-int pb200_key_n2(const pb200_key* k, uint64_t* out) {
+int pb200_key_n2(const pb200_key* k, uint64_t* out) try {
     if (!k || !out) return PB200_ERR_INVALID_ARG;
     k->n2.to_u64_le(out, k->words_out);
     return PB200_OK;
-}
+} PB200_CATCH
 const char* pb200_key_engine(const pb200_key* k) {
     if (!k) return "";
     return use_fast(k) ? k->engine_name.c_str() : "simple64";
 }
-int pb200_key_set_engine(pb200_key* k, int engine) {
+int pb200_key_set_engine(pb200_key* k, int engine) try {
     if (!k || engine < 0 || engine > 3) return PB200_ERR_INVALID_ARG;
     if (engine >= 2 && !k->fast) return PB200_ERR_UNSUPPORTED;
     k->engine = engine;
     if (k->fast) { block28_set_mma(k->fast, engine != 2); k->engine_name = block28_name(k->fast); }
     return PB200_OK;
-}
+} PB200_CATCH
 void* pb200_key_stream(const pb200_key* k) { return k ? (void*)k->stream : nullptr; }
-int pb200_key_chain_counts(const pb200_key* k, uint64_t* n_sqr, uint64_t* n_mul) {
+int pb200_key_chain_counts(const pb200_key* k, uint64_t* n_sqr, uint64_t* n_mul) try {
     if (!k || !n_sqr || !n_mul) return PB200_ERR_INVALID_ARG;
     if (use_fast(k)) { block28_chain_counts(k->fast, n_sqr, n_mul); return PB200_OK; }
     // simple64 runs the reference's LSB-first chain: bits(n) squarings; popcount(n) + ~popcount(m) + 1 multiplications
     uint64_t pn = 0; for (size_t i = 0; i < k->n.w.size(); i++) pn += (uint64_t)__builtin_popcount(k->n.w[i]);
     *n_sqr = k->n.bits(); *n_mul = pn + k->n_bits / 2 + 1;
     return PB200_OK;
-}
-int pb200_key_sync(pb200_key* k) {
+} PB200_CATCH
+int pb200_key_sync(pb200_key* k) try {
     if (!k) return PB200_ERR_INVALID_ARG;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
     CU(cudaStreamSynchronize(k->stream));
     return PB200_OK;
-}
+} PB200_CATCH
 
-// reads and clears the device-side range flag
+// The per-key device flag word: bit 0 (PB200_FLAG_RANGE) a quotient / input outside its declared width, bit 1
+// (PB200_FLAG_CONSTRAINT) a (q, rem) that does not satisfy a*b = q*n^2 + rem.  Host entry points clear it when they start
+// (clear_flags) and turn it into a status when they end (take_flags); _dev callers read it with pb200_key_take_flags.
+static int clear_flags(pb200_key* k) {
+    CU(cudaMemsetAsync(k->d_flags, 0, sizeof(int), k->stream));
+    return PB200_OK;
+}
+static int read_flags(pb200_key* k, int* f) {
+    *f = 0;
+    CU(cudaMemcpyAsync(f, k->d_flags, sizeof(int), cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    if (*f) CU(cudaMemsetAsync(k->d_flags, 0, sizeof(int), k->stream));
+    return PB200_OK;
+}
 static int take_flags(pb200_key* k) {
     int f = 0;
-    CU(cudaMemcpyAsync(&f, k->d_flags, sizeof(int), cudaMemcpyDeviceToHost, k->stream));
-    CU(cudaStreamSynchronize(k->stream));
-    if (f) { CU(cudaMemsetAsync(k->d_flags, 0, sizeof(int), k->stream)); return PB200_ERR_RANGE; }
+    int rc = read_flags(k, &f); if (rc) return rc;
+    if (f & PB200_FLAG_CONSTRAINT) return PB200_ERR_CONSTRAINT;
+    if (f & ~PB200_FLAG_CONSTRAINT) return PB200_ERR_RANGE;
     return PB200_OK;
 }
+int pb200_key_take_flags(pb200_key* k, uint32_t* flags_out) try {
+    if (!k || !flags_out) return PB200_ERR_INVALID_ARG;
+    USE_DEVICE(k);
+    int f = 0;
+    int rc = read_flags(k, &f); if (rc) return rc;
+    *flags_out = (uint32_t)f;
+    return PB200_OK;
+} PB200_CATCH
 
 // per-key g-chain records: by the witness engine when it serves this key (it builds its table in the same pass), else by
 // simple64 (one thread, the reference's chain)
@@ -219,27 +289,28 @@ static int run_witness(pb200_key* k, const u64* d_m, const u64* d_r, size_t coun
 }
 
 // ---- encrypt --------------------------------------------------------------------------------
-int pb200_encrypt_batch_dev(pb200_key* k, const uint64_t* d_m, const uint64_t* d_r, size_t count, uint64_t* d_c) {
+int pb200_encrypt_batch_dev(pb200_key* k, const uint64_t* d_m, const uint64_t* d_r, size_t count, uint64_t* d_c) try {
     if (!k || (count && (!d_m || !d_r || !d_c))) return PB200_ERR_INVALID_ARG;
     if (!count) return PB200_OK;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
     if (use_fast(k)) { CU(block28_encrypt(k->fast, (const u64*)d_m, (const u64*)d_r, count, (u64*)d_c, k->stream)); return PB200_OK; }
     int rc = ensure_gchain(k); if (rc) return rc;
     CU(simple_encrypt(k->d_simple, k->d_gchain, (const u64*)d_m, (const u64*)d_r, count, (u64*)d_c, nullptr, nullptr,
                       nullptr, k->d_flags, k->stream));
     return PB200_OK;
-}
+} PB200_CATCH
 
 static int check_inputs(const pb200_key* k, const uint64_t* v, size_t count) {
     for (size_t u = 0; u < count; u++) if (!fits(v + u * k->words_in, k->words_in, k->n_bits)) return PB200_ERR_RANGE;
     return PB200_OK;
 }
 
-int pb200_encrypt_batch(pb200_key* k, const uint64_t* m, const uint64_t* r, size_t count, uint64_t* c_out) {
+int pb200_encrypt_batch(pb200_key* k, const uint64_t* m, const uint64_t* r, size_t count, uint64_t* c_out) try {
     if (!k || (count && (!m || !r || !c_out))) return PB200_ERR_INVALID_ARG;
     if (!count) return PB200_OK;
     if (k->n_bits % 64) { int rc = check_inputs(k, m, count); if (rc) return rc; rc = check_inputs(k, r, count); if (rc) return rc; }
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
+    { int rc0_ = clear_flags(k); if (rc0_) return rc0_; }
     size_t bin = count * k->words_in * sizeof(u64), bout = count * k->words_out * sizeof(u64);
     CU(k->in_a.reserve(bin)); CU(k->in_b.reserve(bin)); CU(k->out_a.reserve(bout));
     CU(cudaMemcpyAsync(k->in_a.p, m, bin, cudaMemcpyHostToDevice, k->stream));
@@ -249,25 +320,26 @@ int pb200_encrypt_batch(pb200_key* k, const uint64_t* m, const uint64_t* r, size
     CU(cudaMemcpyAsync(c_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
     CU(cudaStreamSynchronize(k->stream));
     return use_fast(k) ? PB200_OK : take_flags(k);
-}
+} PB200_CATCH
 
 // ---- add ------------------------------------------------------------------------------------
 int pb200_add_batch_dev(pb200_key* k, const uint64_t* d_c1, const uint64_t* d_c2, uint32_t c_words, size_t count,
-                        uint64_t* d_out, uint64_t* d_q) {
+                        uint64_t* d_out, uint64_t* d_q) try {
     if (!k || (count && (!d_c1 || !d_c2 || !d_out)) || c_words == 0 || c_words > k->words_out) return PB200_ERR_INVALID_ARG;
     if (!count) return PB200_OK;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
     bool fast = false;
     int rc = witness_engine(k, &fast); if (rc) return rc;
     if (fast) CU(block28_add(k->fast, (const u64*)d_c1, (const u64*)d_c2, (int)c_words, count, (u64*)d_out, (u64*)d_q, k->d_flags, k->stream));
     else CU(simple_add(k->d_simple, (const u64*)d_c1, (const u64*)d_c2, (int)c_words, count, (u64*)d_out, (u64*)d_q, k->d_flags, k->stream));
     return PB200_OK;
-}
+} PB200_CATCH
 int pb200_add_batch(pb200_key* k, const uint64_t* c1, const uint64_t* c2, uint32_t c_words, size_t count, uint64_t* out,
-                    uint64_t* q_out) {
+                    uint64_t* q_out) try {
     if (!k || (count && (!c1 || !c2 || !out)) || c_words == 0 || c_words > k->words_out) return PB200_ERR_INVALID_ARG;
     if (!count) return PB200_OK;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
+    { int rc0_ = clear_flags(k); if (rc0_) return rc0_; }
     size_t bin = count * c_words * sizeof(u64), bout = count * k->words_out * sizeof(u64);
     CU(k->in_a.reserve(bin)); CU(k->in_b.reserve(bin)); CU(k->out_a.reserve(bout));
     if (q_out) CU(k->out_b.reserve(bout));
@@ -280,37 +352,170 @@ int pb200_add_batch(pb200_key* k, const uint64_t* c1, const uint64_t* c2, uint32
     if (q_out) CU(cudaMemcpyAsync(q_out, k->out_b.p, bout, cudaMemcpyDeviceToHost, k->stream));
     CU(cudaStreamSynchronize(k->stream));
     return take_flags(k);
-}
+} PB200_CATCH
 
 // ---- tally ----------------------------------------------------------------------------------
-int pb200_tally_dev(pb200_key* k, const uint64_t* d_c, size_t count, uint64_t* d_out) {
-    if (!k || !d_out || (count && !d_c)) return PB200_ERR_INVALID_ARG;
-    CU(cudaSetDevice(k->device));
-    if (use_fast(k) && count) { CU(block28_tally(k->fast, (const u64*)d_c, count, (u64*)d_out, k->stream)); return PB200_OK; }
+static int tally_dev_impl(pb200_key* k, const uint64_t* d_c, size_t count, uint64_t* d_out, bool collective) {
+    if (use_fast(k)) {
+        if (collective) CU(block28_tally_peer(k->fast, (const u64*)d_c, count, (u64*)d_out, k->stream));
+        else CU(block28_tally(k->fast, (const u64*)d_c, count, (u64*)d_out, k->stream));
+        return PB200_OK;
+    }
     CU(k->scratch.reserve(simple_tally_scratch_words((int)k->words_out) * sizeof(u64)));
     CU(simple_tally(k->d_simple, (int)k->words_out, (const u64*)d_c, count, (u64*)d_out, (u64*)k->scratch.p, k->d_flags, k->stream));
     return PB200_OK;
 }
-int pb200_tally(pb200_key* k, const uint64_t* c, size_t count, uint64_t* out) {
+int pb200_tally_dev(pb200_key* k, const uint64_t* d_c, size_t count, uint64_t* d_out) try {
+    if (!k || !d_out || (count && !d_c)) return PB200_ERR_INVALID_ARG;
+    USE_DEVICE(k);
+    return tally_dev_impl(k, d_c, count, d_out, false);
+} PB200_CATCH
+int pb200_tally(pb200_key* k, const uint64_t* c, size_t count, uint64_t* out) try {
     if (!k || !out || (count && !c)) return PB200_ERR_INVALID_ARG;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
+    { int rc0_ = clear_flags(k); if (rc0_) return rc0_; }
     size_t bin = count * k->words_out * sizeof(u64), bout = k->words_out * sizeof(u64);
     CU(k->in_a.reserve(bin ? bin : 8)); CU(k->out_b.reserve(bout));
     if (bin) CU(cudaMemcpyAsync(k->in_a.p, c, bin, cudaMemcpyHostToDevice, k->stream));
-    int rc = pb200_tally_dev(k, (const uint64_t*)k->in_a.p, count, (uint64_t*)k->out_b.p);
+    int rc = tally_dev_impl(k, (const uint64_t*)k->in_a.p, count, (uint64_t*)k->out_b.p, false);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out, k->out_b.p, bout, cudaMemcpyDeviceToHost, k->stream));
     CU(cudaStreamSynchronize(k->stream));
     return take_flags(k);
-}
-int pb200_tally_combine(pb200_key* k, const uint64_t* partials, size_t n_partials, uint64_t* out) {
-    // the combine of G <= 8 shard partials is the same fold; use the exact simple engine for it
-    if (!k || !out || (n_partials && !partials)) return PB200_ERR_INVALID_ARG;
-    int saved = k->engine; k->engine = 1;
-    int rc = pb200_tally(k, partials, n_partials, out);
-    k->engine = saved;
-    return rc;
-}
+} PB200_CATCH
+int pb200_tally_combine(pb200_key* k, const uint64_t* partials, size_t n_partials, uint64_t* out) try {
+    // the combine of per-shard partials is the same fold, on the key's own engine
+    return pb200_tally(k, partials, n_partials, out);
+} PB200_CATCH
+
+// ---- multi-GPU tally ------------------------------------------------------------------------------------
+static int peer_status(int flags) { return (flags & (int)PB200_FLAG_PEER_TIMEOUT) ? PB200_ERR_PEER : PB200_OK; }
+
+int pb200_tally_peer_export(pb200_key* k, pb200_ipc_handle* out) try {
+    if (!k || !out) return PB200_ERR_INVALID_ARG;
+    if (!k->fast) return PB200_ERR_UNSUPPORTED;
+    USE_DEVICE(k);
+    u64* mail = nullptr;
+    CU(block28_mailbox(k->fast, &mail, k->stream));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, mail));
+    static_assert(sizeof(h) == sizeof(out->bytes), "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out->bytes, &h, sizeof(h));
+    return PB200_OK;
+} PB200_CATCH
+
+int pb200_tally_peer_connect(pb200_key* k, int rank, int world, const pb200_ipc_handle* handles) try {
+    if (!k || world < 1 || rank < 0 || rank >= world || (world > 1 && !handles)) return PB200_ERR_INVALID_ARG;
+    if (!k->fast || world > block28_max_world()) return PB200_ERR_UNSUPPORTED;
+    USE_DEVICE(k);
+    CU(cudaStreamSynchronize(k->stream));
+    u64* mails[16] = {}; void* opened[16] = {};
+    CU(block28_mailbox(k->fast, &mails[rank], k->stream));
+    for (int i = 0; i < world; i++) {
+        if (i == rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles[i].bytes, sizeof(h));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int j = 0; j < i; j++) if (opened[j]) cudaIpcCloseMemHandle(opened[j]);
+            return cuda_fail(e, "cudaIpcOpenMemHandle");
+        }
+        mails[i] = (u64*)p; opened[i] = p;
+    }
+    CU(block28_tally_peer_connect(k->fast, rank, world, mails, opened, k->d_flags));
+    k->group.clear();
+    return PB200_OK;
+} PB200_CATCH
+
+int pb200_tally_peer_dev(pb200_key* k, const uint64_t* d_c, size_t count, uint64_t* d_out) try {
+    if (!k || !d_out || (count && !d_c)) return PB200_ERR_INVALID_ARG;
+    if (!use_fast(k) || block28_peer_world(k->fast) < 1) return PB200_ERR_UNSUPPORTED;
+    USE_DEVICE(k);
+    return tally_dev_impl(k, d_c, count, d_out, true);
+} PB200_CATCH
+
+int pb200_tally_multi(pb200_key* const* keys, int n_gpus, const uint64_t* const* d_c, const size_t* counts, uint64_t* out) try {
+    if (!keys || n_gpus < 1 || !d_c || !counts || !out) return PB200_ERR_INVALID_ARG;
+    for (int i = 0; i < n_gpus; i++) {
+        if (!keys[i] || (counts[i] && !d_c[i])) return PB200_ERR_INVALID_ARG;
+        if (keys[i]->n_bits != keys[0]->n_bits || !(keys[i]->n == keys[0]->n)) return PB200_ERR_INVALID_ARG;
+        for (int j = 0; j < i; j++) if (keys[j] == keys[i] || keys[j]->device == keys[i]->device) return PB200_ERR_INVALID_ARG;
+    }
+    DevGuard dev_guard_;
+    CU(dev_guard_.set(keys[0]->device));
+    const size_t bout = keys[0]->words_out * sizeof(u64);
+    bool peer_ok = n_gpus <= block28_max_world();
+    for (int i = 0; i < n_gpus; i++) peer_ok = peer_ok && use_fast(keys[i]);
+    if (peer_ok && n_gpus > 1) {
+        std::vector<pb200_key*> want(keys, keys + n_gpus);
+        bool connected = true;
+        for (int i = 0; i < n_gpus; i++) connected = connected && keys[i]->group == want;
+        if (!connected) {
+            for (int i = 0; i < n_gpus && peer_ok; i++)
+                for (int j = 0; j < n_gpus && peer_ok; j++) {
+                    if (i == j) continue;
+                    int can = 0;
+                    CU(cudaDeviceCanAccessPeer(&can, keys[i]->device, keys[j]->device));
+                    if (!can) { peer_ok = false; break; }
+                    CU(cudaSetDevice(keys[i]->device));
+                    cudaError_t e = cudaDeviceEnablePeerAccess(keys[j]->device, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+                }
+            if (peer_ok) {
+                u64* mails[16] = {};
+                for (int i = 0; i < n_gpus; i++) {
+                    CU(cudaSetDevice(keys[i]->device));
+                    CU(cudaStreamSynchronize(keys[i]->stream));
+                    CU(block28_mailbox(keys[i]->fast, &mails[i], keys[i]->stream));
+                }
+                for (int i = 0; i < n_gpus; i++) {
+                    CU(cudaSetDevice(keys[i]->device));
+                    CU(block28_tally_peer_connect(keys[i]->fast, i, n_gpus, mails, nullptr, keys[i]->d_flags));
+                    keys[i]->group = want;
+                }
+            }
+        }
+    }
+    if (n_gpus == 1 || peer_ok) {
+        // one launch per GPU; the partials cross NVLink inside the kernels and every GPU ends with the full product
+        for (int i = 0; i < n_gpus; i++) {
+            CU(cudaSetDevice(keys[i]->device));
+            int rc = clear_flags(keys[i]); if (rc) return rc;
+            CU(keys[i]->out_b.reserve(bout));
+            rc = tally_dev_impl(keys[i], d_c[i], counts[i], (uint64_t*)keys[i]->out_b.p, n_gpus > 1);
+            if (rc) return rc;
+        }
+        CU(cudaSetDevice(keys[0]->device));
+        CU(cudaMemcpyAsync(out, keys[0]->out_b.p, bout, cudaMemcpyDeviceToHost, keys[0]->stream));
+        int status = PB200_OK;
+        for (int i = 0; i < n_gpus; i++) {
+            CU(cudaSetDevice(keys[i]->device));
+            int f = 0;
+            int rc = read_flags(keys[i], &f); if (rc) return rc;
+            if (f & (int)PB200_FLAG_PEER_TIMEOUT) status = PB200_ERR_PEER;
+            else if (f && status == PB200_OK) status = PB200_ERR_RANGE;
+        }
+        return status;
+    }
+    // no peer access between these devices (or an engine without the fused kernel): per-GPU partials, gathered through the host,
+    // combined on keys[0] — the host only moves bytes, every multiplication still runs on a GPU
+    std::vector<uint64_t> partials((size_t)n_gpus * keys[0]->words_out);
+    for (int i = 0; i < n_gpus; i++) {
+        CU(cudaSetDevice(keys[i]->device));
+        int rc = clear_flags(keys[i]); if (rc) return rc;
+        CU(keys[i]->out_b.reserve(bout));
+        rc = tally_dev_impl(keys[i], d_c[i], counts[i], (uint64_t*)keys[i]->out_b.p, false);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(partials.data() + (size_t)i * keys[0]->words_out, keys[i]->out_b.p, bout, cudaMemcpyDeviceToHost, keys[i]->stream));
+    }
+    for (int i = 0; i < n_gpus; i++) {
+        CU(cudaSetDevice(keys[i]->device));
+        int rc = take_flags(keys[i]); if (rc) return rc;
+    }
+    return pb200_tally(keys[0], partials.data(), (size_t)n_gpus, out);
+} PB200_CATCH
 
 // ---- witness --------------------------------------------------------------------------------
 static uint64_t popcount_words(const uint64_t* v, uint32_t words) {
@@ -322,73 +527,185 @@ uint64_t pb200_witness_records_for(const pb200_key* k, const uint64_t* m) {
     return popcount_words(m, k->words_in) + k->n.bits() + pn + 1;
 }
 
-int pb200_key_g_chain(pb200_key* k, uint64_t* records_out) {
+int pb200_key_g_chain(pb200_key* k, uint64_t* records_out) try {
     if (!k || !records_out) return PB200_ERR_INVALID_ARG;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
+    { int rc0_ = clear_flags(k); if (rc0_) return rc0_; }
     int rc = ensure_gchain(k); if (rc) return rc;
     CU(cudaMemcpyAsync(records_out, k->d_gchain, (size_t)k->n_bits * 2 * k->words_out * sizeof(u64), cudaMemcpyDeviceToHost, k->stream));
     CU(cudaStreamSynchronize(k->stream));
     return take_flags(k);
+} PB200_CATCH
+
+// Delivery pipeline of the witness stream.  The stream is ~4 MB per unit at |n| = 2048, so it is produced in device CHUNKS
+// (two record buffers: the kernel of chunk c+1 runs while chunk c drains) and drained in PIECES through a ring of pinned staging
+// slots on a second stream (piece i+1..i+3 are in flight on the copy engine while the caller's sink consumes piece i).  The
+// sink always reads pinned host memory and is called on the calling thread.
+static size_t env_bytes(const char* name, size_t dflt) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const double v = atof(e);
+    return v >= 1.0 ? (size_t)v : dflt;
 }
 
-int pb200_encrypt_witness_batch(pb200_key* k, const uint64_t* m, const uint64_t* r, size_t count, uint64_t* c_out,
-                                size_t max_chunk_units, pb200_witness_sink_fn sink, void* user) {
-    if (!k || !sink || (count && (!m || !r))) return PB200_ERR_INVALID_ARG;
-    if (!count) return PB200_OK;
-    int rc = check_inputs(k, m, count); if (rc) return rc;
-    rc = check_inputs(k, r, count); if (rc) return rc;
-    CU(cudaSetDevice(k->device));
-    const size_t rec_words = 2 * (size_t)k->words_out;
-    uint64_t fixed = pb200_witness_records_for(k, m) - popcount_words(m, k->words_in);  // bits(n)+popcount(n)+1
-    size_t max_unit_records = (size_t)fixed + k->n_bits;
-    // bytes of staged records per chunk: a chunk costs one kernel launch whose latency is that of ONE unit's chain (147 ms at
-    // |n| = 2048) however few units it holds, so chunks are made as large as a 2 GiB staging buffer allows when memory is plentiful
-    size_t budget = (size_t)256 << 20;
-    { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr > ((size_t)16 << 30)) budget = (size_t)2 << 30; }
-    size_t auto_units = budget / (max_unit_records * rec_words * sizeof(u64));
-    if (auto_units < 1) auto_units = 1;
-    size_t chunk_units = max_chunk_units ? max_chunk_units : auto_units;
-    std::vector<uint64_t> offsets, host_records;
-    std::vector<uint32_t> gcounts;
-    for (size_t first = 0; first < count; first += chunk_units) {
-        size_t nu = count - first < chunk_units ? count - first : chunk_units;
-        offsets.assign(nu + 1, 0); gcounts.assign(nu, 0);
-        for (size_t u = 0; u < nu; u++) {
-            uint64_t pc = popcount_words(m + (first + u) * k->words_in, k->words_in);
-            gcounts[u] = (uint32_t)pc;
-            offsets[u + 1] = offsets[u] + pc + fixed;
+static int pipe_init(pb200_key* k, size_t slot_bytes) {
+    pb200_key::Pipe& P = k->pipe;
+    if (!P.ready) {
+        CU(cudaStreamCreateWithFlags(&P.copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&P.kern_done[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&P.buf_free[i], cudaEventDisableTiming));
         }
-        size_t total_records = (size_t)offsets[nu];
-        size_t bin = nu * k->words_in * sizeof(u64), bout = nu * k->words_out * sizeof(u64);
-        CU(k->in_a.reserve(bin)); CU(k->in_b.reserve(bin)); CU(k->out_a.reserve(bout));
-        CU(k->offs.reserve((nu + 1) * sizeof(u64)));
-        CU(k->scratch.reserve(total_records * rec_words * sizeof(u64)));
-        CU(cudaMemcpyAsync(k->in_a.p, m + first * k->words_in, bin, cudaMemcpyHostToDevice, k->stream));
-        CU(cudaMemcpyAsync(k->in_b.p, r + first * k->words_in, bin, cudaMemcpyHostToDevice, k->stream));
-        CU(cudaMemcpyAsync(k->offs.p, offsets.data(), (nu + 1) * sizeof(u64), cudaMemcpyHostToDevice, k->stream));
-        rc = run_witness(k, (const u64*)k->in_a.p, (const u64*)k->in_b.p, nu, (u64*)k->out_a.p, (u64*)k->scratch.p,
-                         (const u64*)k->offs.p, nullptr);
-        if (rc) return rc;
-        host_records.resize(total_records * rec_words);
-        CU(cudaMemcpyAsync(host_records.data(), k->scratch.p, total_records * rec_words * sizeof(u64), cudaMemcpyDeviceToHost, k->stream));
-        if (c_out) CU(cudaMemcpyAsync(c_out + first * k->words_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
-        CU(cudaStreamSynchronize(k->stream));
-        rc = take_flags(k); if (rc) return rc;
-        pb200_witness_chunk ch;
-        ch.first_unit = first; ch.n_units = nu; ch.words_out = k->words_out;
-        ch.offsets = offsets.data(); ch.records = host_records.data(); ch.g_mul_counts = gcounts.data();
-        if (sink(user, &ch) != 0) return PB200_ERR_SINK;
+        for (int i = 0; i < pb200_key::Pipe::NS; i++) CU(cudaEventCreateWithFlags(&P.slot_done[i], cudaEventDisableTiming));
+        P.ready = true;
+    }
+    if (slot_bytes > P.slot_bytes) {
+        for (int i = 0; i < pb200_key::Pipe::NS; i++) {
+            if (P.pinned[i]) { cudaFreeHost(P.pinned[i]); P.pinned[i] = nullptr; }
+        }
+        P.slot_bytes = 0;
+        for (int i = 0; i < pb200_key::Pipe::NS; i++) CU(cudaHostAlloc(&P.pinned[i], slot_bytes, cudaHostAllocDefault));
+        P.slot_bytes = slot_bytes;
     }
     return PB200_OK;
 }
 
+int pb200_encrypt_witness_batch(pb200_key* k, const uint64_t* m, const uint64_t* r, size_t count, uint64_t* c_out,
+                                size_t max_chunk_units, pb200_witness_sink_fn sink, void* user) try {
+    if (!k || !sink || (count && (!m || !r))) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    int rc = check_inputs(k, m, count); if (rc) return rc;
+    rc = check_inputs(k, r, count); if (rc) return rc;
+    USE_DEVICE(k);
+    { int rc0_ = clear_flags(k); if (rc0_) return rc0_; }
+    const size_t wo = k->words_out, wi = k->words_in, rec_bytes = 2 * wo * sizeof(u64);
+    const uint64_t fixed = pb200_witness_records_for(k, m) - popcount_words(m, k->words_in);  // bits(n) + popcount(n) + 1
+    // record offsets of every unit (in records) and the g-chain multiplication counts
+    std::vector<uint64_t> offsets(count + 1, 0);
+    std::vector<uint32_t> gcounts(count);
+    uint64_t max_unit = 0;
+    for (size_t u = 0; u < count; u++) {
+        const uint64_t pc = popcount_words(m + u * wi, k->words_in);
+        gcounts[u] = (uint32_t)pc;
+        offsets[u + 1] = offsets[u] + pc + fixed;
+        if (pc + fixed > max_unit) max_unit = pc + fixed;
+    }
+    // sizes: a pinned slot holds at least one unit; a device chunk is bounded by the free memory (two record buffers)
+    size_t slot_bytes = env_bytes("PB200_WITNESS_SLOT_BYTES", (size_t)256 << 20);
+    if (slot_bytes < max_unit * rec_bytes) slot_bytes = (size_t)max_unit * rec_bytes;
+    if (slot_bytes > offsets[count] * rec_bytes) slot_bytes = (size_t)offsets[count] * rec_bytes;
+    // a chunk's kernel takes the latency of ONE unit's chain whatever its size (about 0.15 s at |n| = 2048), and the first piece
+    // can leave only when the first chunk's kernel has ended: chunks of 8 GiB keep that start-up short while one chunk's drain
+    // (8 GiB over PCIe, ~0.15 s) still covers the next chunk's kernel
+    size_t chunk_bytes = (size_t)8 << 30;
+    { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) { size_t third = fr / 3; if (third < chunk_bytes) chunk_bytes = third; } }
+    chunk_bytes = env_bytes("PB200_WITNESS_CHUNK_BYTES", chunk_bytes);
+    if (chunk_bytes < max_unit * rec_bytes) chunk_bytes = (size_t)max_unit * rec_bytes;
+    // chunks: [cu0[c], cu0[c+1]) greedy by bytes;  pieces inside a chunk: greedy by slot bytes and max_chunk_units
+    struct Piece { size_t u0, u1; int chunk; bool first, last; };
+    std::vector<size_t> cu0{0};
+    std::vector<Piece> pieces;
+    {
+        size_t u = 0;
+        while (u < count) {
+            size_t e = u + 1;
+            while (e < count && (offsets[e + 1] - offsets[u]) * rec_bytes <= chunk_bytes) e++;
+            const int c = (int)cu0.size() - 1;
+            size_t p0 = u;
+            while (p0 < e) {
+                size_t p1 = p0 + 1;
+                while (p1 < e && (offsets[p1 + 1] - offsets[p0]) * rec_bytes <= slot_bytes && (!max_chunk_units || p1 - p0 < max_chunk_units)) p1++;
+                pieces.push_back(Piece{p0, p1, c, p0 == u, p1 == e});
+                p0 = p1;
+            }
+            cu0.push_back(e);
+            u = e;
+        }
+    }
+    const int nchunks = (int)cu0.size() - 1;
+    rc = pipe_init(k, slot_bytes); if (rc) return rc;
+    pb200_key::Pipe& P = k->pipe;
+    constexpr int NS = pb200_key::Pipe::NS;
+    // inputs and the (absolute) record offsets of ALL units go up once, before the pipeline starts: a pageable host-to-device
+    // copy synchronises its stream first, which inside the loop would stall the thread that feeds the copy engine
+    CU(k->in_a.reserve(count * wi * sizeof(u64))); CU(k->in_b.reserve(count * wi * sizeof(u64))); CU(k->offs.reserve((count + 1) * sizeof(u64)));
+    CU(cudaMemcpyAsync(k->in_a.p, m, count * wi * sizeof(u64), cudaMemcpyHostToDevice, k->stream));
+    CU(cudaMemcpyAsync(k->in_b.p, r, count * wi * sizeof(u64), cudaMemcpyHostToDevice, k->stream));
+    CU(cudaMemcpyAsync(k->offs.p, offsets.data(), (count + 1) * sizeof(u64), cudaMemcpyHostToDevice, k->stream));
+    {   // the two record buffers at their final size (cudaMalloc inside the loop would synchronise the device)
+        size_t need_rec[2] = {0, 0}, need_c[2] = {0, 0};
+        for (int c = 0; c < nchunks; c++) {
+            const size_t recs = (size_t)(offsets[cu0[c + 1]] - offsets[cu0[c]]), nu = cu0[c + 1] - cu0[c];
+            if (recs * rec_bytes > need_rec[c & 1]) need_rec[c & 1] = recs * rec_bytes;
+            if (nu * wo * sizeof(u64) > need_c[c & 1]) need_c[c & 1] = nu * wo * sizeof(u64);
+        }
+        for (int b = 0; b < 2; b++) if (need_rec[b]) { CU(P.rec[b].reserve(need_rec[b])); CU(P.cbuf[b].reserve(need_c[b])); }
+    }
+    // fallible steps of the pipeline; every exit path below drains both streams first (the sink's memory must not be in flight)
+    auto launch_chunk = [&](int c) -> int {
+        const int b = c & 1;
+        const size_t u0 = cu0[c], nu = cu0[c + 1] - u0;
+        if (c >= 2) CU(cudaStreamWaitEvent(k->stream, P.buf_free[b], 0));        // chunk c-2 has left this buffer
+        // the kernels address records as base + offsets[unit] * record words with ABSOLUTE offsets: shift the base
+        u64* rec_base = (u64*)P.rec[b].p - (size_t)offsets[u0] * 2 * wo;
+        int rcw = run_witness(k, (const u64*)k->in_a.p + u0 * wi, (const u64*)k->in_b.p + u0 * wi, nu, (u64*)P.cbuf[b].p, rec_base,
+                              (const u64*)k->offs.p + u0, nullptr);
+        if (rcw) return rcw;
+        CU(cudaEventRecord(P.kern_done[b], k->stream));
+        return PB200_OK;
+    };
+    int next_chunk = 0;
+    auto issue = [&](size_t p) -> int {
+        const Piece& pc = pieces[p];
+        const int b = pc.chunk & 1, slot = (int)(p % NS);
+        const size_t cu = cu0[pc.chunk];
+        if (pc.first) {
+            CU(cudaStreamWaitEvent(P.copy, P.kern_done[b], 0));
+            if (c_out) CU(cudaMemcpyAsync(c_out + cu * wo, P.cbuf[b].p, (cu0[pc.chunk + 1] - cu) * wo * sizeof(u64), cudaMemcpyDeviceToHost, P.copy));
+        }
+        const size_t r0 = (size_t)(offsets[pc.u0] - offsets[cu]), nrec = (size_t)(offsets[pc.u1] - offsets[pc.u0]);
+        CU(cudaMemcpyAsync(P.pinned[slot], (const char*)P.rec[b].p + r0 * rec_bytes, nrec * rec_bytes, cudaMemcpyDeviceToHost, P.copy));
+        CU(cudaEventRecord(P.slot_done[slot], P.copy));
+        if (pc.last) {
+            CU(cudaEventRecord(P.buf_free[b], P.copy));
+            if (next_chunk < nchunks) { int rcl = launch_chunk(next_chunk++); if (rcl) return rcl; }
+        }
+        return PB200_OK;
+    };
+    auto drain = [&]() { cudaStreamSynchronize(k->stream); cudaStreamSynchronize(P.copy); };
+    rc = launch_chunk(next_chunk++);
+    if (!rc && next_chunk < nchunks) rc = launch_chunk(next_chunk++);
+    if (rc) { drain(); return rc; }
+    size_t issued = 0;
+    std::vector<uint64_t> poffs;
+    for (size_t i = 0; i < pieces.size(); i++) {
+        while (issued < pieces.size() && issued < i + NS) {
+            rc = issue(issued++);
+            if (rc) { drain(); return rc; }
+        }
+        cudaError_t e = cudaEventSynchronize(P.slot_done[i % NS]);
+        if (e != cudaSuccess) { drain(); return cuda_fail(e, "witness pipeline"); }
+        const Piece& pc = pieces[i];
+        poffs.resize(pc.u1 - pc.u0 + 1);
+        for (size_t u = pc.u0; u <= pc.u1; u++) poffs[u - pc.u0] = offsets[u] - offsets[pc.u0];
+        pb200_witness_chunk ch;
+        ch.first_unit = pc.u0; ch.n_units = pc.u1 - pc.u0; ch.words_out = k->words_out;
+        ch.offsets = poffs.data(); ch.records = (const uint64_t*)P.pinned[i % NS]; ch.g_mul_counts = gcounts.data() + pc.u0;
+        if (sink(user, &ch) != 0) { drain(); return PB200_ERR_SINK; }
+    }
+    CU(cudaStreamSynchronize(P.copy));
+    CU(cudaStreamSynchronize(k->stream));
+    return take_flags(k);
+} PB200_CATCH
+
 int pb200_encrypt_witness_digest(pb200_key* k, const uint64_t* m, const uint64_t* r, size_t count, uint64_t* c_out,
-                                 uint64_t* digest_out) {
+                                 uint64_t* digest_out) try {
     if (!k || !digest_out || (count && (!m || !r))) return PB200_ERR_INVALID_ARG;
     if (!count) return PB200_OK;
     int rc = check_inputs(k, m, count); if (rc) return rc;
     rc = check_inputs(k, r, count); if (rc) return rc;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
+    { int rc0_ = clear_flags(k); if (rc0_) return rc0_; }
     size_t bin = count * k->words_in * sizeof(u64), bout = count * k->words_out * sizeof(u64);
     CU(k->in_a.reserve(bin)); CU(k->in_b.reserve(bin)); CU(k->out_a.reserve(bout)); CU(k->out_b.reserve(count * sizeof(u64)));
     CU(cudaMemcpyAsync(k->in_a.p, m, bin, cudaMemcpyHostToDevice, k->stream));
@@ -399,15 +716,15 @@ int pb200_encrypt_witness_digest(pb200_key* k, const uint64_t* m, const uint64_t
     if (c_out) CU(cudaMemcpyAsync(c_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
     CU(cudaStreamSynchronize(k->stream));
     return take_flags(k);
-}
+} PB200_CATCH
 
 int pb200_encrypt_witness_digest_dev(pb200_key* k, const uint64_t* d_m, const uint64_t* d_r, size_t count, uint64_t* d_c,
-                                     uint64_t* d_digest) {
+                                     uint64_t* d_digest) try {
     if (!k || !d_digest || (count && (!d_m || !d_r))) return PB200_ERR_INVALID_ARG;
     if (!count) return PB200_OK;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
     return run_witness(k, (const u64*)d_m, (const u64*)d_r, count, (u64*)d_c, nullptr, nullptr, (u64*)d_digest);
-}
+} PB200_CATCH
 const char* pb200_key_witness_engine(pb200_key* k) {
     if (!k) return "";
     return (use_fast(k) && block28_witness_supported(k->fast)) ? "block28w" : "simple64";
@@ -492,9 +809,9 @@ static int cell_ctx(pb200_key* k, uint32_t lookup_bits, pb200_key::CellCtx** out
     return PB200_OK;
 }
 
-int pb200_cells_layout(pb200_key* k, uint32_t lookup_bits, pb200_cell_layout* out) {
+int pb200_cells_layout(pb200_key* k, uint32_t lookup_bits, pb200_cell_layout* out) try {
     if (!k || !out) return PB200_ERR_INVALID_ARG;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
     pb200_key::CellCtx* C = nullptr;
     int rc = cell_ctx(k, lookup_bits, &C); if (rc) return rc;
     out->limbs = (uint32_t)C->Y.L; out->cells_per_limb = (uint32_t)C->Y.cpl; out->carry_bits = (uint32_t)C->Y.carry_bits;
@@ -502,25 +819,26 @@ int pb200_cells_layout(pb200_key* k, uint32_t lookup_bits, pb200_cell_layout* ou
     out->off_rem = (uint32_t)C->Y.off_rem; out->off_ab = (uint32_t)C->Y.off_ab; out->off_qn = (uint32_t)C->Y.off_qn;
     out->off_qn_rem = (uint32_t)C->Y.off_qnp; out->off_eq = (uint32_t)C->Y.off_eq; out->eq_stride = (uint32_t)C->Y.eq_stride;
     return PB200_OK;
-}
+} PB200_CATCH
 
 int pb200_mulmod_cells_batch_dev(pb200_key* k, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_q, const uint64_t* d_rem,
-                                 size_t count, uint32_t lookup_bits, int montgomery, uint64_t* d_cells) {
+                                 size_t count, uint32_t lookup_bits, int montgomery, uint64_t* d_cells) try {
     if (!k || (count && (!d_a || !d_b || !d_q || !d_rem || !d_cells))) return PB200_ERR_INVALID_ARG;
     if (!count) return PB200_OK;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
     pb200_key::CellCtx* C = nullptr;
     int rc = cell_ctx(k, lookup_bits, &C); if (rc) return rc;
     CU(cells_mulmod(C->Y, C->d_consts, (const u64*)d_a, (const u64*)d_b, (const u64*)d_q, (const u64*)d_rem, count, (int)k->words_out,
                     montgomery ? 1 : 0, (u64*)d_cells, k->d_flags, k->sms, C->d_mtab, k->stream));
     return PB200_OK;
-}
+} PB200_CATCH
 
 int pb200_mulmod_cells_batch(pb200_key* k, const uint64_t* a, const uint64_t* b, const uint64_t* q, const uint64_t* rem, size_t count,
-                             uint32_t lookup_bits, int montgomery, uint64_t* cells_out) {
+                             uint32_t lookup_bits, int montgomery, uint64_t* cells_out) try {
     if (!k || (count && (!a || !b || !q || !rem || !cells_out))) return PB200_ERR_INVALID_ARG;
     if (!count) return PB200_OK;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
+    { int rc0_ = clear_flags(k); if (rc0_) return rc0_; }
     pb200_key::CellCtx* C = nullptr;
     int rc = cell_ctx(k, lookup_bits, &C); if (rc) return rc;
     const size_t bin = count * k->words_out * sizeof(u64), bout = count * (size_t)C->Y.n_cells * 32;
@@ -534,17 +852,14 @@ int pb200_mulmod_cells_batch(pb200_key* k, const uint64_t* a, const uint64_t* b,
     if (rc) return rc;
     CU(cudaMemcpyAsync(cells_out, k->scratch.p, bout, cudaMemcpyDeviceToHost, k->stream));
     CU(cudaStreamSynchronize(k->stream));
-    int f = 0;
-    CU(cudaMemcpy(&f, k->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
-    if (f) { CU(cudaMemset(k->d_flags, 0, sizeof(int))); return PB200_ERR_RANGE; }   // (q, rem) do not satisfy a*b = q*n^2 + rem
-    return PB200_OK;
-}
+    return take_flags(k);      // PB200_ERR_CONSTRAINT: (q, rem) do not satisfy a*b = q*n^2 + rem
+} PB200_CATCH
 
 int pb200_assign_cells_batch(pb200_key* k, const uint64_t* values, size_t count, uint32_t value_bits, uint32_t lookup_bits,
-                             int montgomery, uint64_t* cells_out) {
+                             int montgomery, uint64_t* cells_out) try {
     if (!k || !values || !cells_out || value_bits == 0 || value_bits % k->limb_bits || lookup_bits > 32) return PB200_ERR_INVALID_ARG;
     if (!count) return PB200_OK;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
     const int lb = (int)k->limb_bits, nl = (int)(value_bits / k->limb_bits);
     const int kl = lookup_bits ? (lb + (int)lookup_bits - 1) / (int)lookup_bits : 0, xl = lookup_bits && (lb % (int)lookup_bits) ? 1 : 0;
     const int cpl = 1 + kl + xl, words = (int)PB200_WORDS(value_bits);
@@ -555,11 +870,12 @@ int pb200_assign_cells_batch(pb200_key* k, const uint64_t* values, size_t count,
     CU(cudaMemcpyAsync(cells_out, k->scratch.p, bout, cudaMemcpyDeviceToHost, k->stream));
     CU(cudaStreamSynchronize(k->stream));
     return PB200_OK;
-}
+} PB200_CATCH
 
-int pb200_key_n2_cells(pb200_key* k, uint32_t lookup_bits, int montgomery, uint64_t* cells_out) {
+int pb200_key_n2_cells(pb200_key* k, uint32_t lookup_bits, int montgomery, uint64_t* cells_out) try {
     if (!k || !cells_out) return PB200_ERR_INVALID_ARG;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
+    { int rc0_ = clear_flags(k); if (rc0_) return rc0_; }
     pb200_key::CellCtx* C = nullptr;
     int rc = cell_ctx(k, lookup_bits, &C); if (rc) return rc;
     std::vector<u64> nw(k->words_in);
@@ -575,14 +891,14 @@ int pb200_key_n2_cells(pb200_key* k, uint32_t lookup_bits, int montgomery, uint6
     CU(cudaStreamSynchronize(k->stream));
     if (written != C->n2_cells) { t_cuda_error = "n2 cell count mismatch"; return PB200_ERR_CUDA; }
     return take_flags(k);
-}
+} PB200_CATCH
 
 // ---- limb formatting ------------------------------------------------------------------------
 int pb200_repack_limbs(pb200_key* k, const uint64_t* values, size_t count, uint32_t value_bits, uint32_t limb_bits,
-                       uint64_t* limbs_out) {
+                       uint64_t* limbs_out) try {
     if (!k || !values || !limbs_out || limb_bits == 0 || limb_bits > 128 || value_bits % limb_bits) return PB200_ERR_INVALID_ARG;
     if (!count) return PB200_OK;
-    CU(cudaSetDevice(k->device));
+    USE_DEVICE(k);
     uint32_t wpv = PB200_WORDS(value_bits), nl = value_bits / limb_bits;
     size_t bin = count * wpv * sizeof(u64), bout = count * nl * 2 * sizeof(u64);
     CU(k->in_a.reserve(bin)); CU(k->out_a.reserve(bout));
@@ -591,6 +907,6 @@ int pb200_repack_limbs(pb200_key* k, const uint64_t* values, size_t count, uint3
     CU(cudaMemcpyAsync(limbs_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
     CU(cudaStreamSynchronize(k->stream));
     return PB200_OK;
-}
+} PB200_CATCH
 
 }  // extern "C"

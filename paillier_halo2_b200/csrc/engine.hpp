@@ -39,6 +39,13 @@ void block28_set_mma(Block28Key*, bool on);   // constant-operand phases on the 
 void block28_chain_counts(const Block28Key*, uint64_t* n_sqr, uint64_t* n_mul);
 cudaError_t block28_encrypt(Block28Key*, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st);
 cudaError_t block28_tally(Block28Key*, const u64* d_c, size_t count, u64* d_out, cudaStream_t st);
+// multi-GPU tally: one launch per GPU, partials exchanged through peer-mapped mailboxes inside the kernel (collective call)
+cudaError_t block28_tally_peer(Block28Key*, const u64* d_c, size_t count, u64* d_out, cudaStream_t st);
+cudaError_t block28_mailbox(Block28Key*, u64** d_mail, cudaStream_t st);
+size_t block28_mailbox_bytes();
+int block28_max_world();
+int block28_peer_world(const Block28Key*);
+cudaError_t block28_tally_peer_connect(Block28Key*, int rank, int world, u64* const* mail, void* const* opened, int* d_flags);
 // witness engine: the reference's chain with exact (q, rem) per mul_mod (block28t arithmetic + exact tail)
 bool block28_witness_supported(const Block28Key*);
 // d_gchain: n_bits records (q, rem) of the g-chain squarings; gchain_ready = false lets the witness engine produce them

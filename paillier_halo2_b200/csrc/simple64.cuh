@@ -97,6 +97,18 @@ static __device__ __noinline__ int mulmod_simple(const SimpleConsts* __restrict_
     u64 r[PB200_SIMPLE_MAXK + 1];
     mul_full(X, a, k, b, k);
     X[2 * k] = 0;
+    // X << s must stay inside 2k words.  Operands that are not reduced (pb200_add_batch accepts them) can make X >= 2^(128k - s);
+    // then q = floor(X / n^2) > 2^(128k - s) / 2^(64k - s) = 2^(64k) does not fit k words: exactly the range failure, reported
+    // here before the shift would drop the top bits
+    if (K->s) {
+        const int top = 128 * k - K->s, w = top >> 6, b0 = top & 63;
+        u64 over = X[w] >> b0;
+        for (int i = w + 1; i < 2 * k; i++) over |= X[i];
+        if (over) {
+            for (int i = 0; i < k; i++) { q[i] = 0; rem[i] = 0; }
+            return 1;
+        }
+    }
     shl_words(X, 2 * k, K->s);
     // q3 = (q1 * mu) >> 64(k+1); q1 = X[k-1 .. 2k] (k+1 words), mu: k+1 words
     mul_cols(q3, k + 1, k + 1, X + (k - 1), k + 1, K->mu, k + 1);

@@ -22,6 +22,18 @@ pub const PB200_ERR_UNSUPPORTED: c_int = -5;
 pub const PB200_ERR_CUDA: c_int = -6;
 pub const PB200_ERR_NOMEM: c_int = -7;
 pub const PB200_ERR_SINK: c_int = -8;
+pub const PB200_ERR_CONSTRAINT: c_int = -9;
+pub const PB200_ERR_PEER: c_int = -10;
+pub const PB200_FLAG_RANGE: u32 = 1;
+pub const PB200_FLAG_CONSTRAINT: u32 = 2;
+pub const PB200_FLAG_PEER_TIMEOUT: u32 = 4;
+
+/// 64-byte handle of a key's tally mailbox (CUDA IPC), exchanged between the ranks of a multi-process tally group
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct pb200_ipc_handle {
+    pub bytes: [u8; 64],
+}
 
 #[repr(C)]
 pub struct pb200_witness_chunk {
@@ -69,6 +81,7 @@ extern "C" {
     pub fn pb200_key_stream(key: *const pb200_key) -> *mut c_void;
     pub fn pb200_key_chain_counts(key: *const pb200_key, n_sqr: *mut u64, n_mul: *mut u64) -> c_int;
     pub fn pb200_key_sync(key: *mut pb200_key) -> c_int;
+    pub fn pb200_key_take_flags(key: *mut pb200_key, flags_out: *mut u32) -> c_int;
 
     pub fn pb200_encrypt_batch(key: *mut pb200_key, m_le: *const u64, r_le: *const u64, count: usize, c_out_le: *mut u64) -> c_int;
     pub fn pb200_encrypt_batch_dev(key: *mut pb200_key, d_m_le: *const u64, d_r_le: *const u64, count: usize, d_c_out_le: *mut u64) -> c_int;
@@ -79,6 +92,10 @@ extern "C" {
     pub fn pb200_tally(key: *mut pb200_key, c_le: *const u64, count: usize, out_le: *mut u64) -> c_int;
     pub fn pb200_tally_dev(key: *mut pb200_key, d_c_le: *const u64, count: usize, d_partial_out_le: *mut u64) -> c_int;
     pub fn pb200_tally_combine(key: *mut pb200_key, partials_le: *const u64, n_partials: usize, out_le: *mut u64) -> c_int;
+    pub fn pb200_tally_multi(keys: *const *mut pb200_key, n_gpus: c_int, d_c: *const *const u64, counts: *const usize, out_le: *mut u64) -> c_int;
+    pub fn pb200_tally_peer_export(key: *mut pb200_key, out: *mut pb200_ipc_handle) -> c_int;
+    pub fn pb200_tally_peer_connect(key: *mut pb200_key, rank: c_int, world: c_int, handles: *const pb200_ipc_handle) -> c_int;
+    pub fn pb200_tally_peer_dev(key: *mut pb200_key, d_c_le: *const u64, count: usize, d_out_le: *mut u64) -> c_int;
 
     pub fn pb200_encrypt_witness_batch(key: *mut pb200_key, m_le: *const u64, r_le: *const u64, count: usize, c_out_le: *mut u64,
                                        max_chunk_units: usize, sink: pb200_witness_sink_fn, user: *mut c_void) -> c_int;

@@ -85,14 +85,14 @@ static void paillier_enc_add(Context* ctx, const RangeChip* range, size_t enc_bi
     CHECK(biguint_chip.assert_equal_fresh(ctx, c_add_assigned, res_assigned).unwrap());
 }
 
-static BigUint odd(BigUint v) { if (v.is_zero()) v = BigUint(1); v.w[0] |= 1; return v; }     // the GPU path's contract: odd, non-zero n
+static BigUint nonzero(BigUint v) { if (v.is_zero()) v = BigUint(1); return v; }   // num-bigint panics on n = 0; any other n (even, short) is the reference's own test distribution
 
 static void test_paillier_encryption(size_t ENC_BIT_LEN, size_t LIMB_BIT_LEN, int rounds, uint32_t K = 16, uint32_t LOOKUP = 15) {
     for (int it = 0; it < rounds; it++) {
         std::vector<std::string> why; Context kept;
         BigUint n, g, m, r;
         bool ok = base_test().k(K).lookup_bits(LOOKUP).expect_satisfied(true).run((uint32_t)LIMB_BIT_LEN, [&](Context* ctx, const RangeChip* range) {
-            n = odd(gen_biguint(ENC_BIT_LEN)); g = gen_biguint(ENC_BIT_LEN); m = gen_biguint(ENC_BIT_LEN); r = gen_biguint(ENC_BIT_LEN);
+            n = nonzero(gen_biguint(ENC_BIT_LEN)); g = gen_biguint(ENC_BIT_LEN); m = gen_biguint(ENC_BIT_LEN); r = gen_biguint(ENC_BIT_LEN);
             if (it == 1) m = BigUint();                                  // empty g-chain
             if (it == 2) { r = BigUint(1); m = BigUint(1); }
             BigUint res = expected_enc(n, g, m, r);
@@ -120,7 +120,7 @@ static void test_encryption_addition(size_t ENC_BIT_LEN, size_t LIMB_BIT_LEN, in
     for (int it = 0; it < rounds; it++) {
         std::vector<std::string> why; Context kept;
         bool ok = base_test().k(16).lookup_bits(15).expect_satisfied(true).run((uint32_t)LIMB_BIT_LEN, [&](Context* ctx, const RangeChip* range) {
-            BigUint n = odd(gen_biguint(ENC_BIT_LEN)), g = gen_biguint(ENC_BIT_LEN), c1 = gen_biguint(ENC_BIT_LEN), c2 = gen_biguint(ENC_BIT_LEN);
+            BigUint n = nonzero(gen_biguint(ENC_BIT_LEN)), g = gen_biguint(ENC_BIT_LEN), c1 = gen_biguint(ENC_BIT_LEN), c2 = gen_biguint(ENC_BIT_LEN);
             BigUint res = expected_add(n, c1, c2);
             KeyCache keys;
             CHECK(paillier_add_native(n, c1, c2, (uint32_t)ENC_BIT_LEN, &keys, (uint32_t)LIMB_BIT_LEN).unwrap() == res);
@@ -136,7 +136,7 @@ static void test_error_behaviour() {
     KeyCache keys;
     // num-bigint panics on a zero modulus (src/paillier.rs:89-91); here it is an Err, never an abort
     CHECK(paillier_enc_native(BigUint(), BigUint(3), BigUint(5), BigUint(7), 128, &keys).status == PB200_ERR_ZERO_MODULUS);
-    CHECK(paillier_enc_native(BigUint(10), BigUint(3), BigUint(5), BigUint(7), 128, &keys).status == PB200_ERR_EVEN_MODULUS);
+    CHECK(paillier_enc_native(BigUint(10), BigUint(3), BigUint(5), BigUint(7), 128, &keys).unwrap() == expected_enc(BigUint(10), BigUint(3), BigUint(5), BigUint(7)));   // even n: accepted like the reference
     RangeChip range{15};
     BigUintChip chip = BigUintChip::construct(&range, 64);
     Context ctx;

@@ -198,9 +198,8 @@ def test_empty_and_error_paths(built_lib):
             with PaillierKey(3, 2, 128, 64) as small:
                 small.paillier_add_native([(1 << 256) - 1], [(1 << 256) - 1])
         assert e.value.status == _lib.PB200_ERR_RANGE
-    with pytest.raises(Pb200Error) as e:
-        PaillierKey(10, 3, 128, 64)
-    assert e.value.status == _lib.PB200_ERR_EVEN_MODULUS
+    with PaillierKey(10, 3, 128, 64) as even:          # even n is accepted, as in the reference (n = rng.gen_biguint(bits))
+        assert even.paillier_enc_native([5, 0], [7, 9]) == [paillier_enc_native(10, 3, 5, 7), paillier_enc_native(10, 3, 0, 9)]
     with PaillierKey(0x1FFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFF, 5, 264, 88) as key:
         with pytest.raises(Pb200Error) as e:   # m has bits above enc_bits = 264
             key.encrypt_words(np.full((1, 5), 2**64 - 1, dtype="<u8"), np.ones((1, 5), dtype="<u8"))
@@ -306,8 +305,9 @@ def test_gpu_mulmod_cells_large(built_lib, n_bits):
         got_nolookup = key.mulmod_cells(groups[:2], 0)
         lay = key.cells_layout(15)
         bad = key.mulmod_cells
-        with pytest.raises(Pb200Error):
+        with pytest.raises(Pb200Error) as e:
             bad([(pairs[0][0], pairs[0][1], qs[0] ^ 1, res[0])], 15)
+        assert e.value.status == _lib.PB200_ERR_CONSTRAINT
     big = BigUintChip(64, 15)
     n2_as = Assigned(decompose(n2, L, 64), n2, 64, True)
     for (a, b, q, rem), cells in zip(groups, got):

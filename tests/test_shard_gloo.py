@@ -67,3 +67,49 @@ def test_tally_allgather_combine_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(r, True) for r in range(world)]
+
+
+class _FakeKey:
+    """Stands in for PaillierKey in the handle exchange (no GPU in this suite): records what connect receives."""
+
+    def __init__(self, rank, fail_on=None):
+        self.rank, self.fail_on, self.device, self.connected = rank, fail_on, 0, None
+
+    def tally_peer_export(self):
+        return bytes([self.rank]) * 64
+
+    def tally_peer_connect(self, rank, world, handles):
+        if self.fail_on == rank:
+            raise RuntimeError("cudaIpcOpenMemHandle failed")
+        self.connected = (rank, world, list(handles))
+
+
+def _peer_worker(rank, world, port, fail_on, q):
+    from paillier_halo2_b200.shard import connect_tally_peers
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    key = _FakeKey(rank, fail_on)
+    mode = connect_tally_peers(key, rank, world)
+    ok = mode == ("nccl" if fail_on is not None else "peer-memory")
+    if key.connected is not None:
+        r, w, hs = key.connected
+        ok = ok and r == rank and w == world and hs == [bytes([i]) * 64 for i in range(world)]
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_on", [None, 1])
+def test_peer_handle_exchange_gloo(fail_on):
+    """connect_tally_peers: handles all-gathered in rank order; if ANY rank cannot map its peers, EVERY rank falls back."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, fail_on, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(r, True) for r in range(world)]
