@@ -597,7 +597,9 @@ int pb200_encrypt_witness_batch(pb200_key* k, const uint64_t* m, const uint64_t*
     // a chunk's kernel takes the latency of ONE unit's chain whatever its size (about 0.15 s at |n| = 2048), and the first piece
     // can leave only when the first chunk's kernel has ended: chunks of 8 GiB keep that start-up short while one chunk's drain
     // (8 GiB over PCIe, ~0.15 s) still covers the next chunk's kernel
-    size_t chunk_bytes = (size_t)8 << 30;
+    // (the chain latency grows with the square of the key size: 0.15 s at 2048, 0.3 s at 3072)
+    size_t chunk_bytes = (size_t)(8.0 * 1073741824.0 * ((double)k->n_bits / 2048.0) * ((double)k->n_bits / 2048.0));
+    if (chunk_bytes < ((size_t)1 << 30)) chunk_bytes = (size_t)1 << 30;
     { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) { size_t third = fr / 3; if (third < chunk_bytes) chunk_bytes = third; } }
     chunk_bytes = env_bytes("PB200_WITNESS_CHUNK_BYTES", chunk_bytes);
     if (chunk_bytes < max_unit * rec_bytes) chunk_bytes = (size_t)max_unit * rec_bytes;
