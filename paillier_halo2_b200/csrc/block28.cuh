@@ -48,11 +48,14 @@ struct Cfg {
     static constexpr int KSTEPS = (K7 + 31) / 32;                     // k-steps of mma.m16n8k32
     static constexpr bool HALF_LAST = (K7 % 32) != 0;                 // last k-step only half populated (K7 % 32 == 16)
     static constexpr int RS = K7 + ((((K7 / 4) % 8) == 4) ? 0 : ((4 - ((K7 / 4) % 8) + 8) % 8) * 4);   // row stride, (RS/4) % 8 == 4
-    static constexpr int PAD7 = 48;
+    static constexpr int PAD7 = 64;                                   // zero padding either side of the reversed constant: a quad of
+                                                                      // tiles reaches 62 bytes beyond the band at both ends
     static constexpr int XLEN = K7 + 2 * PAD7;                        // reversed constant table, zero padded
-    static constexpr int RTAB4 = (4 * XLEN + 15) / 16;                // int4 per constant (4 byte-shifted copies)
+    // stride between the four byte-shifted copies: XSTR / 4 == 16 (mod 32), so that the two shift classes a warp reads in one
+    // instruction (even and odd MMA columns) fall on disjoint banks
+    static constexpr int XSTR = ((XLEN - 64 + 127) / 128) * 128 + 64;
+    static constexpr int RTAB4 = (4 * XSTR + 15) / 16;                // int4 per constant (4 byte-shifted copies)
     static constexpr int NP_HIGH = (L + 2 + 3) / 4, NP_LOW = (L + 3) / 4;   // tile pairs (4 digits each) per phase
-    static constexpr int NPW = (NP_HIGH + G_ - 1) / G_;               // tile pairs per warp
     // shared memory: V, B, Q (L digits each), T (2L digits), constants mu, Nt, two_sh, reversed s8 tables of mu, Nt
     static constexpr int SMEM_INT4 = 5 * VAL4 + 3 * ENTRY4 + 2 * RTAB4;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_INT4 * 16;
@@ -562,7 +565,12 @@ __device__ __forceinline__ int dl_index(int jj, int m) { return jj * 32 + ((m + 
 
 __device__ __forceinline__ unsigned lds32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 
-// C[lane][p] for the tile pairs of this warp, p = p_base + 16*U + ...; folded: LO[jj] / CA[jj+1], jj = 4U + t
+// C[lane][p] for the tile pairs of this warp, p = p_base + 16*U + ...; folded: LO[jj] / CA[jj+1], jj = 4U + t.
+// A warp works on a QUAD = two adjacent tile pairs (32 columns, 8 digits) per pass: the A fragments of a k-step serve both, and by
+// the Toeplitz structure the B fragments of the second pair are those of the first shifted by half a k-step — b0(U+1, ks) is
+// b1(U, ks-1) and b1(U+1, ks) is b0(U, ks) — so a k-step costs two ldmatrix.x4 and four 32-bit loads for EIGHT mma.sync
+// (the one-pair-per-pass version: the same loads for four; its IMMA phases ran at 69 % shared-memory pipe and 8.5 instructions
+// per MMA, profiles/ncu_k_encrypt_r01_fused_summary.txt).
 template <class C, bool HIGH>
 __device__ __noinline__ void phase_mma(int4* smem_base) {
     constexpr int G = C::G, L = C::L, K7 = C::K7;
@@ -571,61 +579,18 @@ __device__ __noinline__ void phase_mma(int4* smem_base) {
     const int g = lane >> 2, t = lane & 3;
     constexpr int P_BASE = HIGH ? 4 * (L - 2) : 0;
     constexpr int NP = HIGH ? C::NP_HIGH : C::NP_LOW;
+    constexpr int NQ = (NP + 1) / 2, NQW = (NQ + G - 1) / G;
     constexpr int NOUT = HIGH ? L + 2 : L;
     // ldmatrix.x4 row addresses: lanes 0-7 rows 0-7 (k bytes 0-15), 8-15 rows 8-15, 16-23 rows 0-7 (+16), 24-31 rows 8-15 (+16)
     const unsigned as_base = (unsigned)__cvta_generic_to_shared(as_ptr<C>(S)) + ((lane & 7) + ((lane >> 3) & 1) * 8) * C::RS + (lane >> 4) * 16;
     const unsigned rt_base = (unsigned)__cvta_generic_to_shared(HIGH ? S.rmu : S.rnt);
     int* LO = lo_ptr<C>(S);
     int* CA = ca_ptr<C>(S);
-#pragma unroll 1
-    for (int q = 0; q < C::NPW; q++) {
-        // tile pair: columns [P0, P0+16) = digits 4U .. 4U+3.  Tile pairs are dealt to the warps in serpentine order: the number
-        // of k-steps of a tile grows (phase C) or shrinks (phase B) linearly with U, a plain round-robin gives warp 0 the most
-        // expensive tile of every round (55 against 38 k-steps at |n| = 2048) and the phase ends at a CTA barrier (measured: +0.1 %)
-        const int U = ((q & 1) ? (G - 1 - warp) : warp) + q * G;
-        if (U >= NP) continue;
-        const int P0 = P_BASE + 16 * U;
-        // k-steps with some (k, p): 0 <= p - k <= K7-1, k in [32ks, 32ks+32), p in [P0, P0+16)
-        int ks_lo = (P0 - (K7 - 1) - 31 + 31) / 32; if (P0 - (K7 - 1) - 31 <= 0) ks_lo = 0;
-        int ks_hi = (P0 + 15) / 32; if (ks_hi > C::KSTEPS - 1) ks_hi = C::KSTEPS - 1;
-        // B-fragment addresses: column n = g of tile h is p = P0 + 4(g>>1) + (g&1) + 2h; 4 ascending bytes of the reversed table
-        unsigned baddr[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int p = P0 + 4 * (g >> 1) + (g & 1) + 2 * h;
-            const int idx0 = C::PAD7 + K7 - 1 - p + 4 * t;
-            const int sft = idx0 & 3;
-            baddr[h] = rt_base + sft * C::XLEN + (idx0 - sft);
-        }
-        int acc[2][2][4];           // [tile h][m-tile][c0..c3]
-#pragma unroll
-        for (int h = 0; h < 2; h++)
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                for (int i = 0; i < 4; i++) acc[h][mt][i] = 0;
-#pragma unroll 2
-        for (int ks = ks_lo; ks <= ks_hi; ks++) {
-            const unsigned ko = 32u * ks;
-            unsigned a[2][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++) {
-                const unsigned ap = as_base + mt * 16 * C::RS + ko;
-                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(a[mt][0]), "=r"(a[mt][1]), "=r"(a[mt][2]), "=r"(a[mt][3]) : "r"(ap));
-                if (C::HALF_LAST && ks == C::KSTEPS - 1) { a[mt][2] = 0; a[mt][3] = 0; }
-            }
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const unsigned b0 = lds32(baddr[h] + ko), b1 = lds32(baddr[h] + ko + 16);
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++) mma_s8(acc[h][mt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
-            }
-        }
-        // fold: thread (g, t) owns the 4 radix-2^7 columns of digit jj = 4U + t for rows g, g+8 of each m-tile
+    // fold of one tile pair: thread (g, t) owns the 4 radix-2^7 columns of digit jj = 4U + t for rows g, g+8 of each m-tile:
+    // v = c0 + c1 2^7 + c2 2^14 + c3 2^21 (|c| < 2^23) in 32-bit pieces, lo digit + carry into the next digit
+    auto fold = [&](const int (&acc)[2][2][4], int U) {
         const int jj = 4 * U + t;
         if (jj < NOUT) {
-            // v = c0 + c1 2^7 + c2 2^14 + c3 2^21 (|c| < 2^23) in 32-bit pieces: v = lowp + hr 2^14 + hq 2^28
             const int x0 = (g + 8 * jj) & 31, x1 = (g + 8 * (jj + 1)) & 31;
             int* lo_row = LO + jj * 32;
             int* ca_row = CA + (jj + 1) * 32;
@@ -643,8 +608,108 @@ __device__ __noinline__ void phase_mma(int4* smem_base) {
                     ca_row[(x1 + off) & 31] = ca;
                 }
         }
+    };
+#pragma unroll 1
+    for (int q = 0; q < NQW; q++) {
+        // quads are dealt to the warps in serpentine order (the k-steps of a quad grow (phase C) or shrink (phase B) linearly
+        // with its index and the phase ends at a CTA barrier)
+        const int Qi = ((q & 1) ? (G - 1 - warp) : warp) + q * G;
+        if (Qi >= NQ) continue;
+        const int U = 2 * Qi;
+        const bool two = U + 1 < NP;                 // the last quad of an odd NP holds one tile pair
+        const int P0 = P_BASE + 16 * U;
+        // k-steps with some (k, p): 0 <= p - k <= K7-1, k in [32ks, 32ks+32), p in [P0, P0+32)
+        int ks_lo = (P0 - (K7 - 1)) / 32; if (P0 - (K7 - 1) <= 0) ks_lo = 0;
+        int ks_hi = (P0 + (two ? 31 : 15)) / 32; if (ks_hi > C::KSTEPS - 1) ks_hi = C::KSTEPS - 1;
+        // B-fragment addresses of the first pair: column n = g of tile h is p = P0 + 4(g>>1) + (g&1) + 2h; 4 ascending bytes of the
+        // reversed table, taken from the copy whose shift makes the read an aligned word
+        unsigned baddr[2], prev[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int p = P0 + 4 * (g >> 1) + (g & 1) + 2 * h;
+            const int idx0 = C::PAD7 + K7 - 1 - p + 4 * t;
+            const int sft = idx0 & 3;
+            baddr[h] = rt_base + sft * C::XSTR + (idx0 - sft) + 32u * ks_lo;
+            prev[h] = lds32(baddr[h] - 16);
+        }
+        int acc0[2][2][4], acc1[2][2][4];           // [tile h][m-tile][c0..c3] of the two pairs
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) { acc0[h][mt][i] = 0; acc1[h][mt][i] = 0; }
+        unsigned ap = as_base + 32u * ks_lo;
+        const int nks = ks_hi - ks_lo + 1;
+        const int half_at = (C::HALF_LAST && ks_hi == C::KSTEPS - 1) ? nks - 1 : -1;      // the half populated last k-step
+        if (two) {
+#pragma unroll 2
+            for (int i = 0; i < nks; i++, ap += 32, baddr[0] += 32, baddr[1] += 32) {
+                unsigned a[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(a[mt][0]), "=r"(a[mt][1]), "=r"(a[mt][2]), "=r"(a[mt][3]) : "r"(ap + mt * 16 * C::RS));
+                    if (i == half_at) { a[mt][2] = 0; a[mt][3] = 0; }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const unsigned b0 = lds32(baddr[h]), b1 = lds32(baddr[h] + 16);
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        mma_s8(acc0[h][mt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+                        mma_s8(acc1[h][mt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], prev[h], b0);
+                    }
+                    prev[h] = b1;
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (int i = 0; i < nks; i++, ap += 32, baddr[0] += 32, baddr[1] += 32) {
+                unsigned a[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(a[mt][0]), "=r"(a[mt][1]), "=r"(a[mt][2]), "=r"(a[mt][3]) : "r"(ap + mt * 16 * C::RS));
+                    if (i == half_at) { a[mt][2] = 0; a[mt][3] = 0; }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const unsigned b0 = lds32(baddr[h]), b1 = lds32(baddr[h] + 16);
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) mma_s8(acc0[h][mt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+                }
+            }
+        }
+        fold(acc0, U);
+        if (two) fold(acc1, U + 1);
     }
     __syncthreads();
+}
+
+// One block of packed s8 digits (BL words) into a lane's row of As.  Rows are RS bytes apart: a 32-bit store per lane touches only
+// 8 banks (4-way conflict, 76 wavefronts per block), a 128-bit store per lane is conflict-free (a quarter warp covers all 32 banks).
+// The block starts at word warp*BL of the 16-byte aligned row, i.e. at one of four alignments: LEAD single words reach the next
+// 16-byte boundary, the rest goes out as 128-bit stores plus a short tail.
+template <int BL, int LEAD>
+__device__ __forceinline__ void store_row_aligned(unsigned* row, const unsigned (&w)[BL]) {
+#pragma unroll
+    for (int k = 0; k < LEAD; k++) row[k] = w[k];
+    constexpr int NV = (BL - LEAD) / 4;
+#pragma unroll
+    for (int c = 0; c < NV; c++)
+        *reinterpret_cast<uint4*>(row + LEAD + 4 * c) = make_uint4(w[LEAD + 4 * c], w[LEAD + 4 * c + 1], w[LEAD + 4 * c + 2], w[LEAD + 4 * c + 3]);
+#pragma unroll
+    for (int k = LEAD + 4 * NV; k < BL; k++) row[k] = w[k];
+}
+template <int BL>
+__device__ __forceinline__ void store_row(unsigned* row, const unsigned (&w)[BL], int warp) {
+    switch ((4 - ((warp * BL) & 3)) & 3) {          // warp-uniform
+        case 0: store_row_aligned<BL, 0>(row, w); break;
+        case 1: store_row_aligned<BL, 1>(row, w); break;
+        case 2: store_row_aligned<BL, 2>(row, w); break;
+        default: store_row_aligned<BL, 3>(row, w); break;
+    }
 }
 
 // q1 (T digits [L-1, 2L-1)) -> s8 rows in As.  One (block = warp, lane) per thread.
@@ -653,8 +718,10 @@ __device__ __forceinline__ void q1_to_bytes(Smem<C>& S, int warp, int lane) {
     int a[C::CH * 4];
     load_q1_block<C>(a, S.T, warp, lane);
     unsigned* row = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + warp * C::BL;
+    unsigned w[C::BL];
 #pragma unroll
-    for (int k = 0; k < C::BL; k++) row[k] = split7_pack(a[k]);
+    for (int k = 0; k < C::BL; k++) w[k] = split7_pack(a[k]);
+    store_row<C::BL>(row, w, warp);
     if (C::K7 < C::KSTEPS * 32 && warp == C::G - 1) {           // zero the tail of a half populated last k-step
         unsigned* tail = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + C::L;
 #pragma unroll
@@ -679,11 +746,13 @@ __device__ __forceinline__ void qhat_to_bytes(Smem<C>& S, int warp, int lane) {
         carry = (t1 - sgxt28(t1)) >> W;
     }
     unsigned* row = (unsigned*)(as_ptr<C>(S) + lane * C::RS) + warp * C::BL;      // As (Q buffer) is dead since phase B's MMAs ended
+    unsigned w[C::BL];
 #pragma unroll
     for (int k = 0; k < C::BL; k++) {
         const int jj = warp * C::BL + k + 2;
-        row[k] = split7_pack(LO[dl_index(jj, lane)] + CA[dl_index(jj, lane)] + (k == 0 ? carry : 0));
+        w[k] = split7_pack(LO[dl_index(jj, lane)] + CA[dl_index(jj, lane)] + (k == 0 ? carry : 0));
     }
+    store_row<C::BL>(row, w, warp);
     __syncthreads();
 }
 

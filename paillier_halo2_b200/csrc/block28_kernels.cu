@@ -767,7 +767,7 @@ static void to_rtab(const std::vector<int>& entry, std::vector<int>& out_words) 
     for (int j = 0; j < C::K7; j++) rfull[C::PAD7 + (C::K7 - 1 - j)] = k7[j];
     std::vector<signed char> tab((size_t)C::RTAB4 * 16, 0);
     for (int sft = 0; sft < 4; sft++)
-        for (int x = 0; x < C::XLEN; x++) tab[(size_t)sft * C::XLEN + x] = x + sft < C::XLEN ? rfull[x + sft] : 0;
+        for (int x = 0; x < C::XLEN; x++) tab[(size_t)sft * C::XSTR + x] = x + sft < C::XLEN ? rfull[x + sft] : 0;
     out_words.resize((size_t)C::RTAB4 * 4);
     memcpy(out_words.data(), tab.data(), tab.size());
 }

@@ -187,6 +187,57 @@ __device__ __forceinline__ W4 fr_to_mont32(const W4& x) {
     for (int k = 0; k < 4; k++) a.w[k] = borrow ? a.w[k] : d.w[k];
     return a;
 }
+// x * R mod p for x < 2^(64 NX), NX = 1, 2, 3, branch-free: REDC with the SHORT radix 2^(64 NX) of T = x * K_NX, K_NX = 2^(256 + 64 NX) mod p.
+// T < 2^(64 NX) p, so NX reduction rows leave T / 2^(64 NX) < 2p: 2 NX rows of sixteen 32 x 32 products in all (one-word cells: 32
+// products instead of the 40 + estimate + correction loops of fr_to_mont_u64; carries: 64 instead of 112; columns: 96 instead of 112)
+// and one conditional subtraction.  Not inlined: the conversion pass of the Montgomery kernel is three call sites, not 170 KB of SASS.
+__device__ __constant__ unsigned FR_K32[3][8] = {
+    {0x7c5fb586u, 0xb4c6edf9u, 0xbfeb93beu, 0x708c8d50u, 0x04f7e0efu, 0x9ffd1de4u, 0x9a392866u, 0x215b02acu},
+    {0xef8cfeb9u, 0xb075da81u, 0xa5b6cd8cu, 0xa7f12accu, 0x7957bf7bu, 0x32c47504u, 0x48ffa25eu, 0x03d581d7u},
+    {0xc177f51au, 0x5665c3b5u, 0xde75c713u, 0x00e7f02au, 0x2f747168u, 0xb09192e5u, 0xcccdc65du, 0x0621c0bbu}};
+template <int NX>
+__device__ __noinline__ W4 fr_redc(u64 x0, u64 x1, u64 x2) {
+    unsigned E[2 * NX + 12], O[2 * NX + 12];
+#pragma unroll
+    for (int k = 0; k < 2 * NX + 12; k++) { E[k] = 0; O[k] = 0; }
+    unsigned p[8], kk[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { p[k] = FR_P32[k]; kk[k] = FR_K32[NX - 1][k]; }
+    const u64 xs[3] = {x0, x1, x2};
+#pragma unroll
+    for (int i = 0; i < NX; i++) PB200_ROW(E, O, 2 * i, xs[i], kk)
+    u64 cin = 0;
+#pragma unroll
+    for (int i = 0; i < NX; i++) {
+        u64 s0 = (u64)E[2 * i] + O[2 * i] + cin;
+        u64 s1 = (u64)E[2 * i + 1] + O[2 * i + 1] + (s0 >> 32);
+        const u64 ti = (s0 & 0xffffffffull) | (s1 << 32);
+        const u64 m = ti * FR_INV;
+        PB200_ROW(E, O, 2 * i, m, p)
+        s0 = (u64)E[2 * i] + O[2 * i] + cin;
+        s1 = (u64)E[2 * i + 1] + O[2 * i + 1] + (s0 >> 32);
+        cin = s1 >> 32;
+    }
+    W4 a, b;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        a.w[k] = ((u64)E[2 * NX + 1 + 2 * k] << 32) | E[2 * NX + 2 * k];
+        b.w[k] = ((u64)O[2 * NX + 1 + 2 * k] << 32) | O[2 * NX + 2 * k];
+    }
+    w4_add(a, b);
+    b = w4_zero(); b.w[0] = cin;
+    w4_add(a, b);
+    W4 d = a;
+    u64 borrow = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u64 xk = d.w[k], yk = FR_P[k], t = xk - yk, b1 = xk < yk, t2 = t - borrow, b2 = t < borrow;
+        d.w[k] = t2; borrow = b1 | b2;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) a.w[k] = borrow ? a.w[k] : d.w[k];
+    return a;
+}
 #undef PB200_ROW
 #undef PB200_CHAIN4
 
@@ -282,7 +333,34 @@ __device__ __forceinline__ void store_chunk(u64* out, size_t cell, W4 v, const u
         const ulonglong2 a = __ldg(t), b = __ldg(t + 1);
         v.w[0] = a.x; v.w[1] = a.y; v.w[2] = b.x; v.w[3] = b.y;
         store_cell_k<MONT>(out, cell, v, CK_RAW);
-    } else store_cell_k<MONT>(out, cell, v, CK_SMALL);
+    } else if (MONT) store_cell_k<true>(out, cell, fr_redc<1>(v.w[0], 0, 0), CK_RAW);
+    else store_cell_k<false>(out, cell, v, CK_RAW);
+}
+
+// Four chunk cells per lane and pass: the Montgomery forms are 32-byte gathers from the L2-resident table, and with one gather per
+// pass the kernel sat on their latency (profiles/ncu_k_cells_r02_mont_summary.txt: long-scoreboard 2.4 stall cycles per issue at 16
+// warps per SM).  All eight loads of a pass are issued before the first store.
+template <bool MONT>
+__device__ __forceinline__ void store_chunks4(u64* out, const size_t (&cell)[4], const u64 (&ch)[4], const bool (&ok)[4], const u64* __restrict__ mtab) {
+    if (MONT && mtab) {
+        ulonglong2 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const ulonglong2* t = reinterpret_cast<const ulonglong2*>(mtab) + 2 * (ok[u] ? ch[u] : 0);
+            a[u] = __ldg(t); b[u] = __ldg(t + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (ok[u]) { ulonglong4 o; o.x = a[u].x; o.y = a[u].y; o.z = b[u].x; o.w = b[u].y; reinterpret_cast<ulonglong4*>(out)[cell[u]] = o; }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (ok[u]) {
+                W4 v = w4_zero(); v.w[0] = ch[u];
+                if (MONT) v = fr_redc<1>(ch[u], 0, 0);
+                store_cell_k<MONT>(out, cell[u], v, CK_RAW);
+            }
+    }
 }
 
 __device__ __forceinline__ void store_cell(u64* out, size_t cell, W4 v, int mont) {
@@ -441,7 +519,7 @@ __device__ __forceinline__ void mac64(Acc192& A, u64 a, u64 b) {
 }
 
 template <bool MONT>
-__global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_cpl, u64 m_eq, u64 m_eqs, const u64* __restrict__ consts,
+__global__ void __launch_bounds__(128, MONT ? 4 : 6) k_cells_mulmod64(CellLayout Y, u64 m_cpl, u64 m_eq, u64 m_eqs, u64 m_ch, const u64* __restrict__ consts,
                                                            const u64* __restrict__ a, const u64* __restrict__ b,
                                                            const u64* __restrict__ q, const u64* __restrict__ rem,
                                                            size_t count, u64* __restrict__ out, int* flags, const u64* __restrict__ mtab) {
@@ -450,8 +528,12 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
     const u64* c_accm = consts + 2 * L + 4 + 4 * NC;      // Montgomery forms of q_acc, mod_acc: [NC][4] each
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64* s_n = sm;
-    u64* s_w = sm + L + (size_t)warp * (8 * L + 3 * NC + 1);      // per warp: two limb sets (double buffer), then d
+    // per warp: two limb sets (double buffer), then d; the Montgomery kernel also keeps the canonical columns ab and q*n^2 (3 words
+    // each) for its conversion passes
+    u64* s_w = sm + L + (size_t)warp * (8 * L + (MONT ? 9 : 3) * NC + 1);
     u64* s_d = s_w + 8 * L;
+    u64* s_ab = s_d + 3 * NC;
+    u64* s_qn = s_ab + 3 * NC;
     const u64* c_wmax = consts + 2 * L;        // consts: n2 limbs [L][2], word_max (4 words), q_acc [NC][2], mod_acc [NC][2]
     const u64* c_qacc = c_wmax + 4;
     const u64* c_macc = c_qacc + 2 * NC;
@@ -482,13 +564,36 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
         u64* s_b = s_a + L; u64* s_q = s_b + L; u64* s_r = s_q + L;
         const size_t base = g * (size_t)Y.n_cells;
         // q and rem: limb cells with their range-check chunks
-        for (int c = lane; c < Y.off_ab; c += 32) {
-            const int cc = c < Y.off_rem ? c : c - Y.off_rem;
-            const u64* src = c < Y.off_rem ? s_q : s_r;
-            const int limb = (int)(((u64)cc * m_cpl) >> 32), sub = cc - limb * Y.cpl;
-            const u64 x = src[limb];
-            if (sub == 0) { W4 v = w4_zero(); v.w[0] = x; store_cell_k<MONT>(out, base + c, v, CK_SMALL); }
-            else store_chunk<MONT>(out, base + c, chunk_cell(x, 0, sub, pad_l, Y.lookup_bits, Y.kl), mtab);
+        if (!MONT) {
+            for (int c = lane; c < Y.off_ab; c += 32) {
+                const int cc = c < Y.off_rem ? c : c - Y.off_rem;
+                const u64* src = c < Y.off_rem ? s_q : s_r;
+                const int limb = (int)(((u64)cc * m_cpl) >> 32), sub = cc - limb * Y.cpl;
+                const u64 x = src[limb];
+                if (sub == 0) { W4 v = w4_zero(); v.w[0] = x; store_cell_k<false>(out, base + c, v, CK_RAW); }
+                else store_chunk<false>(out, base + c, chunk_cell(x, 0, sub, pad_l, Y.lookup_bits, Y.kl), mtab);
+            }
+        } else {
+            // the limb cells themselves: one-word conversions, all lanes on the same path
+            for (int c = lane; c < 2 * L; c += 32) {
+                const int limb = c < L ? c : c - L;
+                store_cell_k<true>(out, base + (c < L ? 0 : Y.off_rem) + (size_t)limb * Y.cpl, fr_redc<1>((c < L ? s_q : s_r)[limb], 0, 0), CK_RAW);
+            }
+            // their range-check chunks: table gathers, four per lane and pass
+            const int cpk = Y.cpl - 1, n_ch = 2 * L * cpk;
+            for (int i0 = lane; i0 < n_ch; i0 += 128) {
+                size_t cell[4]; u64 ch[4]; bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int idx = i0 + 32 * u;
+                    ok[u] = idx < n_ch;
+                    const int li = ok[u] ? (int)(((u64)idx * m_ch) >> 32) : 0, sub = ok[u] ? idx - li * cpk + 1 : 1;      // li: limb index over q then rem
+                    const u64 x = li < L ? s_q[li] : s_r[li - L];
+                    ch[u] = chunk_cell(x, 0, sub, pad_l, Y.lookup_bits, Y.kl).w[0];
+                    cell[u] = base + (li < L ? 0 : Y.off_rem) + (size_t)(li < L ? li : li - L) * Y.cpl + sub;
+                }
+                store_chunks4<true>(out, cell, ch, ok, mtab);
+            }
         }
         // no-carry columns ab and q*n^2, the sums, and d
         for (int c = lane; c < L; c += 32) {
@@ -520,16 +625,13 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
                     W4 ab, qn;
                     ab.w[0] = h ? ah0 : al0; ab.w[1] = h ? ah1 : al1; ab.w[2] = h ? ah2 : al2; ab.w[3] = 0;
                     qn.w[0] = h ? qh0 : ql0; qn.w[1] = h ? qh1 : ql1; qn.w[2] = h ? qh2 : ql2; qn.w[3] = 0;
-                    store_cell_k<MONT>(out, base + Y.off_ab + col, ab, CK_WIDE);
                     W4 qp = qn;
                     if (h == 0) mac3p(qp.w[0], qp.w[1], qp.w[2], s_r[c], 0);
-                    if (MONT) {
-                        // Montgomery form is linear: the cell of qn + rem is the cell of qn plus the (one-word) cell of rem, and for the
-                        // upper columns it IS the cell of qn: one general conversion serves two cells
-                        const W4 qn_m = fr_to_mont32<3>(qn);
-                        store_cell_k<true>(out, base + Y.off_qn + col, qn_m, CK_RAW);
-                        store_cell_k<true>(out, base + Y.off_qnp + col, h == 0 ? fr_add(qn_m, fr_to_mont_u64(s_r[c])) : qn_m, CK_RAW);
+                    if (MONT) {      // canonical columns kept for the conversion passes below
+                        s_ab[3 * col] = ab.w[0]; s_ab[3 * col + 1] = ab.w[1]; s_ab[3 * col + 2] = ab.w[2];
+                        s_qn[3 * col] = qn.w[0]; s_qn[3 * col + 1] = qn.w[1]; s_qn[3 * col + 2] = qn.w[2];
                     } else {
+                        store_cell_k<false>(out, base + Y.off_ab + col, ab, CK_RAW);
                         store_cell_k<false>(out, base + Y.off_qn + col, qn, CK_RAW);
                         store_cell_k<false>(out, base + Y.off_qnp + col, qp, CK_RAW);
                     }
@@ -587,34 +689,46 @@ __global__ void __launch_bounds__(128, 6) k_cells_mulmod64(CellLayout Y, u64 m_c
             __syncwarp();
             continue;
         }
-        // eq section in passes of uniform cell kind (no divergence between the conversion paths):
-        // per column [carry (wide), cs (one word), q_acc, mod_acc (per-key, pre-converted)], then the carries' chunks
+        // Montgomery output: conversion passes of uniform cell kind (no divergence between the conversion paths, one call site each).
+        // Columns: Montgomery form is linear, so the cell of qn + rem is the cell of qn plus the (one-word) cell of rem, and for the
+        // upper columns it IS the cell of qn: one general conversion serves two cells.
+        for (int col = lane; col < NC; col += 32)
+            store_cell_k<true>(out, base + Y.off_ab + col, fr_redc<3>(s_ab[3 * col], s_ab[3 * col + 1], s_ab[3 * col + 2]), CK_RAW);
+        for (int col = lane; col < NC; col += 32) {
+            const W4 qn_m = fr_redc<3>(s_qn[3 * col], s_qn[3 * col + 1], s_qn[3 * col + 2]);
+            store_cell_k<true>(out, base + Y.off_qn + col, qn_m, CK_RAW);
+            store_cell_k<true>(out, base + Y.off_qnp + col, col < L ? fr_add(qn_m, fr_redc<1>(s_r[col], 0, 0)) : qn_m, CK_RAW);
+        }
+        // eq section, per column [carry (two words), cs (one word), q_acc, mod_acc (per-key, pre-converted)], then the carries' chunks
         for (int i = lane; i < NC; i += 32) {
             const size_t cell = base + Y.off_eq + (size_t)i * Y.eq_stride;
-            W4 v = w4_zero();
-            v.w[0] = s_d[3 * i + 1]; v.w[1] = s_d[3 * i + 2];
-            store_cell_k<MONT>(out, cell, v, CK_WIDE);
-            v.w[0] = s_d[3 * i]; v.w[1] = 0;
-            store_cell_k<MONT>(out, cell + 1, v, CK_SMALL);
+            store_cell_k<true>(out, cell, fr_redc<2>(s_d[3 * i + 1], s_d[3 * i + 2], 0), CK_RAW);
+            store_cell_k<true>(out, cell + 1, fr_redc<1>(s_d[3 * i], 0, 0), CK_RAW);
 #pragma unroll
             for (int w = 0; w < 2; w++) {
-                if (MONT) {
-                    const u64* m4 = c_accm + 4 * ((size_t)w * NC + i);
-                    v.w[0] = __ldg(m4); v.w[1] = __ldg(m4 + 1); v.w[2] = __ldg(m4 + 2); v.w[3] = __ldg(m4 + 3);
-                } else {
-                    const u64* src = w ? c_macc : c_qacc;
-                    v.w[0] = __ldg(src + 2 * i); v.w[1] = __ldg(src + 2 * i + 1); v.w[2] = v.w[3] = 0;
-                }
-                store_cell_k<MONT>(out, cell + 2 + w, v, CK_RAW);
+                const u64* m4 = c_accm + 4 * ((size_t)w * NC + i);
+                W4 v; v.w[0] = __ldg(m4); v.w[1] = __ldg(m4 + 1); v.w[2] = __ldg(m4 + 2); v.w[3] = __ldg(m4 + 3);
+                store_cell_k<true>(out, cell + 2 + w, v, CK_RAW);
             }
         }
-        const int cpc = Y.kc + Y.xc;
-        for (int idx = lane; idx < (NC - 1) * cpc; idx += 32) {
-            const int i = (int)(((u64)idx * m_eq) >> 32), sub = idx - i * cpc;     // m_eq: magic of cpc
-            store_chunk<MONT>(out, base + Y.off_eq + (size_t)i * Y.eq_stride + 4 + sub,
-                              chunk_cell(s_d[3 * i + 1], s_d[3 * i + 2], sub + 1, pad_c, Y.lookup_bits, Y.kc), mtab);
+        const int cpc = Y.kc + Y.xc, n_cc = (NC - 1) * cpc;
+        for (int i0 = lane; i0 < n_cc; i0 += 128) {
+            size_t cell[4]; u64 ch[4]; bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = i0 + 32 * u;
+                ok[u] = idx < n_cc;
+                const int i = ok[u] ? (int)(((u64)idx * m_eq) >> 32) : 0, sub = ok[u] ? idx - i * cpc : 0;     // m_eq: magic of cpc
+                ch[u] = chunk_cell(s_d[3 * i + 1], s_d[3 * i + 2], sub + 1, pad_c, Y.lookup_bits, Y.kc).w[0];
+                cell[u] = base + Y.off_eq + (size_t)i * Y.eq_stride + 4 + sub;
+            }
+            store_chunks4<true>(out, cell, ch, ok, mtab);
         }
-        if (lane == 0) { W4 v = w4_zero(); v.w[0] = (u64)eq; store_cell_k<MONT>(out, base + Y.n_cells - 1, v, CK_SMALL); }
+        if (lane == 0) {       // the flag cell: Montgomery form of 1 is R mod p
+            W4 v = w4_zero();
+            if (eq) { v.w[0] = FR_R1[0]; v.w[1] = FR_R1[1]; v.w[2] = FR_R1[2]; v.w[3] = FR_R1[3]; }
+            store_cell_k<true>(out, base + Y.n_cells - 1, v, CK_RAW);
+        }
         __syncwarp();
     }
 }
@@ -685,7 +799,7 @@ cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_
     if (!count) return cudaSuccess;
     if (Y.limb_bits == 64 && Y.n_cells < 65536) {
         const size_t L = Y.L, NC = 2 * L - 1;
-        const size_t smem64 = (L + 4 * (8 * L + 3 * NC + 1)) * sizeof(u64);
+        const size_t smem64 = (L + 4 * (8 * L + (mont ? 9 : 3) * NC + 1)) * sizeof(u64);
         {   // per device (a function attribute belongs to the current context): set on every launch, it is a host-side table write
             cudaError_t e = mont ? cudaFuncSetAttribute(k_cells_mulmod64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)
                                  : cudaFuncSetAttribute(k_cells_mulmod64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -693,12 +807,14 @@ cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_
         }
         const u64 m_eqs = (0x100000000ull + Y.eq_stride - 1) / Y.eq_stride;
         const u64 m_cpl = (0x100000000ull + Y.cpl - 1) / Y.cpl, m_eq = (Y.kc + Y.xc) ? (0x100000000ull + (Y.kc + Y.xc) - 1) / (Y.kc + Y.xc) : 0;
+        const u64 m_ch = Y.cpl > 1 ? (0x100000000ull + (Y.cpl - 1) - 1) / (Y.cpl - 1) : 0;
         size_t ctas = (count + 3) / 4;
         const size_t per_sm = smem64 ? (200 * 1024) / smem64 : 6;
-        const size_t cap = (size_t)sms * (per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm));
+        const size_t occ = mont ? 4 : 6;
+        const size_t cap = (size_t)sms * (per_sm < 1 ? 1 : (per_sm > occ ? occ : per_sm));
         if (ctas > cap) ctas = cap;
-        if (mont) k_cells_mulmod64<true><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, m_eqs, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags, d_mtab);
-        else k_cells_mulmod64<false><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, m_eqs, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags, nullptr);
+        if (mont) k_cells_mulmod64<true><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, m_eqs, m_ch, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags, d_mtab);
+        else k_cells_mulmod64<false><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, m_eqs, m_ch, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags, nullptr);
         count_launch();
         return cudaGetLastError();
     }

@@ -58,6 +58,39 @@ def to_mont(x):
     return res
 
 
+def k_words(nx):
+    return words32(pow(2, 256 + 64 * nx, P), 8)
+
+
+def redc_short(x, nx):
+    """fr_redc<NX> of cells.cu: x < 2^(64 nx); T = x * K_nx (nx rows), nx reduction rows with radix 2^(64 nx), result T / 2^(64 nx) < 2p,
+    one conditional subtraction.  Same E/O arrays, same chains, every carry asserted."""
+    assert 0 <= x < 1 << (64 * nx)
+    E, O = Arr(), Arr()
+    kw = k_words(nx)
+    xw = [(x >> (64 * i)) & ((1 << 64) - 1) for i in range(nx)]
+    for i in range(nx):
+        row(E, O, 2 * i, xw[i], kw)
+    cin = 0
+    for i in range(nx):
+        s0 = E.w[2 * i] + O.w[2 * i] + cin
+        s1 = E.w[2 * i + 1] + O.w[2 * i + 1] + (s0 >> 32)
+        Ti = (s0 & M32) | ((s1 & M32) << 32)
+        m = (Ti * INV64) & ((1 << 64) - 1)
+        row(E, O, 2 * i, m, p32)
+        s0 = E.w[2 * i] + O.w[2 * i] + cin
+        s1 = E.w[2 * i + 1] + O.w[2 * i + 1] + (s0 >> 32)
+        assert (s0 & M32) == 0 and (s1 & M32) == 0
+        cin = s1 >> 32
+    res = cin
+    for k in range(8):          # the kernel reads exactly four 64-bit pairs of each array
+        res += (E.w[2 * nx + k] + O.w[2 * nx + k]) << (32 * k)
+    assert all(w == 0 for w in E.w[2 * nx + 8:]) and all(w == 0 for w in O.w[2 * nx + 8:]), "value above the four result words"
+    assert res < 2 * P
+    if res >= P: res -= P
+    return res
+
+
 def self_test(count=3000, seed=5):
     rng = random.Random(seed)
     tests = [0, 1, 2, (1 << 64) - 1, (1 << 64), (1 << 128) - 1, (1 << 135) - 1, (1 << 136) - 1, P - 1]
@@ -65,4 +98,9 @@ def self_test(count=3000, seed=5):
     for x in tests:
         x %= P
         assert to_mont(x) == (x << 256) % P, hex(x)
+    for nx in (1, 2, 3):
+        top = (1 << (64 * nx)) - 1
+        for x in [0, 1, 2, top, top - 1, 1 << (64 * nx - 1)] + [rng.getrandbits(rng.choice([1, 15, 33, 64 * nx - 1, 64 * nx])) for _ in range(count)]:
+            x &= top
+            assert redc_short(x, nx) == (x << 256) % P, (nx, hex(x))
     return len(tests)

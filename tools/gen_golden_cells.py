@@ -2,7 +2,11 @@
 
 The reference holds no fixtures for its cells (layout "parity unpinned"); these pin OUR restatement so that
 the oracle and the GPU kernels cannot drift together unnoticed.  A stream is hashed as SHA-256 over its cells, each written
-as 32 little-endian bytes.  Re-run: `python tools/gen_golden_cells.py`."""
+as 32 little-endian bytes.  Re-run: `python tools/gen_golden_cells.py`.
+
+`python tools/gen_golden_cells.py --dump IDX` writes the cells of flow IDX of the committed fixture, one 32-byte little-endian hex
+line per cell, to stdout: the file to diff against `target/advice_cells_flowIDX.hex` of rust/paillier-b200/tests/mockprover_cells.rs
+(the pin-on-first-toolchain recipe)."""
 import hashlib, json, os, random, sys
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
@@ -17,6 +21,15 @@ def cell_hash(cells):
         h.update(int(c).to_bytes(32, "little"))
     return h.hexdigest()
 
+
+if len(sys.argv) == 3 and sys.argv[1] == "--dump":
+    f = json.load(open(os.path.join(ROOT, "tests", "golden", "cells.json")))["flows"][int(sys.argv[2])]
+    hx = lambda k: int(f[k], 16)
+    ctx = paillier_enc_test(f["enc_bits"], f["limb_bits"], hx("n"), hx("g"), hx("m"), hx("r"), hx("c"), lookup_bits=f["lookup_bits"])
+    assert cell_hash(ctx.cells) == f["sha256"]
+    for c in ctx.cells:
+        print(int(c).to_bytes(32, "little").hex())
+    sys.exit(0)
 
 rng = random.Random(0xCE115)
 out = {"flows": [], "groups": []}
