@@ -430,6 +430,39 @@ def leg_witness_e2e(cx, key, kd, g, n_bits, m_w, r_w, units, dig_ref=None):
             "sink_rehashed_units": state["checked"], "parity": bool(state["ok"] and state["units"] == units)}
 
 
+def leg_decrypt(cx, key, kd, g, n_bits, d_c, m_w, reps=2):
+    """decrypt the ciphertexts the headline step produced (c^lambda mod n^2 on the key's engine, then the L function
+    and the multiplication by mu).  Parity: the round trip must return EVERY plaintext of the batch; a few units against the oracle."""
+    import numpy as np
+    from paillier_halo2_b200.api import private_from_primes, words_to_ints
+    torch = cx.torch
+    units = m_w.shape[0]
+    lam, mu = private_from_primes(kd["p"], kd["q"], g)
+    key.set_private(lam, mu)
+    d_m = torch.empty((units, key.words_in), dtype=torch.int64, device=cx.dev)
+    stream = cx.stream_of(key)
+    key.decrypt_dev(d_c.data_ptr(), units, d_m.data_ptr())
+    cx.barrier()
+    l0 = cx.launches()
+    evs = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); key.decrypt_dev(d_c.data_ptr(), units, d_m.data_ptr()); e1.record(stream)
+        evs.append((e0, e1))
+    cx.barrier()
+    (ms,) = cx.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / len(evs))
+    flags = key.take_flags()
+    got = d_m.cpu().numpy().view(np.uint64)
+    ok = bool((got == m_w).all()) and flags == 0
+    if cx.rank == 0:
+        from oracle.paillier_oracle import paillier_dec_native
+        cs = words_to_ints(d_c[:3].cpu().numpy().view(np.uint64))
+        ok = ok and words_to_ints(got[:3]) == [paillier_dec_native(kd["n"], lam, mu, c) for c in cs]
+    return {"value": cx.world * units / (ms * 1e-3), "unit": "dec/s", "ms_per_launch": ms, "units_per_gpu": units,
+            "gpu_launches": int(cx.launches() - l0), "parity": ok, "parity_units": units,
+            "note": "m = L(c^lambda mod n^2) * mu mod n; round trip of the headline step's ciphertexts, every plaintext compared"}
+
+
 TALLY_TOTAL = 1 << 20
 TALLY_PARTS = 8            # the 2^20 ciphertexts are 8 fixed Philox streams, so the SET is the same for every GPU count
 
@@ -583,7 +616,7 @@ def main():
     ap.add_argument("--g", default="rand", choices=["rand", "std"], help="rand: random g (headline); std: g = n+1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the full-batch CPU witness parity")
     ap.add_argument("--no-witness", action="store_true", help="only the headline encrypt leg (used for ncu captures)")
-    ap.add_argument("--skip", default="", help="comma-separated legs to skip: witness,witness_e2e,tally,cells,witness3072")
+    ap.add_argument("--skip", default="", help="comma-separated legs to skip: witness,witness_e2e,decrypt,tally,cells,witness3072")
     ap.add_argument("--parity-budget", type=float, default=float(os.environ.get("PB200_PARITY_BUDGET_S", "240")),
                     help="seconds of host time the full-batch CPU witness parity may take (units are checked in index order)")
     ap.add_argument("--engine", type=int, default=0)
@@ -610,7 +643,7 @@ def main():
     torch, lib, world, rank, local_rank = cx.torch, cx.lib, cx.world, cx.rank, cx.local_rank
     skip = set(x for x in args.skip.split(",") if x)
     if args.no_witness:
-        skip |= {"witness", "witness_e2e", "tally", "cells", "witness3072"}
+        skip |= {"witness", "witness_e2e", "tally", "cells", "witness3072", "decrypt"}
     kd = workload.load_key(N_BITS)
     g = kd["g_rand"] if args.g == "rand" else kd["g_std"]
     units = args.units
@@ -683,6 +716,8 @@ def main():
         del d_dig, d_cw
         if "witness_e2e" not in skip:
             witness["e2e"] = leg_witness_e2e(cx, key, kd, g, N_BITS, m_w, r_w, 16384, dig)
+    # ---- decryption of the step's ciphertexts
+    decrypt = leg_decrypt(cx, key, kd, g, N_BITS, d_c, m_w) if "decrypt" not in skip else None
     # ---- tally (configs[2]) before the host cores get busy with the parity job: its launches are sub-millisecond
     tally = leg_tally(cx, kd, N_BITS, 10, 3) if "tally" not in skip else None
     # ---- full-batch witness parity on the host cores, in the background while the remaining GPU legs run
@@ -743,6 +778,7 @@ def main():
             "witness": witness,
             "tally": tally,
             "witness3072": witness3072,
+            "decrypt": decrypt,
             "cells": cells,
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC/s (32x32->64 multiply-accumulate)",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get((N_BITS, units)), "peak_source": peak_src,

@@ -49,13 +49,15 @@ typedef enum pb200_status {
     PB200_ERR_NOMEM = -7,
     PB200_ERR_SINK = -8,          /* the witness sink callback returned non-zero */
     PB200_ERR_CONSTRAINT = -9,    /* a supplied (q, rem) does not satisfy a*b = q*n^2 + rem (mul_mod's equality would fail) */
-    PB200_ERR_PEER = -10          /* multi-GPU tally: a peer's partial did not arrive within the kernel's time-out */
+    PB200_ERR_PEER = -10,         /* multi-GPU tally: a peer's partial did not arrive within the kernel's time-out */
+    PB200_ERR_DECRYPT = -11       /* c^lambda mod n^2 is not 1 modulo n: not a valid ciphertext for this key */
 } pb200_status;
 
 /* bits of the per-key device flag word (pb200_key_take_flags) */
 #define PB200_FLAG_RANGE 1u       /* -> PB200_ERR_RANGE */
 #define PB200_FLAG_CONSTRAINT 2u  /* -> PB200_ERR_CONSTRAINT */
 #define PB200_FLAG_PEER_TIMEOUT 4u /* a peer GPU's tally partial did not arrive (pb200_tally_peer_dev / pb200_tally_multi) */
+#define PB200_FLAG_DECRYPT 8u     /* -> PB200_ERR_DECRYPT */
 
 typedef struct pb200_key pb200_key;
 
@@ -150,6 +152,17 @@ typedef struct pb200_ipc_handle { unsigned char bytes[64]; } pb200_ipc_handle;
 int pb200_tally_peer_export(pb200_key* key, pb200_ipc_handle* out);
 int pb200_tally_peer_connect(pb200_key* key, int rank, int world, const pb200_ipc_handle* handles /* world entries */);
 int pb200_tally_peer_dev(pb200_key* key, const uint64_t* d_c_le, size_t count, uint64_t* d_out_le);
+
+/* ---- decryption ---------------------------------------------------------------
+ * The reference states decryption (README.md:5-22 there: m = L(c^lambda mod n^2) * mu mod n, L(x) = (x - 1) / n) and never
+ * implements it; it is the natural end of a tally pipeline (decrypt the product).  pb200_key_set_private attaches the private
+ * part to a key: lambda = lcm(p - 1, q - 1) and mu = L(g^lambda mod n^2)^-1 mod n, words_in words each.  c^lambda runs on the
+ * key's engine (block28: sliding window over the per-key exponent, like r^n), the L function and the multiplication by mu on
+ * 64-bit limbs, one thread per ciphertext.  c: count * words_out words; m_out: count * words_in words.
+ * PB200_ERR_DECRYPT when some c^lambda mod n^2 is not 1 modulo n (that unit's output is zero). */
+int pb200_key_set_private(pb200_key* key, const uint64_t* lambda_le, const uint64_t* mu_le);
+int pb200_decrypt_batch(pb200_key* key, const uint64_t* c_le, size_t count, uint64_t* m_out_le);
+int pb200_decrypt_batch_dev(pb200_key* key, const uint64_t* d_c_le, size_t count, uint64_t* d_m_out_le);
 
 /* ---- witness --------------------------------------------------------------------------------
  * Replaces: the witness generation inside BigUintChip::pow_mod_fixed_exp / mul_mod that

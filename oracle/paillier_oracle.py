@@ -493,3 +493,12 @@ def encrypt_steps(n: int, g: int, m: int, r: int) -> Tuple[int, List[MulModStep]
     rn, s2 = pow_chain_steps(r, n, n2)
     q, c = divmod(gm * rn, n2)
     return c, s1 + s2 + [MulModStep("final", gm, rn, q, c)]
+
+
+def paillier_dec_native(n: int, lam: int, mu: int, c: int) -> int:
+    """Decryption as the reference's README states it (README.md:17-22 there; its code has no decryption):
+    m = L(c^lambda mod n^2) * mu mod n with L(x) = (x - 1) / n.  Raises if c is not a valid ciphertext (x != 1 mod n)."""
+    x = pow(c, lam, n * n)
+    if (x - 1) % n:
+        raise ValueError("c^lambda mod n^2 is not 1 modulo n")
+    return ((x - 1) // n) * mu % n

@@ -22,7 +22,8 @@ PB200_ERR_NOMEM = -7
 PB200_ERR_SINK = -8
 PB200_ERR_CONSTRAINT = -9
 PB200_ERR_PEER = -10
-PB200_FLAG_RANGE, PB200_FLAG_CONSTRAINT, PB200_FLAG_PEER_TIMEOUT = 1, 2, 4
+PB200_ERR_DECRYPT = -11
+PB200_FLAG_RANGE, PB200_FLAG_CONSTRAINT, PB200_FLAG_PEER_TIMEOUT, PB200_FLAG_DECRYPT = 1, 2, 4, 8
 
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
@@ -72,6 +73,9 @@ SYMBOLS = {
     "pb200_tally_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pb200_tally_peer_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "pb200_tally_peer_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pb200_key_set_private": (C.c_int, [C.c_void_p, u64p, u64p]),
+    "pb200_decrypt_batch": (C.c_int, [C.c_void_p, u64p, C.c_size_t, u64p]),
+    "pb200_decrypt_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "pb200_encrypt_witness_batch": (C.c_int, [C.c_void_p, u64p, u64p, C.c_size_t, u64p, C.c_size_t, SINK_FN, C.c_void_p]),
     "pb200_witness_records_for": (C.c_uint64, [C.c_void_p, u64p]),
     "pb200_encrypt_witness_digest": (C.c_int, [C.c_void_p, u64p, u64p, C.c_size_t, u64p, u64p]),

@@ -326,6 +326,30 @@ class PaillierKey(CellMixin):
         c_w = ints_to_words(cs, self.words_out) if len(cs) else np.empty((0, self.words_out), dtype="<u8")
         return words_to_ints(self.tally_words(c_w))[0]
 
+    # -- decryption -----------------------------------------------------------------------------------
+    def set_private(self, lam: int, mu: int) -> None:
+        """lambda = lcm(p-1, q-1), mu = L(g^lambda mod n^2)^-1 mod n (private_from_primes gives both)."""
+        try:
+            a, b = ints_to_words([lam], self.words_in), ints_to_words([mu], self.words_in)
+        except OverflowError:
+            raise Pb200Error(_lib.PB200_ERR_RANGE, "set_private")
+        check(self._lib.pb200_key_set_private(self._h, _p(a), _p(b)), "pb200_key_set_private")
+
+    def decrypt_words(self, c_w: np.ndarray) -> np.ndarray:
+        c_w = np.ascontiguousarray(c_w, dtype="<u8").reshape(-1, self.words_out)
+        out = np.empty((c_w.shape[0], self.words_in), dtype="<u8")
+        check(self._lib.pb200_decrypt_batch(self._h, _p(c_w) if c_w.shape[0] else None, c_w.shape[0], _p(out)), "pb200_decrypt_batch")
+        return out
+
+    def decrypt(self, cs: Sequence[int]) -> List[int]:
+        """m_i = L(c_i^lambda mod n^2) * mu mod n for every ciphertext."""
+        if not len(cs):
+            return []
+        return words_to_ints(self.decrypt_words(ints_to_words(cs, self.words_out)))
+
+    def decrypt_dev(self, d_c: int, count: int, d_m: int) -> None:
+        check(self._lib.pb200_decrypt_batch_dev(self._h, d_c, count, d_m), "pb200_decrypt_batch_dev")
+
     # -- witness ------------------------------------------------------------------------------
     def g_chain(self) -> List[Tuple[int, int]]:
         """Per-key records (q, rem) of the g-chain squarings, i < enc_bits."""
@@ -420,3 +444,13 @@ def witness_digest(records: Iterable[Tuple[int, int]], words_out: int) -> int:
                 c = (c * DIGEST_C) & MASK64
         d = ((d ^ h) * DIGEST_PRIME) & MASK64
     return d
+
+
+def private_from_primes(p: int, q: int, g: int):
+    """(lambda, mu) of the Paillier key n = p*q, g: lambda = lcm(p-1, q-1), mu = L(g^lambda mod n^2)^-1 mod n.  Host-side key
+    material preparation (a handful of big-integer operations per KEY, not per ciphertext)."""
+    from math import gcd
+    n = p * q
+    lam = (p - 1) * (q - 1) // gcd(p - 1, q - 1)
+    x = pow(g, lam, n * n)
+    return lam, pow((x - 1) // n, -1, n)

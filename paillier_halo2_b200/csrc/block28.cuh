@@ -579,7 +579,9 @@ __device__ __noinline__ void phase_mma(int4* smem_base) {
     const int g = lane >> 2, t = lane & 3;
     constexpr int P_BASE = HIGH ? 4 * (L - 2) : 0;
     constexpr int NP = HIGH ? C::NP_HIGH : C::NP_LOW;
-    constexpr int NQ = (NP + 1) / 2, NQW = (NQ + G - 1) / G;
+    // dealing: RQ full rounds in which every warp takes a quad, then one tail round for the R < 2G pairs left: R - G warps take a
+    // quad and the others a single pair (R > G), or R warps take a single pair — no warp ever holds more than ceil(NP / G) pairs
+    constexpr int RQ = NP / (2 * G), R = NP - 2 * G * RQ, NROUNDS = RQ + (R > 0 ? 1 : 0), TQ = R > G ? R - G : 0;
     constexpr int NOUT = HIGH ? L + 2 : L;
     // ldmatrix.x4 row addresses: lanes 0-7 rows 0-7 (k bytes 0-15), 8-15 rows 8-15, 16-23 rows 0-7 (+16), 24-31 rows 8-15 (+16)
     const unsigned as_base = (unsigned)__cvta_generic_to_shared(as_ptr<C>(S)) + ((lane & 7) + ((lane >> 3) & 1) * 8) * C::RS + (lane >> 4) * 16;
@@ -610,13 +612,14 @@ __device__ __noinline__ void phase_mma(int4* smem_base) {
         }
     };
 #pragma unroll 1
-    for (int q = 0; q < NQW; q++) {
-        // quads are dealt to the warps in serpentine order (the k-steps of a quad grow (phase C) or shrink (phase B) linearly
-        // with its index and the phase ends at a CTA barrier)
-        const int Qi = ((q & 1) ? (G - 1 - warp) : warp) + q * G;
-        if (Qi >= NQ) continue;
-        const int U = 2 * Qi;
-        const bool two = U + 1 < NP;                 // the last quad of an odd NP holds one tile pair
+    for (int q = 0; q < NROUNDS; q++) {
+        // serpentine order over the rounds (the k-steps of a tile pair grow (phase C) or shrink (phase B) linearly with its index and
+        // the phase ends at a CTA barrier)
+        const int ws = (q & 1) ? (G - 1 - warp) : warp;
+        int U; bool two;
+        if (q < RQ) { U = 2 * (q * G + ws); two = true; }
+        else if (ws < TQ) { U = 2 * G * RQ + 2 * ws; two = true; }
+        else { U = 2 * G * RQ + 2 * TQ + (ws - TQ); two = false; if (U >= NP) continue; }
         const int P0 = P_BASE + 16 * U;
         // k-steps with some (k, p): 0 <= p - k <= K7-1, k in [32ks, 32ks+32), p in [P0, P0+32)
         int ks_lo = (P0 - (K7 - 1)) / 32; if (P0 - (K7 - 1) <= 0) ks_lo = 0;

@@ -342,6 +342,49 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K
     if (threadIdx.x == 0) slot_release(pool, slot);
 }
 
+// out = base^e mod n^2 for a per-key exponent e: the r-chain of k_encrypt (odd-power table in the CTA's scratch slot, sliding-window
+// schedule computed once per key) with its own schedule.  Decryption's c^lambda mod n^2.
+struct PowSched { const int2* ops; int n_ops; int first_idx; };
+template <class C, bool MMA>
+__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_pow(B28Dev K, PowSched E, const u64* __restrict__ base, int base_words,
+                                                                    size_t count, u64* __restrict__ out, int4* scratch, SlotPool pool) {
+    extern __shared__ int4 smem[];
+    __shared__ int s_slot;
+    Smem<C> S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_slot = slot_acquire(pool);
+    load_consts<C>(smem, K);
+    const int slot = s_slot;
+    size_t unit = (size_t)blockIdx.x * 32 + lane;
+    const bool active = unit < count;
+    if (!active) unit = count - 1;
+    int4* tab = scratch + (size_t)slot * SCRATCH_ENTRIES * C::VAL4;
+    load_value<C>(S.V, base + unit * base_words, base_words, role, lane);
+    copy_to_global<C>(tab, S.V, role, lane);                                        // tab[0] = x
+    mulmod<C, true, MMA>(S, nullptr, role, lane);                                   // x^2
+    copy_to_global<C>(tab + (size_t)TABN * C::VAL4, S.V, role, lane);
+    __syncthreads();
+    copy_from_global<C>(S.V, tab, role, lane);
+    for (int j = 1; j < TABN; j++) {
+        copy_from_global<C>(S.B, tab + (size_t)TABN * C::VAL4, role, lane);
+        mulmod<C, false, MMA>(S, S.B, role, lane);                                  // x^(2j+1)
+        copy_to_global<C>(tab + (size_t)j * C::VAL4, S.V, role, lane);
+    }
+    __syncthreads();
+    if (E.first_idx < 0) set_one<C>(S.V, role, lane);                               // e == 0
+    else copy_from_global<C>(S.V, tab + (size_t)E.first_idx * C::VAL4, role, lane);
+    for (int o = 0; o < E.n_ops; o++) {
+        const int2 op = E.ops[o];
+        for (int s_ = 0; s_ < op.x; s_++) mulmod<C, true, MMA>(S, nullptr, role, lane);
+        if (op.y >= 0) {
+            copy_from_global<C>(S.B, tab + (size_t)op.y * C::VAL4, role, lane);
+            mulmod<C, false, MMA>(S, S.B, role, lane);
+        }
+    }
+    finalize<C, MMA>(S, K, out + unit * K.words_out, active, role, lane);
+    if (threadIdx.x == 0) slot_release(pool, slot);
+}
+
 // ---- tally: the N-ary fold of paillier_add_native (/root/reference/src/paillier.rs:94-97) in ONE launch per GPU -------------------
 // 1. every lane of every CTA folds a strided subset of the inputs (main loop, all lanes useful);
 // 2. the CTAs fold pairwise up a binary tree by "last arriver continues": a CTA stores its 32 lane values in its node slot, bumps
@@ -352,7 +395,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K
 //    memory, then a release flag at system scope), waits for the peers' partials in its own mailbox, folds the `world` partials
 //    (3 steps at 8 GPUs) and canonicalises again — every GPU ends with the full product, no host hop and no second launch.
 constexpr int TALLY_MAXW = 8;                          // GPUs of one NVSwitch domain
-constexpr int MAIL_WORDS = 128;                        // one partial: up to 2*4096/64 words
+constexpr int MAIL_WORDS = 160;                        // one partial as lazy digits: ENTRY4 int4 = up to 16 blocks x 5 chunks x 16 B = 1280 B
 constexpr size_t MAIL_FLAG_OFF = (size_t)2 * TALLY_MAXW * MAIL_WORDS;      // u64 index of flags[parity][src]
 constexpr size_t MAIL_U64 = MAIL_FLAG_OFF + 2 * TALLY_MAXW;
 struct TallyPeer {
@@ -437,16 +480,16 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, 
     // ---- 3. the surviving CTA: fold its lanes, canonical partial
     fold_lanes<C, MMA>(S, 32, role, lane);
     if (P.world <= 1) { finalize<C, MMA>(S, K, out, lane == 0, role, lane); return; }
-    // ---- 4. exchange over peer memory and combine
+    // ---- 4. exchange over peer memory and combine.  What crosses NVLink is lane 0's LAZY value (strict digits, ENTRY4 int4): the
+    // receivers multiply digit arrays directly, so neither a canonicalisation before the exchange nor a digit conversion after it
     const int par = (int)(P.epoch & 1);
-    u64* mine = P.mail[P.rank] + ((size_t)par * TALLY_MAXW + P.rank) * MAIL_WORDS;
-    finalize<C, MMA>(S, K, mine, lane == 0, role, lane);
-    __threadfence();
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < (P.world - 1) * K.words_out; idx += C::THREADS) {
-        int peer = idx / K.words_out; const int w = idx - peer * K.words_out;
-        if (peer >= P.rank) peer++;
-        P.mail[peer][((size_t)par * TALLY_MAXW + P.rank) * MAIL_WORDS + w] = __ldcg(mine + w);
+    {
+        const int4* v0 = S.V;                                   // lane 0's chunks: S.V[(block * CH + chunk) * 32 + 0]
+        for (int idx = threadIdx.x; idx < P.world * C::ENTRY4; idx += C::THREADS) {
+            const int peer = idx / C::ENTRY4, e = idx - peer * C::ENTRY4;
+            int4* dst = reinterpret_cast<int4*>(P.mail[peer] + ((size_t)par * TALLY_MAXW + P.rank) * MAIL_WORDS) + e;
+            *dst = v0[e * 32];
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -467,25 +510,9 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, 
     __syncthreads();
     {
         const int src = lane < P.world ? lane : P.world - 1;
-        const u64* w = P.mail[P.rank] + ((size_t)par * TALLY_MAXW + src) * MAIL_WORDS;
-        int a[C::CH * 4];
-        int carry = 0;
+        const int4* e = reinterpret_cast<const int4*>(P.mail[P.rank] + ((size_t)par * TALLY_MAXW + src) * MAIL_WORDS);
 #pragma unroll
-        for (int k = 0; k < C::BL; k++) {
-            const int bit = W * (role * C::BL + k);
-            const int wi = bit >> 6, sh = bit & 63;
-            const u64 lo = wi < K.words_out ? __ldcg(w + wi) : 0, hi = wi + 1 < K.words_out ? __ldcg(w + wi + 1) : 0;
-            const u64 v = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
-            const int t = (int)(v & ((1u << W) - 1)) + carry;
-            const int d = sgxt28(t);
-            carry = (t - d) >> W;
-            a[k] = d;
-        }
-#pragma unroll
-        for (int k = C::BL; k < C::CH * 4; k++) a[k] = 0;
-        store_block<C>(blk_ptr<C>(S.V, role, lane), a);
-        __syncthreads();
-        if (role + 1 < C::G) ((int*)blk_ptr<C>(S.V, role + 1, lane))[0] += carry;
+        for (int c = 0; c < C::CH; c++) S.V[(role * C::CH + c) * 32 + lane] = __ldcg(e + role * C::CH + c);
         __syncthreads();
     }
     set_one_where<C>(S.V, lane >= P.world, role, lane);
@@ -729,6 +756,8 @@ struct Block28Key {
     TallyPeer peer{};                                        // world <= 1 until block28_tally_peer_connect
     void* ipc_opened[TALLY_MAXW] = {};                       // peer mailboxes opened with cudaIpcOpenMemHandle
     int device = 0;
+    int2* d_pow_ops = nullptr; PowSched pow{};               // decryption exponent (block28_pow_prepare)
+    bool pow_ready = false;
     int sms = 148;
     uint64_t n_sqr = 0, n_mul = 0;   // modular squarings / multiplications per encryption
     bool use_mma = true;             // constant-operand phases on the tensor pipe (engine 3) or on IMAD (engine 2)
@@ -772,6 +801,25 @@ static void to_rtab(const std::vector<int>& entry, std::vector<int>& out_words) 
     memcpy(out_words.data(), tab.data(), tab.size());
 }
 
+// left-to-right sliding window (width WIN) over a fixed exponent: returns the table index the chain starts from (-1 for e == 0)
+// and the list of (squarings, table index to multiply by or -1)
+static int window_schedule(const BigInt& e, std::vector<int2>& ops) {
+    int first_idx = -1;
+    int i = (int)e.bits() - 1, pending = 0; bool first = true;
+    while (i >= 0) {
+        if (!e.bit(i)) { pending++; i--; continue; }
+        int j = i - WIN + 1; if (j < 0) j = 0;
+        while (!e.bit(j)) j++;
+        int val = 0; for (int b = i; b >= j; b--) val = (val << 1) | (e.bit(b) ? 1 : 0);
+        int len = i - j + 1;
+        if (first) { first_idx = (val - 1) / 2; first = false; }
+        else ops.push_back(make_int2(pending + len, (val - 1) / 2));
+        pending = 0; i = j - 1;
+    }
+    if (pending) ops.push_back(make_int2(pending, -1));
+    return first_idx;
+}
+
 #define CUK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { *cuda_err = e_; block28_destroy(key); return nullptr; } } while (0)
 
 template <class C>
@@ -801,21 +849,7 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     CUK(cudaMemcpyAsync(key->d_consts, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     // sliding-window schedule for the exponent n
     std::vector<int2> ops;
-    int first_idx = 0;
-    {
-        int i = (int)n.bits() - 1, pending = 0; bool first = true;
-        while (i >= 0) {
-            if (!n.bit(i)) { pending++; i--; continue; }
-            int j = i - WIN + 1; if (j < 0) j = 0;
-            while (!n.bit(j)) j++;
-            int val = 0; for (int b = i; b >= j; b--) val = (val << 1) | (n.bit(b) ? 1 : 0);
-            int len = i - j + 1;
-            if (first) { first_idx = (val - 1) / 2; first = false; }
-            else ops.push_back(make_int2(pending + len, (val - 1) / 2));
-            pending = 0; i = j - 1;
-        }
-        if (pending) ops.push_back(make_int2(pending, -1));
-    }
+    int first_idx = window_schedule(n, ops);
     int comb_bits = n_bits >= 1024 ? 12 : 8;
     if (const char* e = getenv("PB200_COMB_BITS")) { int v = atoi(e); if (v >= 4 && v <= 16) comb_bits = v; }
     const int n_windows = (int)((n_bits + comb_bits - 1) / comb_bits);
@@ -867,7 +901,7 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
 #define CUW(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
 
 template <class C>
-static cudaError_t encrypt_cfg(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st) {
+static cudaError_t ensure_slots(Block28Key* key, cudaStream_t st) {
     if (!key->d_scratch) {
         // slots = SM ids x resident CTAs per SM (occupancy of the kernel as compiled), independent of the batch size
         unsigned* d_n = nullptr; unsigned h_n = 0;
@@ -886,10 +920,29 @@ static cudaError_t encrypt_cfg(Block28Key* key, const u64* d_m, const u64* d_r, 
         CUW(cudaMalloc(&key->d_scratch, slots * SCRATCH_ENTRIES * C::VAL4 * sizeof(int4)));
         key->scratch_slots = slots;
     }
+    return cudaSuccess;
+}
+
+template <class C>
+static cudaError_t encrypt_cfg(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st) {
+    CUW(ensure_slots<C>(key, st));
     const SlotPool pool{key->d_slot_masks, key->enc_per_sm};
     const size_t ctas = (count + 31) / 32;
     if (key->use_mma) k_encrypt<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
     else k_encrypt<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <class C>
+static cudaError_t pow_cfg(Block28Key* key, const u64* d_base, int base_words, size_t count, u64* d_out, cudaStream_t st) {
+    CUW(ensure_slots<C>(key, st));
+    CUW((cudaFuncSetAttribute(k_pow<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    CUW((cudaFuncSetAttribute(k_pow<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    const SlotPool pool{key->d_slot_masks, key->enc_per_sm};
+    const size_t ctas = (count + 31) / 32;
+    if (key->use_mma) k_pow<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->pow, d_base, base_words, count, d_out, key->d_scratch, pool);
+    else k_pow<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->pow, d_base, base_words, count, d_out, key->d_scratch, pool);
     count_launch();
     return cudaGetLastError();
 }
@@ -1022,6 +1075,7 @@ void block28_destroy(Block28Key* key) {
     if (key->d_gwords) cudaFree(key->d_gwords);
     if (key->d_scratch) cudaFree(key->d_scratch);
     if (key->d_slot_masks) cudaFree(key->d_slot_masks);
+    if (key->d_pow_ops) cudaFree(key->d_pow_ops);
     if (key->d_nodes) cudaFree(key->d_nodes);
     if (key->d_node_cnt) cudaFree(key->d_node_cnt);
     for (int i = 0; i < TALLY_MAXW; i++) if (key->ipc_opened[i]) cudaIpcCloseMemHandle(key->ipc_opened[i]);
@@ -1046,6 +1100,26 @@ cudaError_t block28_encrypt(Block28Key* key, const u64* d_m, const u64* d_r, siz
     if (key->BL == 14) return encrypt_cfg<Cfg3072>(key, d_m, d_r, count, d_c, st);
     return encrypt_cfg<Cfg4096>(key, d_m, d_r, count, d_c, st);
 }
+cudaError_t block28_pow_prepare(Block28Key* key, const BigInt& e, cudaStream_t st) {
+    std::vector<int2> ops;
+    const int first_idx = window_schedule(e, ops);
+    if (key->d_pow_ops) { cudaFree(key->d_pow_ops); key->d_pow_ops = nullptr; }
+    CUW(cudaMalloc(&key->d_pow_ops, (ops.size() + 1) * sizeof(int2)));
+    if (!ops.empty()) CUW(cudaMemcpyAsync(key->d_pow_ops, ops.data(), ops.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    CUW(cudaStreamSynchronize(st));
+    key->pow.ops = key->d_pow_ops; key->pow.n_ops = (int)ops.size(); key->pow.first_idx = first_idx;
+    key->pow_ready = true;
+    return cudaSuccess;
+}
+cudaError_t block28_pow(Block28Key* key, const u64* d_base, int base_words, size_t count, u64* d_out, cudaStream_t st) {
+    if (!count) return cudaSuccess;
+    if (!key->pow_ready) return cudaErrorInvalidValue;
+    if (key->G == 4) return pow_cfg<Cfg1024>(key, d_base, base_words, count, d_out, st);
+    if (key->G == 8) return pow_cfg<Cfg2048>(key, d_base, base_words, count, d_out, st);
+    if (key->BL == 14) return pow_cfg<Cfg3072>(key, d_base, base_words, count, d_out, st);
+    return pow_cfg<Cfg4096>(key, d_base, base_words, count, d_out, st);
+}
+
 static cudaError_t tally_dispatch(Block28Key* key, const u64* d_c, size_t count, u64* d_out, bool collective, cudaStream_t st) {
     if (key->G == 4) return tally_cfg<Cfg1024>(key, d_c, count, d_out, collective, st);
     if (key->G == 8) return tally_cfg<Cfg2048>(key, d_c, count, d_out, collective, st);

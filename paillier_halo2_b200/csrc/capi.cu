@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 
@@ -75,6 +76,8 @@ struct pb200_key {
     DevBuf cin_a, cin_b, cin_q, cin_r;
     int sms = 148;
     std::vector<pb200_key*> group;          // pb200_tally_multi: the peer group this key is connected to (single process)
+    // private part (pb200_key_set_private): constants of the modulus n with mu in their g slot, lambda's words for the simple pow
+    SimpleConsts* d_simple_n = nullptr; u64* d_lambda = nullptr; int lambda_bits = 0; bool has_private = false;
     // witness delivery pipeline (pb200_encrypt_witness_batch): created on first use
     struct Pipe {
         static const int NS = 4;             // pinned staging slots
@@ -102,6 +105,7 @@ const char* pb200_strerror(int s) {
         case PB200_ERR_NOMEM: return "out of memory";
         case PB200_ERR_SINK: return "witness sink aborted";
         case PB200_ERR_PEER: return "a peer GPU's tally partial did not arrive (every rank of the group must make the same call)";
+        case PB200_ERR_DECRYPT: return "not a valid ciphertext for this key: c^lambda mod n^2 is not 1 modulo n";
         case PB200_ERR_CONSTRAINT: return "(q, rem) do not satisfy a*b = q*n^2 + rem (the chip's equality constraint fails)";
         default: return "unknown status";
     }
@@ -175,6 +179,8 @@ void pb200_key_destroy(pb200_key* k) {
     if (k->d_simple) cudaFree(k->d_simple);
     if (k->d_gchain) cudaFree(k->d_gchain);
     if (k->d_flags) cudaFree(k->d_flags);
+    if (k->d_simple_n) cudaFree(k->d_simple_n);
+    if (k->d_lambda) cudaFree(k->d_lambda);
     k->in_a.release(); k->in_b.release(); k->out_a.release(); k->out_b.release(); k->scratch.release(); k->offs.release();
     k->cin_a.release(); k->cin_b.release(); k->cin_q.release(); k->cin_r.release();
     if (k->pipe.ready) {
@@ -247,7 +253,8 @@ static int take_flags(pb200_key* k) {
     int f = 0;
     int rc = read_flags(k, &f); if (rc) return rc;
     if (f & PB200_FLAG_CONSTRAINT) return PB200_ERR_CONSTRAINT;
-    if (f & ~PB200_FLAG_CONSTRAINT) return PB200_ERR_RANGE;
+    if (f & PB200_FLAG_DECRYPT) return PB200_ERR_DECRYPT;
+    if (f & ~(PB200_FLAG_CONSTRAINT | PB200_FLAG_DECRYPT)) return PB200_ERR_RANGE;
     return PB200_OK;
 }
 int pb200_key_take_flags(pb200_key* k, uint32_t* flags_out) try {
@@ -515,6 +522,63 @@ int pb200_tally_multi(pb200_key* const* keys, int n_gpus, const uint64_t* const*
         int rc = take_flags(keys[i]); if (rc) return rc;
     }
     return pb200_tally(keys[0], partials.data(), (size_t)n_gpus, out);
+} PB200_CATCH
+
+// ---- decryption -----------------------------------------------------------------------------------------
+int pb200_key_set_private(pb200_key* k, const uint64_t* lambda_le, const uint64_t* mu_le) try {
+    if (!k || !lambda_le || !mu_le) return PB200_ERR_INVALID_ARG;
+    if (!fits(lambda_le, k->words_in, k->n_bits) || !fits(mu_le, k->words_in, k->n_bits)) return PB200_ERR_RANGE;
+    USE_DEVICE(k);
+    CU(cudaStreamSynchronize(k->stream));
+    const uint32_t win = k->words_in;
+    BigInt lambda = BigInt::from_u64_le(lambda_le, win), mu = BigInt::from_u64_le(mu_le, win);
+    std::unique_ptr<SimpleConsts> h(new SimpleConsts());
+    memset(h.get(), 0, sizeof(SimpleConsts));
+    h->k = (int)win; h->kin = (int)win; h->n_bits = (int)k->n_bits; h->exp_bits = 0;
+    h->s = (int)(64 * win - k->n.bits());
+    BigInt Nt = BigInt::shl(k->n, h->s);
+    BigInt bmu = BigInt::div(BigInt::pow2(128 * (size_t)win), Nt);
+    Nt.to_u64_le(h->Nt, win); bmu.to_u64_le(h->mu, win + 1);
+    k->n.to_u64_le(h->n, win);
+    BigInt::mod(mu, k->n).to_u64_le(h->g, win);                 // the L-function kernel multiplies by this slot
+    if (!k->d_simple_n) CU(cudaMalloc(&k->d_simple_n, sizeof(SimpleConsts)));
+    if (!k->d_lambda) CU(cudaMalloc(&k->d_lambda, win * sizeof(u64)));
+    CU(cudaMemcpyAsync(k->d_simple_n, h.get(), sizeof(SimpleConsts), cudaMemcpyHostToDevice, k->stream));
+    CU(cudaMemcpyAsync(k->d_lambda, lambda_le, win * sizeof(u64), cudaMemcpyHostToDevice, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    k->lambda_bits = (int)lambda.bits();
+    if (k->fast) CU(block28_pow_prepare(k->fast, lambda, k->stream));
+    k->has_private = true;
+    return PB200_OK;
+} PB200_CATCH
+
+int pb200_decrypt_batch_dev(pb200_key* k, const uint64_t* d_c, size_t count, uint64_t* d_m) try {
+    if (!k || (count && (!d_c || !d_m))) return PB200_ERR_INVALID_ARG;
+    if (!k->has_private) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    USE_DEVICE(k);
+    CU(k->scratch.reserve(count * k->words_out * sizeof(u64)));
+    u64* d_x = (u64*)k->scratch.p;                               // x = c^lambda mod n^2
+    if (use_fast(k)) CU(block28_pow(k->fast, (const u64*)d_c, (int)k->words_out, count, d_x, k->stream));
+    else CU(simple_pow(k->d_simple, (const u64*)d_c, (int)k->words_out, k->d_lambda, k->lambda_bits, count, d_x, k->d_flags, k->stream));
+    CU(simple_lfunc(k->d_simple_n, d_x, count, (u64*)d_m, k->d_flags, k->stream));
+    return PB200_OK;
+} PB200_CATCH
+
+int pb200_decrypt_batch(pb200_key* k, const uint64_t* c, size_t count, uint64_t* m_out) try {
+    if (!k || (count && (!c || !m_out))) return PB200_ERR_INVALID_ARG;
+    if (!k->has_private) return PB200_ERR_INVALID_ARG;
+    if (!count) return PB200_OK;
+    USE_DEVICE(k);
+    { int rc0_ = clear_flags(k); if (rc0_) return rc0_; }
+    const size_t bin = count * k->words_out * sizeof(u64), bout = count * k->words_in * sizeof(u64);
+    CU(k->in_a.reserve(bin)); CU(k->out_a.reserve(bout));
+    CU(cudaMemcpyAsync(k->in_a.p, c, bin, cudaMemcpyHostToDevice, k->stream));
+    int rc = pb200_decrypt_batch_dev(k, (const uint64_t*)k->in_a.p, count, (uint64_t*)k->out_a.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(m_out, k->out_a.p, bout, cudaMemcpyDeviceToHost, k->stream));
+    CU(cudaStreamSynchronize(k->stream));
+    return take_flags(k);
 } PB200_CATCH
 
 // ---- witness --------------------------------------------------------------------------------

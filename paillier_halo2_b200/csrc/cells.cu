@@ -197,6 +197,9 @@ __device__ __constant__ unsigned FR_K32[3][8] = {
     {0xc177f51au, 0x5665c3b5u, 0xde75c713u, 0x00e7f02au, 0x2f747168u, 0xb09192e5u, 0xcccdc65du, 0x0621c0bbu}};
 template <int NX>
 __device__ __noinline__ W4 fr_redc(u64 x0, u64 x1, u64 x2) {
+#ifdef PB200_CELLS_FAKE_REDC      // experiment only (tools/build_variant.py): how much of the kernel is the conversion arithmetic
+    { W4 f; f.w[0] = x0; f.w[1] = x1; f.w[2] = x2; f.w[3] = NX; return f; }
+#endif
     unsigned E[2 * NX + 12], O[2 * NX + 12];
 #pragma unroll
     for (int k = 0; k < 2 * NX + 12; k++) { E[k] = 0; O[k] = 0; }
@@ -337,11 +340,55 @@ __device__ __forceinline__ void store_chunk(u64* out, size_t cell, W4 v, const u
     else store_cell_k<false>(out, cell, v, CK_RAW);
 }
 
+// x * R mod p for a 32-bit x, branch-free and without memory: v * C with C = R mod p (nine words), the quotient by p estimated as
+// q-hat = (v * floor(2^32 C / p)) >> 32 — exact or one low, because C / p - M / 2^32 < 2^-32 and v < 2^32 — then v C - q-hat p in [0, 2p)
+// and one conditional subtraction.  Eight + eight 32 x 32 products on independent register pairs (even / odd word offsets), no table.
+// The range-check chunks are 60 % of the cells: as table gathers they cost two 32-sector L1 wavefront bursts per 32 cells and the
+// kernel sat on the LSU data pipe (64 % busy, profiles/ncu_k_cells_r02_mont_first_summary.txt); as arithmetic they cost ~60 instructions.
+#define FR_CM32 0x4a474626u          // floor(2^32 (R mod p) / p)
+__device__ __forceinline__ void mul8_u32(u64 (&t)[4], unsigned v, const unsigned (&c)[8]) {     // t = v * c mod 2^256 (the 9th word is not needed)
+    const u64 e0 = (u64)v * c[0], e1 = (u64)v * c[2], e2 = (u64)v * c[4], e3 = (u64)v * c[6];
+    const u64 o0 = (u64)v * c[1], o1 = (u64)v * c[3], o2 = (u64)v * c[5], o3 = (u64)v * c[7];
+    // T = E + (O << 32)
+    const u64 s0 = o0 << 32, s1 = (o0 >> 32) | (o1 << 32), s2 = (o1 >> 32) | (o2 << 32), s3 = (o2 >> 32) | (o3 << 32);
+    asm("add.cc.u64 %0, %4, %8; addc.cc.u64 %1, %5, %9; addc.cc.u64 %2, %6, %10; addc.u64 %3, %7, %11;"
+        : "=l"(t[0]), "=l"(t[1]), "=l"(t[2]), "=l"(t[3]) : "l"(e0), "l"(e1), "l"(e2), "l"(e3), "l"(s0), "l"(s1), "l"(s2), "l"(s3));
+}
+__device__ __forceinline__ W4 fr_mont_u32(unsigned v) {
+#ifdef PB200_CELLS_FAKE_CHUNK     // experiment only
+    { W4 f = w4_zero(); f.w[0] = v; return f; }
+#endif
+    unsigned c[8], pw[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { c[2 * k] = (unsigned)FR_R1[k]; c[2 * k + 1] = (unsigned)(FR_R1[k] >> 32); pw[k] = FR_P32[k]; pw[k + 4] = FR_P32[k + 4]; }
+    const unsigned qh = __umulhi(v, FR_CM32);
+    u64 t[4], u[4];
+    mul8_u32(t, v, c);
+    mul8_u32(u, qh, pw);
+    // r = t - u (mod 2^256; the true value is in [0, 2p) < 2^255), then r - p if that is not negative
+    u64 r0, r1, r2, r3, d0, d1, d2, d3, bw;
+    asm("sub.cc.u64 %0, %4, %8; subc.cc.u64 %1, %5, %9; subc.cc.u64 %2, %6, %10; subc.u64 %3, %7, %11;"
+        : "=l"(r0), "=l"(r1), "=l"(r2), "=l"(r3) : "l"(t[0]), "l"(t[1]), "l"(t[2]), "l"(t[3]), "l"(u[0]), "l"(u[1]), "l"(u[2]), "l"(u[3]));
+    asm("sub.cc.u64 %0, %5, %9; subc.cc.u64 %1, %6, %10; subc.cc.u64 %2, %7, %11; subc.cc.u64 %3, %8, %12; subc.u64 %4, 0, 0;"
+        : "=l"(d0), "=l"(d1), "=l"(d2), "=l"(d3), "=l"(bw) : "l"(r0), "l"(r1), "l"(r2), "l"(r3), "l"(FR_P[0]), "l"(FR_P[1]), "l"(FR_P[2]), "l"(FR_P[3]));
+    W4 o;
+    o.w[0] = bw ? r0 : d0; o.w[1] = bw ? r1 : d1; o.w[2] = bw ? r2 : d2; o.w[3] = bw ? r3 : d3;
+    return o;
+}
+
 // Four chunk cells per lane and pass: the Montgomery forms are 32-byte gathers from the L2-resident table, and with one gather per
 // pass the kernel sat on their latency (profiles/ncu_k_cells_r02_mont_summary.txt: long-scoreboard 2.4 stall cycles per issue at 16
 // warps per SM).  All eight loads of a pass are issued before the first store.
 template <bool MONT>
 __device__ __forceinline__ void store_chunks4(u64* out, const size_t (&cell)[4], const u64 (&ch)[4], const bool (&ok)[4], const u64* __restrict__ mtab) {
+#ifdef PB200_CELLS_CHUNK_COMPUTE
+    if (MONT) {          // A/B variant: computed instead of gathered (measured 2.68 ms against 2.53 ms per 2^16 groups: not the default)
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (ok[u]) store_cell_k<true>(out, cell[u], fr_mont_u32((unsigned)ch[u]), CK_RAW);
+        return;
+    }
+#endif
     if (MONT && mtab) {
         ulonglong2 a[4], b[4];
 #pragma unroll
@@ -518,8 +565,11 @@ __device__ __forceinline__ void mac64(Acc192& A, u64 a, u64 b) {
     asm("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;" : "+r"(A.o1), "+r"(A.o2), "+r"(A.o3) : "r"(a1), "r"(b0));
 }
 
+#ifndef PB200_CELLS_MONT_OCC
+#define PB200_CELLS_MONT_OCC 5      // resident CTAs per SM the Montgomery variant is compiled for (A/B: tools/build_variant.py)
+#endif
 template <bool MONT>
-__global__ void __launch_bounds__(128, MONT ? 4 : 6) k_cells_mulmod64(CellLayout Y, u64 m_cpl, u64 m_eq, u64 m_eqs, u64 m_ch, const u64* __restrict__ consts,
+__global__ void __launch_bounds__(128, MONT ? PB200_CELLS_MONT_OCC : 6) k_cells_mulmod64(CellLayout Y, u64 m_cpl, u64 m_eq, u64 m_eqs, u64 m_ch, const u64* __restrict__ consts,
                                                            const u64* __restrict__ a, const u64* __restrict__ b,
                                                            const u64* __restrict__ q, const u64* __restrict__ rem,
                                                            size_t count, u64* __restrict__ out, int* flags, const u64* __restrict__ mtab) {
@@ -528,12 +578,9 @@ __global__ void __launch_bounds__(128, MONT ? 4 : 6) k_cells_mulmod64(CellLayout
     const u64* c_accm = consts + 2 * L + 4 + 4 * NC;      // Montgomery forms of q_acc, mod_acc: [NC][4] each
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64* s_n = sm;
-    // per warp: two limb sets (double buffer), then d; the Montgomery kernel also keeps the canonical columns ab and q*n^2 (3 words
-    // each) for its conversion passes
-    u64* s_w = sm + L + (size_t)warp * (8 * L + (MONT ? 9 : 3) * NC + 1);
+    // per warp: two limb sets (double buffer), then d
+    u64* s_w = sm + L + (size_t)warp * (8 * L + 3 * NC + 1);
     u64* s_d = s_w + 8 * L;
-    u64* s_ab = s_d + 3 * NC;
-    u64* s_qn = s_ab + 3 * NC;
     const u64* c_wmax = consts + 2 * L;        // consts: n2 limbs [L][2], word_max (4 words), q_acc [NC][2], mod_acc [NC][2]
     const u64* c_qacc = c_wmax + 4;
     const u64* c_macc = c_qacc + 2 * NC;
@@ -627,14 +674,11 @@ __global__ void __launch_bounds__(128, MONT ? 4 : 6) k_cells_mulmod64(CellLayout
                     qn.w[0] = h ? qh0 : ql0; qn.w[1] = h ? qh1 : ql1; qn.w[2] = h ? qh2 : ql2; qn.w[3] = 0;
                     W4 qp = qn;
                     if (h == 0) mac3p(qp.w[0], qp.w[1], qp.w[2], s_r[c], 0);
-                    if (MONT) {      // canonical columns kept for the conversion passes below
-                        s_ab[3 * col] = ab.w[0]; s_ab[3 * col + 1] = ab.w[1]; s_ab[3 * col + 2] = ab.w[2];
-                        s_qn[3 * col] = qn.w[0]; s_qn[3 * col + 1] = qn.w[1]; s_qn[3 * col + 2] = qn.w[2];
-                    } else {
-                        store_cell_k<false>(out, base + Y.off_ab + col, ab, CK_RAW);
-                        store_cell_k<false>(out, base + Y.off_qn + col, qn, CK_RAW);
-                        store_cell_k<false>(out, base + Y.off_qnp + col, qp, CK_RAW);
-                    }
+                    // (Montgomery output: the canonical columns are parked in their own output cells — 8 KB per group that stay in L2 —
+                    // and converted in place by the passes below; keeping them in shared memory cost a third of the resident warps)
+                    store_cell_k<false>(out, base + Y.off_ab + col, ab, CK_RAW);
+                    store_cell_k<false>(out, base + Y.off_qn + col, qn, CK_RAW);
+                    if (!MONT) store_cell_k<false>(out, base + Y.off_qnp + col, qp, CK_RAW);
                     // d = ab - qp + word_max (two's complement over 3 words)
                     u64 d0, d1, d2;
                     asm("sub.cc.u64 %0, %3, %6; subc.cc.u64 %1, %4, %7; subc.u64 %2, %5, %8;"
@@ -692,24 +736,41 @@ __global__ void __launch_bounds__(128, MONT ? 4 : 6) k_cells_mulmod64(CellLayout
         // Montgomery output: conversion passes of uniform cell kind (no divergence between the conversion paths, one call site each).
         // Columns: Montgomery form is linear, so the cell of qn + rem is the cell of qn plus the (one-word) cell of rem, and for the
         // upper columns it IS the cell of qn: one general conversion serves two cells.
-        for (int col = lane; col < NC; col += 32)
-            store_cell_k<true>(out, base + Y.off_ab + col, fr_redc<3>(s_ab[3 * col], s_ab[3 * col + 1], s_ab[3 * col + 2]), CK_RAW);
+        __syncwarp();        // (small L: the rem limb cells read back below were written by other lanes of this warp)
         for (int col = lane; col < NC; col += 32) {
-            const W4 qn_m = fr_redc<3>(s_qn[3 * col], s_qn[3 * col + 1], s_qn[3 * col + 2]);
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(out) + 2 * (base + Y.off_ab + col);    // written by this lane above
+            const ulonglong2 x01 = __ldcg(src), x23 = __ldcg(src + 1);
+            store_cell_k<true>(out, base + Y.off_ab + col, fr_redc<3>(x01.x, x01.y, x23.x), CK_RAW);
+        }
+        for (int col = lane; col < NC; col += 32) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(out) + 2 * (base + Y.off_qn + col);
+            const ulonglong2 x01 = __ldcg(src), x23 = __ldcg(src + 1);
+            const W4 qn_m = fr_redc<3>(x01.x, x01.y, x23.x);
             store_cell_k<true>(out, base + Y.off_qn + col, qn_m, CK_RAW);
-            store_cell_k<true>(out, base + Y.off_qnp + col, col < L ? fr_add(qn_m, fr_redc<1>(s_r[col], 0, 0)) : qn_m, CK_RAW);
+            W4 qp_m = qn_m;
+            if (col < L) {       // + the cell of rem_col, which the limb pass above already converted and wrote (L2 hit)
+                const ulonglong2* rc = reinterpret_cast<const ulonglong2*>(out) + 2 * (base + Y.off_rem + (size_t)col * Y.cpl);
+                const ulonglong2 r01 = __ldcg(rc), r23 = __ldcg(rc + 1);
+                W4 rm; rm.w[0] = r01.x; rm.w[1] = r01.y; rm.w[2] = r23.x; rm.w[3] = r23.y;
+                qp_m = fr_add(qn_m, rm);
+            }
+            store_cell_k<true>(out, base + Y.off_qnp + col, qp_m, CK_RAW);
         }
         // eq section, per column [carry (two words), cs (one word), q_acc, mod_acc (per-key, pre-converted)], then the carries' chunks
         for (int i = lane; i < NC; i += 32) {
             const size_t cell = base + Y.off_eq + (size_t)i * Y.eq_stride;
             store_cell_k<true>(out, cell, fr_redc<2>(s_d[3 * i + 1], s_d[3 * i + 2], 0), CK_RAW);
-            store_cell_k<true>(out, cell + 1, fr_redc<1>(s_d[3 * i], 0, 0), CK_RAW);
+            W4 acc_m[2];
 #pragma unroll
             for (int w = 0; w < 2; w++) {
                 const u64* m4 = c_accm + 4 * ((size_t)w * NC + i);
-                W4 v; v.w[0] = __ldg(m4); v.w[1] = __ldg(m4 + 1); v.w[2] = __ldg(m4 + 2); v.w[3] = __ldg(m4 + 3);
-                store_cell_k<true>(out, cell + 2 + w, v, CK_RAW);
+                acc_m[w].w[0] = __ldg(m4); acc_m[w].w[1] = __ldg(m4 + 1); acc_m[w].w[2] = __ldg(m4 + 2); acc_m[w].w[3] = __ldg(m4 + 3);
             }
+            // cs_i equals mod_acc_i whenever the chip's equality holds (checked above): its cell is then the pre-converted constant
+            const bool same = s_d[3 * i] == __ldg(c_macc + 2 * i);
+            store_cell_k<true>(out, cell + 1, same ? acc_m[1] : fr_redc<1>(s_d[3 * i], 0, 0), CK_RAW);
+            store_cell_k<true>(out, cell + 2, acc_m[0], CK_RAW);
+            store_cell_k<true>(out, cell + 3, acc_m[1], CK_RAW);
         }
         const int cpc = Y.kc + Y.xc, n_cc = (NC - 1) * cpc;
         for (int i0 = lane; i0 < n_cc; i0 += 128) {
@@ -799,7 +860,7 @@ cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_
     if (!count) return cudaSuccess;
     if (Y.limb_bits == 64 && Y.n_cells < 65536) {
         const size_t L = Y.L, NC = 2 * L - 1;
-        const size_t smem64 = (L + 4 * (8 * L + (mont ? 9 : 3) * NC + 1)) * sizeof(u64);
+        const size_t smem64 = (L + 4 * (8 * L + 3 * NC + 1)) * sizeof(u64);
         {   // per device (a function attribute belongs to the current context): set on every launch, it is a host-side table write
             cudaError_t e = mont ? cudaFuncSetAttribute(k_cells_mulmod64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)
                                  : cudaFuncSetAttribute(k_cells_mulmod64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -810,7 +871,7 @@ cudaError_t cells_mulmod(const CellLayout& Y, const u64* d_consts, const u64* d_
         const u64 m_ch = Y.cpl > 1 ? (0x100000000ull + (Y.cpl - 1) - 1) / (Y.cpl - 1) : 0;
         size_t ctas = (count + 3) / 4;
         const size_t per_sm = smem64 ? (200 * 1024) / smem64 : 6;
-        const size_t occ = mont ? 4 : 6;
+        const size_t occ = mont ? PB200_CELLS_MONT_OCC : 6;
         const size_t cap = (size_t)sms * (per_sm < 1 ? 1 : (per_sm > occ ? occ : per_sm));
         if (ctas > cap) ctas = cap;
         if (mont) k_cells_mulmod64<true><<<(unsigned)ctas, 128, smem64, st>>>(Y, m_cpl, m_eq, m_eqs, m_ch, d_consts, d_a, d_b, d_q, d_rem, count, d_out, d_flags, d_mtab);

@@ -27,6 +27,11 @@ cudaError_t simple_tally(const SimpleConsts* dK, int k, const u64* d_c, size_t c
                          int* d_flags, cudaStream_t st);
 cudaError_t repack_limbs(const u64* d_vals, size_t count, int words_per_value, int value_bits, int limb_bits,
                          u64* d_out, cudaStream_t st);
+// decryption pieces on the simple engine: x = base^e mod n^2 (exponent words on the device), and m = (x - 1) / n * mu mod n with
+// the constants of the modulus n (mu in their g slot); flag bit 3 when x != 1 (mod n)
+cudaError_t simple_pow(const SimpleConsts* dK, const u64* d_base, int base_words, const u64* d_e, int e_bits, size_t count, u64* d_out,
+                       int* d_flags, cudaStream_t st);
+cudaError_t simple_lfunc(const SimpleConsts* dKn, const u64* d_x, size_t count, u64* d_m, int* d_flags, cudaStream_t st);
 
 // ---- block28 engine (block28_kernels.cu) ----------------------------------------------------
 struct Block28Key;  // opaque per-key state of the fast engine
@@ -39,6 +44,9 @@ void block28_set_mma(Block28Key*, bool on);   // constant-operand phases on the 
 void block28_chain_counts(const Block28Key*, uint64_t* n_sqr, uint64_t* n_mul);
 cudaError_t block28_encrypt(Block28Key*, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st);
 cudaError_t block28_tally(Block28Key*, const u64* d_c, size_t count, u64* d_out, cudaStream_t st);
+// out = base^e mod n^2 for a per-key exponent e (sliding-window schedule built by block28_pow_prepare): the decryption's c^lambda
+cudaError_t block28_pow_prepare(Block28Key*, const BigInt& e, cudaStream_t st);
+cudaError_t block28_pow(Block28Key*, const u64* d_base, int base_words, size_t count, u64* d_out, cudaStream_t st);
 // multi-GPU tally: one launch per GPU, partials exchanged through peer-mapped mailboxes inside the kernel (collective call)
 cudaError_t block28_tally_peer(Block28Key*, const u64* d_c, size_t count, u64* d_out, cudaStream_t st);
 cudaError_t block28_mailbox(Block28Key*, u64** d_mail, cudaStream_t st);

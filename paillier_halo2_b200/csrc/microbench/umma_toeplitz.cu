@@ -1,0 +1,310 @@
+// umma_toeplitz.cu — the constant-operand Barrett phase of block28 (q1 * mu, high part) as a Blackwell-native kernel:
+// tcgen05.mma kind::i8 with the accumulators in TMEM, 128 ciphertexts (MMA rows) per CTA, the Toeplitz operand addressed through
+// UMMA shared-memory descriptors, tcgen05.ld for the fold.  A MEASUREMENT and a numerical check, not part of the product library:
+// it answers what DESIGN.md §8.1 left open — what the 5th-generation tensor core delivers on this product once a CTA holds 128
+// lanes — and its SASS is the UTCIMMA / LDTM evidence.  VERDICT r1 item 5.
+//
+//   D[lane][p] = sum_k A7[lane][k] * K7[p - k],   p in [4(L-2), 4(L-2) + 640),  k in [0, 4L)          (L = 152: |n| = 2048)
+//
+// A7: signed 7-bit digits of the per-lane operand, in shared memory as [16-byte K chunk][lane][16] — the canonical K-major,
+//     no-swizzle UMMA layout (8 x 16-byte core matrices 128 B apart along M, 2048 B apart along K).
+// K7: per-key constant.  A B tile is 64 output columns taken in DECREASING p, so that row n of the tile is the reversed constant
+//     shifted by n bytes; core matrix (g, j) of any (tile, k-step) is then entry u0 + g + 2j of ONE table
+//     CM[u][r][b] = Rev[8u + r + b] (92 entries of 128 B): stride 128 B along N, 256 B along K — no tile is ever materialised.
+// Epilogue: 16 warps; warp w reads the 32 TMEM lanes of quadrant w % 4 (the hardware's rule) and the column slice w / 4 of the pass;
+//     per 16 columns one tcgen05.ld.32x32b.x16 (the load of the next group is in flight while this one is folded), the fold of four
+//     radix-2^7 columns into a 28-bit digit + carry (same arithmetic as phase_mma's fold in block28.cuh), the digit of q-hat packed
+//     as four s8 into the next phase's operand rows (one 128-bit store per 4 digits).  The carry into a slice's lowest digit comes
+//     from the top four columns of the slice below, which the thread reads itself (the fold is local to a digit).
+//
+// build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o build/umma_toeplitz umma_toeplitz.cu
+// run:    build/umma_toeplitz [iters]      -> one JSON line (cycles per phase with and without the epilogue, parity of CTA 0 against the host)
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+constexpr int L = 152, K7 = 4 * L;                 // 608 s8 digits per operand
+constexpr int KCH = K7 / 16;                       // 38 chunks of 16 bytes
+constexpr int KSTEPS = K7 / 32;                    // 19 k-steps of 32 bytes
+constexpr int LANES = 128;                         // ciphertexts per CTA = MMA M
+constexpr int NWARPS = 16, THREADS = 32 * NWARPS;  // warp w: TMEM quadrant w % 4, column slice w / 4
+constexpr int TN = 64;                             // tile width (MMA N)
+constexpr int NT = 10;                             // tiles: 640 columns >= 4(L+2) = 616
+constexpr int P_BASE = 4 * (L - 2);                // first output column (phase B keeps two guard digits)
+constexpr int PADZ = 288, Z0 = K7 - 1 + PADZ;      // Rev[z] = K7[Z0 - z];  Z0 = 7 (mod 8) like the top column of every tile; the
+                                                   // padding keeps the rows of a 256-column tile that lie far above the band inside the table
+constexpr int NCM = 116;                           // table entries of 128 B
+constexpr int A_BYTES = KCH * LANES * 16;          // 77 824
+constexpr int CM_BYTES = NCM * 128;                // 11 776
+constexpr int SMEM_BYTES = 2 * A_BYTES + CM_BYTES + 1024;
+constexpr int W28 = 28;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed 8 bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t idesc_n(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(LANES >> 4) << 24); }
+
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+// returns false when the barrier did not complete within the budget (a wrong descriptor must not hang the box)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (long long spin = 0; spin < 20000000ll; spin++) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ unsigned split7_pack(int d) {      // block28.cuh: one 28-bit digit -> four signed 7-bit digits in a word
+    const unsigned dp = (unsigned)d + (64u | (64u << 7) | (64u << 14));
+    const unsigned x = (dp & 0x7Fu) | ((dp << 1) & 0x7F00u) | ((dp << 2) & 0x7F0000u);
+    return ((x + 0x404040u) ^ 0x808080u) | ((unsigned)((int)dp >> 21) << 24);
+}
+
+// passes of one phase, from the top columns down: tiles {9, 8}, {7..4}, {3..0}; a pass fills one half of TMEM (256 columns)
+__device__ __forceinline__ void pass_tiles(int pt, int& t_hi, int& t_lo) {
+    if (pt == 0) { t_hi = 9; t_lo = 8; } else if (pt == 1) { t_hi = 7; t_lo = 4; } else { t_hi = 3; t_lo = 0; }
+}
+
+__device__ __forceinline__ void fold4(const int* v, int& lo, int& ca) {     // v[0..3] = columns c3, c2, c1, c0 of one digit
+    const int lowp = v[3] + (v[2] << 7), highp = v[1] + (v[0] << 7);
+    const int tb = lowp + ((highp & 0x3FFF) << 14) + (1 << (W28 - 1));
+    lo = (tb & ((1 << W28) - 1)) - (1 << (W28 - 1));
+    ca = (tb >> W28) + (highp >> 14);                                      // carry into the digit above
+}
+
+// mode bit 0: MMAs only (the tensor core's own time on this shape), else MMAs + epilogue;  bit 1: wide tiles (one per pass)
+__global__ void __launch_bounds__(THREADS, 1) k_umma_toeplitz(const signed char* __restrict__ a_in /* [ctas][LANES][K7] */,
+                                                              const signed char* __restrict__ k7 /* [K7] */, int iters, int mode,
+                                                              int* __restrict__ digits_out /* CTA 0: [LANES][160] or null */,
+                                                              unsigned* __restrict__ packed_out /* [ctas][THREADS] checksum */,
+                                                              long long* __restrict__ cycles, int* __restrict__ status) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sA = smem;                       // [KCH][LANES][16]
+    unsigned char* sA2 = smem + A_BYTES;            // next phase's operand rows, same layout
+    unsigned char* sCM = smem + 2 * A_BYTES;        // [NCM][8][16]
+    uint64_t* bars = (uint64_t*)(smem + 2 * A_BYTES + CM_BYTES);      // two mbarriers (one per TMEM half)
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane_row = (warp & 3) * 32 + (tid & 31), slice = warp >> 2;
+    // ---- operands into shared memory (generic proxy), then made visible to the tensor core's async proxy
+    if (tid < LANES) {
+        const signed char* src = a_in + ((size_t)blockIdx.x * LANES + tid) * K7;
+        for (int c = 0; c < KCH; c++) *(int4*)(sA + ((size_t)c * LANES + tid) * 16) = *(const int4*)(src + 16 * c);
+    }
+    for (int i = tid; i < NCM * 128; i += THREADS) {
+        const int u = i >> 7, r = (i >> 4) & 7, b = i & 15;
+        const int d = Z0 - (8 * u + r + b);                           // Rev[z] = K7[Z0 - z]
+        sCM[i] = (d >= 0 && d < K7) ? (unsigned char)k7[d] : 0;
+    }
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t a_base = smem_u32(sA), cm_base = smem_u32(sCM);
+    const int total = 3 * iters;
+    auto issue = [&](int c) {                       // one thread: all MMAs of pass c into TMEM half c & 1, then the commit
+        int t_hi, t_lo;
+        pass_tiles(c % 3, t_hi, t_lo);
+        const uint32_t d0 = tmem + (uint32_t)((c & 1) * 256);
+        if (mode & 2) {
+            // WIDE: the whole pass as one tile of N = 128 or 256 columns per k-step.  More products fall outside the band (34.6 M
+            // int8 MACs per phase instead of 28.6 M) but the A rows are read from shared memory once per k-step instead of once
+            // per 64 columns, which is what bounds the narrow form
+            const int n = (t_hi - t_lo + 1) * TN, p_hi = P_BASE + TN * t_hi + TN - 1, p_lo = P_BASE + TN * t_lo;
+            const int ks_lo = p_lo - (K7 - 1) > 0 ? (p_lo - (K7 - 1)) / 32 : 0;
+            for (int ks = ks_lo; ks < KSTEPS; ks++) {
+                const int u0 = (Z0 - p_hi + 32 * ks) >> 3;
+                umma_i8(d0, umma_desc(a_base + (uint32_t)(2 * ks) * LANES * 16, LANES * 16, 128),
+                        umma_desc(cm_base + (uint32_t)u0 * 128, 256, 128), ks > ks_lo ? 1u : 0u, idesc_n(n));
+            }
+        } else {
+            for (int T = t_hi; T >= t_lo; T--) {
+                const int p_hi = P_BASE + TN * T + TN - 1;
+                const int ks_lo = T ? 2 * T - 1 : 0;                  // k-steps that meet the band 0 <= p - k <= K7 - 1
+                for (int ks = ks_lo; ks < KSTEPS; ks++) {
+                    const int u0 = (Z0 - p_hi + 32 * ks) >> 3;
+                    umma_i8(d0 + (uint32_t)((t_hi - T) * TN), umma_desc(a_base + (uint32_t)(2 * ks) * LANES * 16, LANES * 16, 128),
+                            umma_desc(cm_base + (uint32_t)u0 * 128, 256, 128), ks > ks_lo ? 1u : 0u, idesc_n(TN));
+                }
+            }
+        }
+        umma_commit(&bars[c & 1]);
+    };
+    long long t_start = 0;
+    if (tid == 0) { t_start = clock64(); issue(0); if (total > 1) issue(1); }
+    unsigned checksum = 0;
+    bool ok = true;
+    for (int c = 0; c < total && ok; c++) {
+        ok = mbar_wait(&bars[c & 1], (uint32_t)((c >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ok && !(mode & 1)) {
+            int t_hi, t_lo;
+            pass_tiles(c % 3, t_hi, t_lo);
+            const int ncols = (t_hi - t_lo + 1) * TN, per = ncols / 4;      // this warp's slice: columns [slice * per, (slice + 1) * per)
+            const uint32_t row = tmem + (uint32_t)((c & 1) * 256) + ((uint32_t)((warp & 3) * 32) << 16);
+            // columns n = 0.. of the pass are p = p_top - n, p_top = 3 (mod 4): 16 columns = digits jj0+3 .. jj0, top digit first
+            const int p_top = P_BASE + TN * t_hi + TN - 1;
+            const int n_begin = slice * per, n_end = n_begin + per;
+            int va[16], vb[16], below[4];
+            tmem_ld16(row + (uint32_t)n_begin, va);
+            int pend_lo = 0, pend_q = -1;
+            unsigned pw1 = 0, pw2 = 0, pw3 = 0;                       // the three complete digits of the pending group, packed
+            auto emit = [&](int c_in) {                               // the pending group's lowest digit is complete: one 128-bit store
+                const int d0 = pend_lo + c_in;
+                const unsigned w0 = split7_pack(d0);
+                checksum = (((checksum * 0x9E3779B1u + pw3) * 0x9E3779B1u + pw2) * 0x9E3779B1u + pw1) * 0x9E3779B1u + w0;
+                if ((pend_q >> 2) < KCH) *(uint4*)(sA2 + ((size_t)(pend_q >> 2) * LANES + lane_row) * 16) = make_uint4(w0, pw1, pw2, pw3);
+                if (digits_out && blockIdx.x == 0 && c < 3) digits_out[lane_row * 160 + pend_q] = d0;
+            };
+            auto step = [&](int (&cur)[16], int (&nxt)[16], int n0) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // the next request is in flight while this group is folded: the next group, or (after the slice's last group) the top
+                // digit of the slice below, whose carry completes this slice's lowest digit
+                if (n0 + 16 < n_end) tmem_ld16(row + (uint32_t)(n0 + 16), nxt);
+                else if (slice != 3) tmem_ld4(row + (uint32_t)n_end, below);
+                int lo[4], ca[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) fold4(&cur[4 * i], lo[i], ca[i]);          // i = 0: top digit jj0 + 3
+                const int q = ((p_top - n0 - 15) >> 2) - (P_BASE >> 2);               // lowest digit of this group within the phase
+                if (pend_q >= 0) emit(ca[0]);
+                else if (digits_out && blockIdx.x == 0 && c < 3 && slice == 0 && c % 3 != 0)
+                    atomicAdd(digits_out + lane_row * 160 + q + 4, ca[0]);             // the pass above left its last digit open
+                const int d3 = lo[0] + ca[1], d2 = lo[1] + ca[2], d1 = lo[2] + ca[3];
+                pw3 = split7_pack(d3); pw2 = split7_pack(d2); pw1 = split7_pack(d1);
+                pend_lo = lo[3]; pend_q = q;
+                if (digits_out && blockIdx.x == 0 && c < 3) { int* o = digits_out + lane_row * 160 + q; o[3] = d3; o[2] = d2; o[1] = d1; }
+            };
+            for (int n0 = n_begin; n0 < n_end; n0 += 32) { step(va, vb, n0); step(vb, va, n0 + 16); }
+            if (slice != 3) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                int l2, c2;
+                fold4(below, l2, c2);
+                emit(c2);
+            } else emit(0);          // bottom of the pass: the carry belongs to the next pass (parity run: added there), or to nothing
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        ok = __syncthreads_and(ok);                  // this TMEM half is free again; a time-out ends the loop for every thread
+        if (ok && tid == 0 && c + 2 < total) { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); issue(c + 2); }
+    }
+    if (tid == 0) cycles[blockIdx.x] = clock64() - t_start;
+    packed_out[(size_t)blockIdx.x * THREADS + tid] = checksum ^ *(unsigned*)(sA2 + (tid & 127) * 16);
+    if (!ok) atomicExch(status, 1);
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("{\"error\": \"%s: %s\"}\n", #x, cudaGetErrorString(e_)); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    const int iters = argc > 1 ? atoi(argv[1]) : 2000;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int ctas = prop.multiProcessorCount;
+    std::vector<signed char> a((size_t)ctas * LANES * K7), k7(K7);
+    uint64_t s = 0x1234567;
+    auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (int)((s >> 33) % 127) - 63; };      // [-63, 63]
+    for (auto& x : a) x = (signed char)rnd();
+    for (auto& x : k7) x = (signed char)rnd();
+    signed char *d_a, *d_k; int *d_dig, *d_status; unsigned* d_packed; long long* d_cyc;
+    CK(cudaMalloc(&d_a, a.size())); CK(cudaMalloc(&d_k, k7.size()));
+    CK(cudaMalloc(&d_dig, (size_t)LANES * 4 * NT * 4 * sizeof(int))); CK(cudaMemset(d_dig, 0, (size_t)LANES * 4 * NT * 4 * sizeof(int)));
+    CK(cudaMalloc(&d_packed, (size_t)ctas * THREADS * sizeof(unsigned))); CK(cudaMalloc(&d_cyc, ctas * sizeof(long long)));
+    CK(cudaMalloc(&d_status, sizeof(int))); CK(cudaMemset(d_status, 0, sizeof(int)));
+    CK(cudaMemcpy(d_a, a.data(), a.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_k, k7.data(), k7.size(), cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(k_umma_toeplitz, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    // 1. one phase, CTA 0's digits against the host, narrow and wide tiles
+    const int ND = 4 * NT * 4;       // 160 digits of 4 columns
+    std::vector<int> want((size_t)LANES * ND);
+    for (int lane = 0; lane < LANES; lane++) {
+        std::vector<long long> lo(ND), ca(ND + 1, 0);
+        for (int q = 0; q < ND; q++) {
+            long long v = 0;
+            for (int i = 0; i < 4; i++) {
+                const int p = P_BASE + 4 * q + i;
+                long long col = 0;
+                for (int k = 0; k < K7; k++) { const int d = p - k; if (d >= 0 && d < K7) col += (long long)a[(size_t)lane * K7 + k] * k7[d]; }
+                v += col << (7 * i);
+            }
+            long long l = ((v + (1ll << 27)) & ((1ll << 28) - 1)) - (1ll << 27);
+            lo[q] = l; ca[q + 1] = (v - l) >> 28;
+        }
+        for (int q = 0; q < ND; q++) want[(size_t)lane * ND + q] = (int)(lo[q] + ca[q]);
+    }
+    int status = 0;
+    long long bad = 0, checked = 0;
+    std::vector<int> dig((size_t)LANES * ND);
+    for (int wide = 0; wide < 2; wide++) {
+        CK(cudaMemset(d_dig, 0, dig.size() * sizeof(int)));
+        k_umma_toeplitz<<<ctas, THREADS, SMEM_BYTES>>>(d_a, d_k, 1, 2 * wide, d_dig, d_packed, d_cyc, d_status);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(dig.data(), d_dig, dig.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        // the wide form's top pass computes columns above 4(L+2) too; only the 154 digits of the phase are compared
+        for (int lane = 0; lane < LANES; lane++)
+            for (int q = 0; q < L + 2; q++) { checked++; if (dig[(size_t)lane * ND + q] != want[(size_t)lane * ND + q]) bad++; }
+    }
+    // 2. timing: narrow / wide tiles, with the epilogue and the tensor core alone
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double avg_mode[4] = {0, 0, 0, 0}; float ms_mode[4] = {0, 0, 0, 0};
+    std::vector<long long> cyc(ctas);
+    for (int mode = 0; mode < 4; mode++) {
+        k_umma_toeplitz<<<ctas, THREADS, SMEM_BYTES>>>(d_a, d_k, 50, mode, nullptr, d_packed, d_cyc, d_status);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        k_umma_toeplitz<<<ctas, THREADS, SMEM_BYTES>>>(d_a, d_k, iters, mode, nullptr, d_packed, d_cyc, d_status);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventElapsedTime(&ms_mode[mode], e0, e1));
+        CK(cudaMemcpy(cyc.data(), d_cyc, ctas * sizeof(long long), cudaMemcpyDeviceToHost));
+        for (auto c : cyc) avg_mode[mode] += (double)c;
+        avg_mode[mode] /= ctas;
+    }
+    CK(cudaMemcpy(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    long long mmas = 0; for (int T = 0; T < NT; T++) mmas += KSTEPS - (T ? 2 * T - 1 : 0);
+    const double mac_narrow = (double)mmas * LANES * TN * 32, mac_wide = (double)LANES * 32 * (4 * 128 + 12 * 256 + 19 * 256), mac_useful = (double)LANES * 194600.0;
+    printf("{\"kernel\": \"k_umma_toeplitz\", \"ctas\": %d, \"lanes_per_cta\": %d, \"iters\": %d, \"timeout\": %d, "
+           "\"parity_digits_checked\": %lld, \"parity_mismatches\": %lld, "
+           "\"narrow_n64\": {\"mma_per_phase\": %lld, \"cycles_per_phase\": %.1f, \"cycles_per_lane_phase\": %.2f, \"cycles_per_phase_mma_only\": %.1f, "
+           "\"int8_mac_issued_per_clk_per_sm_mma_only\": %.1f, \"ms\": %.3f}, "
+           "\"wide_n256\": {\"mma_per_phase\": 35, \"cycles_per_phase\": %.1f, \"cycles_per_lane_phase\": %.2f, \"cycles_per_phase_mma_only\": %.1f, "
+           "\"int8_mac_issued_per_clk_per_sm_mma_only\": %.1f, \"ms\": %.3f}, "
+           "\"int8_mac_useful_per_lane_phase\": %.0f, "
+           "\"note\": \"mma.sync phase of k_encrypt: ~119 SM-cycles per lane-phase (32 lanes per CTA, 2 CTAs per SM)\"}\n",
+           ctas, LANES, iters, status, checked, bad,
+           mmas, avg_mode[0] / iters, avg_mode[0] / iters / LANES, avg_mode[1] / iters, mac_narrow / (avg_mode[1] / iters), ms_mode[0],
+           avg_mode[2] / iters, avg_mode[2] / iters / LANES, avg_mode[3] / iters, mac_wide / (avg_mode[3] / iters), ms_mode[2], mac_useful / LANES);
+    return (bad || status) ? 2 : 0;
+}

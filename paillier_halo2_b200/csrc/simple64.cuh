@@ -88,14 +88,12 @@ __device__ __forceinline__ void shr_words(u64* out, const u64* x, int n, int s, 
     }
 }
 
-// q[0..k), rem[0..k) <- floor(a*b/n2), a*b mod n2.  a, b: k words (zero-extended).  Returns 1 if
-// the quotient does not fit k words (the reference's range check on q would fail), else 0.
-static __device__ __noinline__ int mulmod_simple(const SimpleConsts* __restrict__ K, u64* q, u64* rem, const u64* a, const u64* b) {
+// q[0..k), rem[0..k) <- floor(X / N), X mod N for the 2k-word X (X[2k] is scratch; X is destroyed), N the modulus the constants
+// were built for.  Returns 1 if the quotient does not fit k words, else 0.
+static __device__ __noinline__ int barrett_simple(const SimpleConsts* __restrict__ K, u64* q, u64* rem, u64* X) {
     const int k = K->k;
-    u64 X[2 * PB200_SIMPLE_MAXK + 1];
     u64 q3[PB200_SIMPLE_MAXK + 2];
     u64 r[PB200_SIMPLE_MAXK + 1];
-    mul_full(X, a, k, b, k);
     X[2 * k] = 0;
     // X << s must stay inside 2k words.  Operands that are not reduced (pb200_add_batch accepts them) can make X >= 2^(128k - s);
     // then q = floor(X / n^2) > 2^(128k - s) / 2^(64k - s) = 2^(64k) does not fit k words: exactly the range failure, reported
@@ -145,6 +143,15 @@ static __device__ __noinline__ int mulmod_simple(const SimpleConsts* __restrict_
     shr_words(rem, r, k + 1, K->s, k);
     for (int i = 0; i < k; i++) q[i] = q3[i];
     return q3[k] != 0;
+}
+
+// q[0..k), rem[0..k) <- floor(a*b/n2), a*b mod n2.  a, b: k words (zero-extended).  Returns 1 if
+// the quotient does not fit k words (the reference's range check on q would fail), else 0.
+static __device__ __noinline__ int mulmod_simple(const SimpleConsts* __restrict__ K, u64* q, u64* rem, const u64* a, const u64* b) {
+    const int k = K->k;
+    u64 X[2 * PB200_SIMPLE_MAXK + 1];
+    mul_full(X, a, k, b, k);
+    return barrett_simple(K, q, rem, X);
 }
 
 __device__ __forceinline__ u64 record_hash(const u64* q, const u64* rem, int k) {

@@ -127,6 +127,45 @@ __global__ void k_simple_tally_final(const SimpleConsts* __restrict__ K, const u
     if (bad) atomicOr(flags, 1);
 }
 
+// ---- decryption (the reference's README.md:5-22 states it, its code never implements it) ------------------------
+// x = base^e mod n^2, LSB-first square-and-multiply, exponent words from device memory: the always-available pow for keys the
+// block engine does not serve
+__global__ void __launch_bounds__(32) k_simple_pow(const SimpleConsts* __restrict__ K, const u64* __restrict__ base, int base_words,
+                                                   const u64* __restrict__ e, int e_bits, size_t count, u64* __restrict__ out, int* flags) {
+    const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= count) return;
+    const int k = K->k;
+    u64 acc[PB200_SIMPLE_MAXK], sq[PB200_SIMPLE_MAXK], q[PB200_SIMPLE_MAXK], t[PB200_SIMPLE_MAXK];
+    int bad = 0;
+    set_one(acc, k);
+    load_ext(sq, base + u * base_words, base_words, k);
+    for (int i = 0; i < e_bits; i++) {
+        if (bit_at(e, i)) { bad |= mulmod_simple(K, q, t, acc, sq); for (int j = 0; j < k; j++) acc[j] = t[j]; }
+        if (i + 1 < e_bits) { bad |= mulmod_simple(K, q, t, sq, sq); for (int j = 0; j < k; j++) sq[j] = t[j]; }
+    }
+    if (e_bits == 0) { u64 one[PB200_SIMPLE_MAXK]; set_one(one, k); bad |= mulmod_simple(K, q, t, acc, one); for (int j = 0; j < k; j++) acc[j] = t[j]; }
+    for (int j = 0; j < k; j++) out[u * k + j] = acc[j];
+    if (bad) atomicOr(flags, 1);
+}
+
+// m = L(x) * mu mod n with L(x) = (x - 1) / n (README.md:17-22 of the reference).  Kn: constants of the modulus n (k = words of n),
+// its g slot carries mu.  x: 2k words.  Raises flag bit 3 when x is not 1 mod n (not the lambda-th power of a valid ciphertext).
+__global__ void __launch_bounds__(32) k_simple_lfunc(const SimpleConsts* __restrict__ Kn, const u64* __restrict__ x, size_t count,
+                                                     u64* __restrict__ m_out, int* flags) {
+    const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= count) return;
+    const int k = Kn->k;
+    u64 X[PB200_SIMPLE_MAXK + 1], t[PB200_SIMPLE_MAXK / 2 + 1], rem[PB200_SIMPLE_MAXK / 2 + 1], q[PB200_SIMPLE_MAXK / 2 + 1], m[PB200_SIMPLE_MAXK / 2 + 1];
+    u64 borrow = 1;                                       // X = x - 1
+    for (int i = 0; i < 2 * k; i++) { const u64 xi = x[u * 2 * k + i]; X[i] = xi - borrow; borrow = xi < borrow; }
+    int bad = (int)borrow;                                // x == 0
+    bad |= barrett_simple(Kn, t, rem, X);
+    for (int i = 0; i < k; i++) bad |= rem[i] != 0;
+    mulmod_simple(Kn, q, m, t, Kn->g);
+    for (int i = 0; i < k; i++) m_out[u * k + i] = bad ? 0 : m[i];
+    if (bad) atomicOr(flags, 8);
+}
+
 // K5: value (words_per_value u64 words) -> value_bits/limb_bits limbs, 2 words per limb (lo, hi)
 __global__ void k_repack(const u64* __restrict__ vals, size_t count, int wpv, int nl, int limb_bits, u64* __restrict__ out) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -178,6 +217,17 @@ cudaError_t simple_tally(const SimpleConsts* dK, int k, const u64* d_c, size_t c
         k_simple_tally_partial<<<(T2 + 31) / 32, 32, 0, st>>>(dK, p1, (size_t)T1, p2, T2, d_flags); count_launch();
     }
     k_simple_tally_final<<<1, 1, 0, st>>>(dK, p2, T2, d_out, d_flags); count_launch();
+    return cudaGetLastError();
+}
+cudaError_t simple_pow(const SimpleConsts* dK, const u64* d_base, int base_words, const u64* d_e, int e_bits, size_t count, u64* d_out,
+                       int* d_flags, cudaStream_t st) {
+    if (!count) return cudaSuccess;
+    k_simple_pow<<<(unsigned)((count + 31) / 32), 32, 0, st>>>(dK, d_base, base_words, d_e, e_bits, count, d_out, d_flags); count_launch();
+    return cudaGetLastError();
+}
+cudaError_t simple_lfunc(const SimpleConsts* dKn, const u64* d_x, size_t count, u64* d_m, int* d_flags, cudaStream_t st) {
+    if (!count) return cudaSuccess;
+    k_simple_lfunc<<<(unsigned)((count + 31) / 32), 32, 0, st>>>(dKn, d_x, count, d_m, d_flags); count_launch();
     return cudaGetLastError();
 }
 cudaError_t repack_limbs(const u64* d_vals, size_t count, int wpv, int value_bits, int limb_bits, u64* d_out, cudaStream_t st) {

@@ -24,9 +24,11 @@ pub const PB200_ERR_NOMEM: c_int = -7;
 pub const PB200_ERR_SINK: c_int = -8;
 pub const PB200_ERR_CONSTRAINT: c_int = -9;
 pub const PB200_ERR_PEER: c_int = -10;
+pub const PB200_ERR_DECRYPT: c_int = -11;
 pub const PB200_FLAG_RANGE: u32 = 1;
 pub const PB200_FLAG_CONSTRAINT: u32 = 2;
 pub const PB200_FLAG_PEER_TIMEOUT: u32 = 4;
+pub const PB200_FLAG_DECRYPT: u32 = 8;
 
 /// 64-byte handle of a key's tally mailbox (CUDA IPC), exchanged between the ranks of a multi-process tally group
 #[repr(C)]
@@ -96,6 +98,10 @@ extern "C" {
     pub fn pb200_tally_peer_export(key: *mut pb200_key, out: *mut pb200_ipc_handle) -> c_int;
     pub fn pb200_tally_peer_connect(key: *mut pb200_key, rank: c_int, world: c_int, handles: *const pb200_ipc_handle) -> c_int;
     pub fn pb200_tally_peer_dev(key: *mut pb200_key, d_c_le: *const u64, count: usize, d_out_le: *mut u64) -> c_int;
+
+    pub fn pb200_key_set_private(key: *mut pb200_key, lambda_le: *const u64, mu_le: *const u64) -> c_int;
+    pub fn pb200_decrypt_batch(key: *mut pb200_key, c_le: *const u64, count: usize, m_out_le: *mut u64) -> c_int;
+    pub fn pb200_decrypt_batch_dev(key: *mut pb200_key, d_c_le: *const u64, count: usize, d_m_out_le: *mut u64) -> c_int;
 
     pub fn pb200_encrypt_witness_batch(key: *mut pb200_key, m_le: *const u64, r_le: *const u64, count: usize, c_out_le: *mut u64,
                                        max_chunk_units: usize, sink: pb200_witness_sink_fn, user: *mut c_void) -> c_int;

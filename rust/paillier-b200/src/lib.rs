@@ -9,7 +9,7 @@
 //! compiler, and the halo2 / biguint-halo2 calls are written against those crates' APIs as the reference uses them
 //! (`/root/reference/src/paillier.rs:1-2,39-57`) plus the `BigUintChip` methods listed in SURVEY.md Appendix A
 //! [UPSTREAM-RECALL].  `tests/mockprover_cells.rs` is the first thing to run on a box that has `cargo`: it is both the
-//! MockProver acceptance test of the GPU-fed circuit and the pin of this repository's oracle (INTEGRATION.md §3c).
+//! MockProver acceptance test of the GPU-fed circuit and the pin of this repository's oracle (INTEGRATION.md §3b).
 pub mod bench;
 pub mod gpu;
 pub mod paillier;

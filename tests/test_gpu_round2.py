@@ -270,3 +270,59 @@ def test_carry_runs_are_exact_and_deterministic(built_lib, n_bits):
             assert cs == words_to_ints(want_c), rep
             assert digs == [int(d) for d in want_d], rep
         assert key.paillier_enc_native(ms, rs) == words_to_ints(want_c)
+
+
+# ---- decryption (README.md:5-22 of the reference states it, its code has none) ----------------------------------
+@pytest.mark.parametrize("n_bits", [1024, 2048, 3072, 4096])
+def test_decrypt_roundtrip_and_oracle(built_lib, n_bits):
+    """m -> encrypt -> decrypt on the GPU is the identity (random g and g = n + 1); decrypt equals the oracle on every unit;
+    the decryption of a tally is the sum of the plaintexts mod n; a non-ciphertext (a multiple of p) raises PB200_ERR_DECRYPT."""
+    from oracle.paillier_oracle import paillier_dec_native
+    from paillier_halo2_b200.api import private_from_primes
+    kd = workload.load_key(n_bits)
+    n, p, q = kd["n"], kd["p"], kd["q"]
+    count = 150 if n_bits <= 2048 else 70
+    m_w, r_w = workload.units(n_bits, count, seed_offset=17)
+    ms, rs = words_to_ints(m_w), words_to_ints(r_w)
+    ms[0], ms[1], ms[2] = 0, 1, n - 1
+    m_w = ints_to_words(ms, n_bits // 64)
+    for g in (kd["g_rand"], n + 1):
+        lam, mu = private_from_primes(p, q, g)
+        with PaillierKey(n, g, n_bits, 64) as key:
+            key.set_private(lam, mu)
+            cs = words_to_ints(key.encrypt_words(m_w, r_w))
+            assert key.decrypt(cs) == ms
+            assert key.decrypt(cs[:3]) == [paillier_dec_native(n, lam, mu, c) for c in cs[:3]]
+            assert key.decrypt([key.tally(cs)]) == [sum(ms) % n]
+            assert key.decrypt([]) == []
+            with pytest.raises(Pb200Error) as e:
+                key.decrypt([cs[0], p * 12345, cs[1]])
+            assert e.value.status == _lib.PB200_ERR_DECRYPT
+            assert key.decrypt(cs[:2]) == ms[:2]              # the key is usable afterwards
+
+
+def test_decrypt_on_the_simple_engine(built_lib):
+    """a 128-bit toy key (two 64-bit primes) and a 1024-bit key forced onto simple64: the always-available pow path"""
+    from oracle.paillier_oracle import paillier_dec_native
+    from paillier_halo2_b200.api import private_from_primes
+    p, q = 18446744073709551557, 18446744073709551533            # the two largest 64-bit primes
+    n = p * q
+    rng = random.Random(8)
+    for g in (n + 1, rng.randrange(2, n * n) % (1 << 128) | 1):
+        try:
+            lam, mu = private_from_primes(p, q, g)
+        except ValueError:
+            continue                                               # g whose L(g^lambda) is not invertible: not a valid generator
+        ms = [0, 1, n - 1] + [rng.randrange(n) for _ in range(20)]
+        rs = [rng.randrange(1, n) for _ in ms]
+        with PaillierKey(n, g, 128, 64) as key:
+            key.set_private(lam, mu)
+            cs = key.paillier_enc_native(ms, rs)
+            assert key.decrypt(cs) == ms == [paillier_dec_native(n, lam, mu, c) for c in cs]
+    kd = workload.load_key(1024)
+    lam, mu = private_from_primes(kd["p"], kd["q"], kd["g_rand"])
+    m_w, r_w = workload.units(1024, 6)
+    with PaillierKey(kd["n"], kd["g_rand"], 1024, 64) as key:
+        key.set_engine(1)
+        key.set_private(lam, mu)
+        assert key.decrypt(words_to_ints(key.encrypt_words(m_w, r_w))) == words_to_ints(m_w)

@@ -6,7 +6,7 @@ as 32 little-endian bytes.  Re-run: `python tools/gen_golden_cells.py`.
 
 `python tools/gen_golden_cells.py --dump IDX` writes the cells of flow IDX of the committed fixture, one 32-byte little-endian hex
 line per cell, to stdout: the file to diff against `target/advice_cells_flowIDX.hex` of rust/paillier-b200/tests/mockprover_cells.rs
-(the pin-on-first-toolchain recipe, INTEGRATION.md 3c)."""
+(the pin-on-first-toolchain recipe, INTEGRATION.md 3b)."""
 import hashlib, json, os, random, sys
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
