@@ -302,7 +302,7 @@ int main(int argc, char** argv) {
            "\"wide_n256\": {\"mma_per_phase\": 35, \"cycles_per_phase\": %.1f, \"cycles_per_lane_phase\": %.2f, \"cycles_per_phase_mma_only\": %.1f, "
            "\"int8_mac_issued_per_clk_per_sm_mma_only\": %.1f, \"ms\": %.3f}, "
            "\"int8_mac_useful_per_lane_phase\": %.0f, "
-           "\"note\": \"mma.sync phase of k_encrypt: ~119 SM-cycles per lane-phase (32 lanes per CTA, 2 CTAs per SM)\"}\n",
+           "\"note\": \"mma.sync phase of k_encrypt: ~240 SM-cycles per lane-phase (32 lanes per CTA, 2 CTAs per SM; profiles/ncu_k_encrypt_r02_summary.txt)\"}\n",
            ctas, LANES, iters, status, checked, bad,
            mmas, avg_mode[0] / iters, avg_mode[0] / iters / LANES, avg_mode[1] / iters, mac_narrow / (avg_mode[1] / iters), ms_mode[0],
            avg_mode[2] / iters, avg_mode[2] / iters / LANES, avg_mode[3] / iters, mac_wide / (avg_mode[3] / iters), ms_mode[2], mac_useful / LANES);
