@@ -10,6 +10,8 @@
 //   c   : gm * rn, then one exact canonicalisation (finalize) and the shift back from Nt to n^2.
 #include "engine.hpp"
 #include "block28.cuh"
+#include "block28u.cuh"
+#include <cstdio>
 #include <vector>
 #include <cstring>
 #include <cstdlib>
@@ -23,6 +25,7 @@ constexpr int SCRATCH_ENTRIES = TABN + 2;   // + r^2 (table build) + rn (kept wh
 
 struct B28Dev {            // per-key device-side descriptor (same for every configuration)
     const int4* consts;    // mu, Nt, two_sh : 3 * ENTRY4 int4
+    const int4* uconsts;   // block28u: constants + CM tables (UL<C>::KEY_BYTES), null when the configuration has no tcgen05 variant
     const int2* ops;       // r-chain schedule: (number of squarings, table index or -1)
     int n_ops;
     int first_idx;         // table index the chain starts from
@@ -144,14 +147,45 @@ __device__ __forceinline__ void load_consts(int4* smem_base, const B28Dev& K) {
     __syncthreads();
 }
 
+
+// ---- engine selection: 0 = block28 (all phases on IMAD), 1 = block28t (mma.sync for phases B, C), 2 = block28u (tcgen05) ----------
+template <class C, int ENG> struct View {
+    typedef Smem<C> type;
+    static constexpr size_t BYTES = C::SMEM_BYTES;
+    static constexpr int PER_SM = C::CTAS_PER_SM;
+};
+template <class C> struct View<C, 2> {
+    typedef SmemU<C> type;
+    static constexpr size_t BYTES = UL<C>::SMEM_BYTES;
+    static constexpr int PER_SM = UL<C>::CTAS_PER_SM;
+};
+template <class C, bool SQR, int ENG, class SV>
+__device__ __forceinline__ void mm(SV& S, const int4* Y, int role, int lane) {
+    if constexpr (ENG == 2) mulmod_u<C, SQR>(S, Y);
+    else mulmod<C, SQR, ENG == 1>(S, Y, role, lane);
+}
+// per-key constants into shared memory (+ TMEM and mbarriers for block28u)
+template <class C, int ENG, class SV>
+__device__ __forceinline__ void cta_begin(SV& S, int4* smem_base, const B28Dev& K) {
+    if constexpr (ENG == 2) {
+        int4* dst = (int4*)((unsigned char*)smem_base + UL<C>::OFF_CONST);
+        for (int i = threadIdx.x; i < UL<C>::KEY_BYTES / 16; i += C::THREADS) dst[i] = K.uconsts[i];
+        umma_setup<C>(S);
+    } else load_consts<C>(smem_base, K);
+}
+template <class C, int ENG, class SV>
+__device__ __forceinline__ void cta_end(SV& S) {
+    if constexpr (ENG == 2) umma_teardown<C>(S);
+}
+
 // V <- V * (constant in shared memory, ENTRY4 int4, broadcast)
-template <class C, bool MMA>
-__device__ __forceinline__ void mulmod_const(Smem<C>& S, const int4* cst, int role, int lane) {
+template <class C, int ENG, class SV>
+__device__ __forceinline__ void mulmod_const(SV& S, const int4* cst, int role, int lane) {
     // expand the constant into the per-lane B buffer (keeps phase_product on one code path)
 #pragma unroll
     for (int c = 0; c < C::CH; c++) S.B[(role * C::CH + c) * 32 + lane] = cst[role * C::CH + c];
     __syncthreads();
-    mulmod<C, false, MMA>(S, S.B, role, lane);
+    mm<C, false, ENG>(S, S.B, role, lane);
 }
 
 // Exact canonicalisation of the lazy value in V (one thread per lane, role 0): out = ((V * 2^sh) mod Nt) >> sh,
@@ -208,9 +242,9 @@ __device__ void canonical_out(int4* V, const int4* NtC, const B28Dev& K, u64* ou
     }
 }
 
-template <class C, bool MMA>
-__device__ __forceinline__ void finalize(Smem<C>& S, const B28Dev& K, u64* out, bool active, int role, int lane) {
-    mulmod_const<C, MMA>(S, S.two_sh, role, lane);
+template <class C, int ENG, class SV>
+__device__ __forceinline__ void finalize(SV& S, const B28Dev& K, u64* out, bool active, int role, int lane) {
+    mulmod_const<C, ENG>(S, S.two_sh, role, lane);
     if (role == 0 && active) canonical_out<C>(S.V, S.Nt, K, out, lane);
     __syncthreads();
 }
@@ -275,15 +309,15 @@ __device__ __forceinline__ void slot_release(const SlotPool& P, int slot) {
 }
 __global__ void k_nsmid(unsigned* out) { unsigned v; asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v)); *out = v; }
 
-template <class C, bool MMA>
-__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K, const u64* __restrict__ m, const u64* __restrict__ r,
+template <class C, int ENG>
+__global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_encrypt(B28Dev K, const u64* __restrict__ m, const u64* __restrict__ r,
                                                             size_t count, u64* __restrict__ c_out, int4* scratch, SlotPool pool) {
     extern __shared__ int4 smem[];
     __shared__ int s_slot;
-    Smem<C> S(smem);
+    typename View<C, ENG>::type S(smem);
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_slot = slot_acquire(pool);
-    load_consts<C>(smem, K);
+    cta_begin<C, ENG>(S, smem, K);
     const int slot = s_slot;
     size_t unit = (size_t)blockIdx.x * 32 + lane;
     const bool active = unit < count;
@@ -292,23 +326,23 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K
     // ---- r^n: odd powers table, then the per-key window schedule
     load_value<C>(S.V, r + unit * K.words_in, K.words_in, role, lane);
     copy_to_global<C>(tab, S.V, role, lane);                                   // tab[0] = r
-    mulmod<C, true, MMA>(S, nullptr, role, lane);                                   // r^2
+    mm<C, true, ENG>(S, nullptr, role, lane);                                   // r^2
     copy_to_global<C>(tab + (size_t)TABN * C::VAL4, S.V, role, lane);
     __syncthreads();
     copy_from_global<C>(S.V, tab, role, lane);
     for (int j = 1; j < TABN; j++) {
         copy_from_global<C>(S.B, tab + (size_t)TABN * C::VAL4, role, lane);
-        mulmod<C, false, MMA>(S, S.B, role, lane);                                  // r^(2j+1)
+        mm<C, false, ENG>(S, S.B, role, lane);                                  // r^(2j+1)
         copy_to_global<C>(tab + (size_t)j * C::VAL4, S.V, role, lane);
     }
     __syncthreads();
     copy_from_global<C>(S.V, tab + (size_t)K.first_idx * C::VAL4, role, lane);
     for (int o = 0; o < K.n_ops; o++) {
         int2 op = K.ops[o];
-        for (int s = 0; s < op.x; s++) mulmod<C, true, MMA>(S, nullptr, role, lane);
+        for (int s = 0; s < op.x; s++) mm<C, true, ENG>(S, nullptr, role, lane);
         if (op.y >= 0) {
             copy_from_global<C>(S.B, tab + (size_t)op.y * C::VAL4, role, lane);
-            mulmod<C, false, MMA>(S, S.B, role, lane);
+            mm<C, false, ENG>(S, S.B, role, lane);
         }
     }
     copy_to_global<C>(tab + (size_t)(TABN + 1) * C::VAL4, S.V, role, lane);    // rn
@@ -325,35 +359,36 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_encrypt(B28Dev K
     if (K.n_entry) {
         // g = n + 1: (1 + n)^m = 1 + m n (mod n^2) — one multiplication by the per-key constant n instead of the comb
         load_value<C>(S.V, mw, K.words_in, role, lane);
-        mulmod_const<C, MMA>(S, K.n_entry, role, lane);
+        mulmod_const<C, ENG>(S, K.n_entry, role, lane);
         if (role == 0) ((int*)blk_ptr<C>(S.V, 0, lane))[0] += 1;
         __syncthreads();
     } else {
         gather_entry<C>(S.V, K.tg + (size_t)comb_digit(0) * C::ENTRY4, role, lane);
         for (int i = 1; i < K.n_windows; i++) {
             gather_entry<C>(S.B, K.tg + (((size_t)i << cb) + comb_digit(i)) * C::ENTRY4, role, lane);
-            mulmod<C, false, MMA>(S, S.B, role, lane);
+            mm<C, false, ENG>(S, S.B, role, lane);
         }
     }
     // ---- c = gm * rn, canonical
     copy_from_global<C>(S.B, tab + (size_t)(TABN + 1) * C::VAL4, role, lane);
-    mulmod<C, false, MMA>(S, S.B, role, lane);
-    finalize<C, MMA>(S, K, c_out + unit * K.words_out, active, role, lane);
+    mm<C, false, ENG>(S, S.B, role, lane);
+    finalize<C, ENG>(S, K, c_out + unit * K.words_out, active, role, lane);
     if (threadIdx.x == 0) slot_release(pool, slot);
+    cta_end<C, ENG>(S);
 }
 
 // out = base^e mod n^2 for a per-key exponent e: the r-chain of k_encrypt (odd-power table in the CTA's scratch slot, sliding-window
 // schedule computed once per key) with its own schedule.  Decryption's c^lambda mod n^2.
 struct PowSched { const int2* ops; int n_ops; int first_idx; };
-template <class C, bool MMA>
-__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_pow(B28Dev K, PowSched E, const u64* __restrict__ base, int base_words,
+template <class C, int ENG>
+__global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_pow(B28Dev K, PowSched E, const u64* __restrict__ base, int base_words,
                                                                     size_t count, u64* __restrict__ out, int4* scratch, SlotPool pool) {
     extern __shared__ int4 smem[];
     __shared__ int s_slot;
-    Smem<C> S(smem);
+    typename View<C, ENG>::type S(smem);
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_slot = slot_acquire(pool);
-    load_consts<C>(smem, K);
+    cta_begin<C, ENG>(S, smem, K);
     const int slot = s_slot;
     size_t unit = (size_t)blockIdx.x * 32 + lane;
     const bool active = unit < count;
@@ -361,13 +396,13 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_pow(B28Dev K, Po
     int4* tab = scratch + (size_t)slot * SCRATCH_ENTRIES * C::VAL4;
     load_value<C>(S.V, base + unit * base_words, base_words, role, lane);
     copy_to_global<C>(tab, S.V, role, lane);                                        // tab[0] = x
-    mulmod<C, true, MMA>(S, nullptr, role, lane);                                   // x^2
+    mm<C, true, ENG>(S, nullptr, role, lane);                                   // x^2
     copy_to_global<C>(tab + (size_t)TABN * C::VAL4, S.V, role, lane);
     __syncthreads();
     copy_from_global<C>(S.V, tab, role, lane);
     for (int j = 1; j < TABN; j++) {
         copy_from_global<C>(S.B, tab + (size_t)TABN * C::VAL4, role, lane);
-        mulmod<C, false, MMA>(S, S.B, role, lane);                                  // x^(2j+1)
+        mm<C, false, ENG>(S, S.B, role, lane);                                  // x^(2j+1)
         copy_to_global<C>(tab + (size_t)j * C::VAL4, S.V, role, lane);
     }
     __syncthreads();
@@ -375,14 +410,15 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_pow(B28Dev K, Po
     else copy_from_global<C>(S.V, tab + (size_t)E.first_idx * C::VAL4, role, lane);
     for (int o = 0; o < E.n_ops; o++) {
         const int2 op = E.ops[o];
-        for (int s_ = 0; s_ < op.x; s_++) mulmod<C, true, MMA>(S, nullptr, role, lane);
+        for (int s_ = 0; s_ < op.x; s_++) mm<C, true, ENG>(S, nullptr, role, lane);
         if (op.y >= 0) {
             copy_from_global<C>(S.B, tab + (size_t)op.y * C::VAL4, role, lane);
-            mulmod<C, false, MMA>(S, S.B, role, lane);
+            mm<C, false, ENG>(S, S.B, role, lane);
         }
     }
-    finalize<C, MMA>(S, K, out + unit * K.words_out, active, role, lane);
+    finalize<C, ENG>(S, K, out + unit * K.words_out, active, role, lane);
     if (threadIdx.x == 0) slot_release(pool, slot);
+    cta_end<C, ENG>(S);
 }
 
 // ---- tally: the N-ary fold of paillier_add_native (/root/reference/src/paillier.rs:94-97) in ONE launch per GPU -------------------
@@ -423,24 +459,24 @@ __device__ __forceinline__ void set_one_where(int4* buf, bool cond, int role, in
     __syncthreads();
 }
 // V[lane] <- product over the lanes of its aligned group of `width` lanes (width a power of two <= 32)
-template <class C, bool MMA>
-__device__ __forceinline__ void fold_lanes(Smem<C>& S, int width, int role, int lane) {
+template <class C, int ENG, class SV>
+__device__ __forceinline__ void fold_lanes(SV& S, int width, int role, int lane) {
     for (int off = width >> 1; off >= 1; off >>= 1) {
 #pragma unroll
         for (int ch = 0; ch < C::CH; ch++) S.B[(role * C::CH + ch) * 32 + lane] = S.V[(role * C::CH + ch) * 32 + (lane ^ off)];
         __syncthreads();
-        mulmod<C, false, MMA>(S, S.B, role, lane);
+        mm<C, false, ENG>(S, S.B, role, lane);
     }
 }
 
-template <class C, bool MMA>
-__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, const u64* __restrict__ c, size_t count, u64* __restrict__ out,
+template <class C, int ENG>
+__global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_tally(B28Dev K, const u64* __restrict__ c, size_t count, u64* __restrict__ out,
                                                                       int4* nodes, unsigned* node_cnt, TallyPeer P) {
     extern __shared__ int4 smem[];
     __shared__ int s_first;
-    Smem<C> S(smem);
+    typename View<C, ENG>::type S(smem);
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    load_consts<C>(smem, K);
+    cta_begin<C, ENG>(S, smem, K);
     // ---- 1. main loop
     const size_t stride = (size_t)gridDim.x * 32;
     const size_t first = (size_t)blockIdx.x * 32 + lane;
@@ -452,7 +488,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, 
         stage_words<C>((u64*)S.T, c + base * K.words_out, base < count ? (int)(count - base < 32 ? count - base : 32) : 0, K.words_out);
         load_value_staged<C>(S.B, (const u64*)S.T, K.words_out, role, lane);
         set_one_where<C>(S.B, u >= count, role, lane);                               // lanes without an input multiply by one
-        mulmod<C, false, MMA>(S, S.B, role, lane);
+        mm<C, false, ENG>(S, S.B, role, lane);
     }
     // ---- 2. tree over the CTAs
     {
@@ -467,19 +503,19 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, 
                 __syncthreads();
                 if (threadIdx.x == 0) s_first = atomicAdd(node_cnt + node_base + j, 1u) == 0u;
                 __syncthreads();
-                if (s_first) return;                                                 // the sibling will pick this value up
+                if (s_first) { cta_end<C, ENG>(S); return; }                                              // the sibling will pick this value up
                 if (threadIdx.x == 0) node_cnt[node_base + j] = 0;                   // both arrived: ready for the next launch
                 __threadfence();
                 copy_from_global_cg<C>(S.B, slot + (size_t)((idx & 1) ^ 1) * C::VAL4, role, lane);
-                mulmod<C, false, MMA>(S, S.B, role, lane);
+                mm<C, false, ENG>(S, S.B, role, lane);
             }
             node_base += (size_t)((n + 1) >> 1);
             idx = j; n = (n + 1) >> 1;
         }
     }
     // ---- 3. the surviving CTA: fold its lanes, canonical partial
-    fold_lanes<C, MMA>(S, 32, role, lane);
-    if (P.world <= 1) { finalize<C, MMA>(S, K, out, lane == 0, role, lane); return; }
+    fold_lanes<C, ENG>(S, 32, role, lane);
+    if (P.world <= 1) { finalize<C, ENG>(S, K, out, lane == 0, role, lane); cta_end<C, ENG>(S); return; }
     // ---- 4. exchange over peer memory and combine.  What crosses NVLink is lane 0's LAZY value (strict digits, ENTRY4 int4): the
     // receivers multiply digit arrays directly, so neither a canonicalisation before the exchange nor a digit conversion after it
     const int par = (int)(P.epoch & 1);
@@ -517,10 +553,52 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_tally(B28Dev K, 
     }
     set_one_where<C>(S.V, lane >= P.world, role, lane);
     int width = 1; while (width < P.world) width <<= 1;
-    fold_lanes<C, MMA>(S, width, role, lane);
-    finalize<C, MMA>(S, K, out, lane == 0, role, lane);
+    fold_lanes<C, ENG>(S, width, role, lane);
+    finalize<C, ENG>(S, K, out, lane == 0, role, lane);
+    cta_end<C, ENG>(S);
 }
 
+
+
+// ---- diagnostic: one modular multiplication on raw lazy digits, on a chosen engine ---------------------------------------------
+// v_in / y_in / v_out: one CTA's values in the shared-memory image layout ([block][chunk][lane] int4, VAL4 int4); t_out: the 2L-digit
+// product after phase A (2 VAL4 int4); rows_out: the q-hat digits as packed s8 words, [lane][L].  Used by the parity tests to compare
+// the engines digit for digit (the lazy digits of block28t and block28u are specified to be identical).
+template <class C, int ENG>
+__global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_mulmod_dbg(B28Dev K, const int4* v_in, const int4* y_in, int reps,
+                                                                                 int4* v_out, int4* t_out, unsigned* rows_out) {
+    extern __shared__ int4 smem[];
+    typename View<C, ENG>::type S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    cta_begin<C, ENG>(S, smem, K);
+    copy_from_global<C>(S.V, v_in, role, lane);
+    if (t_out) {            // phase A alone
+        if (y_in) copy_from_global<C>(S.B, y_in, role, lane);
+        if constexpr (ENG == 2) phase_product_u<C>(S.V, S.B, y_in ? 0 : 1, S.tmem);
+        else if constexpr (ENG == 1) phase_product<C>(S.V, S.B, y_in ? 0 : 1);
+        else run_phase<C>(S.V, S.B, y_in ? PH_MUL : PH_SQR);
+        for (int i = threadIdx.x; i < 2 * C::VAL4; i += C::THREADS) t_out[i] = S.T[i];
+        __syncthreads();
+    } else {
+        for (int r = 0; r < reps; r++) {
+            if (y_in) { copy_from_global<C>(S.B, y_in, role, lane); mm<C, false, ENG>(S, S.B, role, lane); }
+            else mm<C, true, ENG>(S, nullptr, role, lane);
+        }
+        copy_to_global<C>(v_out, S.V, role, lane);
+        if (rows_out) {
+#pragma unroll 1
+            for (int k = 0; k < C::BL; k++) {
+                const int qd = role * C::BL + k;
+                unsigned w = 0;
+                if constexpr (ENG == 2) w = *(const unsigned*)(S.asc() + (UL<C>::FRONT + (qd >> 2)) * 512 + lane * 16 + (qd & 3) * 4);
+                else if constexpr (ENG == 1) w = ((const unsigned*)(as_ptr<C>(S) + lane * C::RS))[qd];
+                rows_out[lane * C::L + qd] = w;
+            }
+        }
+        __syncthreads();
+    }
+    cta_end<C, ENG>(S);
+}
 
 // ---- witness kernels (reference chain with exact (q, rem) per mul_mod) ---------------------------------
 struct WitDev {
@@ -760,7 +838,9 @@ struct Block28Key {
     bool pow_ready = false;
     int sms = 148;
     uint64_t n_sqr = 0, n_mul = 0;   // modular squarings / multiplications per encryption
-    bool use_mma = true;             // constant-operand phases on the tensor pipe (engine 3) or on IMAD (engine 2)
+    int eng = 1;                     // 0: all phases on IMAD (block28), 1: phases B, C on mma.sync (block28t), 2: on tcgen05 (block28u)
+    bool has_u = false;              // a block28u variant is compiled for this configuration
+    int4* d_uconsts = nullptr;
     // witness engine (lazy: block28_witness_prepare)
     BigInt n; uint32_t n_bits = 0;
     bool wit_ready = false;
@@ -782,16 +862,22 @@ static void to_entry(const BigInt& v, std::vector<int>& out) {   // centred digi
     if (carry != 0 || v.bits() > (size_t)W * C::L - 1) throw std::runtime_error("block28: constant does not fit");
 }
 
-// reversed, zero padded, byte-shifted s8 table of a constant's 7-bit digits (B operand of the IMMA phases)
+// signed 7-bit digits of a constant (4 per 28-bit digit, the top one absorbs the remainder)
 template <class C>
-static void to_rtab(const std::vector<int>& entry, std::vector<int>& out_words) {
-    std::vector<signed char> k7(C::K7, 0);
+static void to_k7(const std::vector<int>& entry, std::vector<signed char>& k7) {
+    k7.assign(C::K7, 0);
     for (int p = 0; p < C::L; p++) {
         int d = entry[(p / C::BL) * C::CH * 4 + (p % C::BL)];
         for (int i = 0; i < 3; i++) { int e = ((d + 64) & 127) - 64; k7[4 * p + i] = (signed char)e; d = (d - e) >> 7; }
         if (d < -128 || d > 127) throw std::runtime_error("block28: constant digit does not split into s8");
         k7[4 * p + 3] = (signed char)d;
     }
+}
+// reversed, zero padded, byte-shifted s8 table of a constant's 7-bit digits (B operand of the IMMA phases)
+template <class C>
+static void to_rtab(const std::vector<int>& entry, std::vector<int>& out_words) {
+    std::vector<signed char> k7;
+    to_k7<C>(entry, k7);
     std::vector<signed char> rfull(C::XLEN + 8, 0);
     for (int j = 0; j < C::K7; j++) rfull[C::PAD7 + (C::K7 - 1 - j)] = k7[j];
     std::vector<signed char> tab((size_t)C::RTAB4 * 16, 0);
@@ -827,7 +913,7 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     Block28Key* key = new Block28Key();
     key->G = C::G; key->BL = C::BL;
     key->n = n; key->n_bits = n_bits; key->device = device;
-    key->name = "block28t<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">";
+    key->name = "block28t<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">";      // block28u when the tcgen05 variant exists (below)
     cudaDeviceProp prop;
     CUK(cudaGetDeviceProperties(&prop, device));
     key->sms = prop.multiProcessorCount;
@@ -847,6 +933,24 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     all.insert(all.end(), r_nt.begin(), r_nt.end());
     CUK(cudaMalloc(&key->d_consts, all.size() * sizeof(int)));
     CUK(cudaMemcpyAsync(key->d_consts, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    if constexpr (UL<C>::SUPPORTED) {
+        // block28u: the same constants followed by the two Toeplitz core-matrix tables (image of shared memory from OFF_CONST on)
+        std::vector<signed char> img(UL<C>::KEY_BYTES, 0);
+        memcpy(img.data(), all.data(), 3 * C::ENTRY4 * 16);
+        std::vector<signed char> k7(C::K7);
+        to_k7<C>(e_mu, k7);
+        umma_cm_table<C>(k7.data(), true, img.data() + (UL<C>::OFF_CMH - UL<C>::OFF_CONST));
+        to_k7<C>(e_nt, k7);
+        umma_cm_table<C>(k7.data(), false, img.data() + (UL<C>::OFF_CML - UL<C>::OFF_CONST));
+        CUK(cudaMalloc(&key->d_uconsts, img.size()));
+        CUK(cudaMemcpyAsync(key->d_uconsts, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+        CUK(cudaStreamSynchronize(st));
+        key->has_u = true;
+        CUK((cudaFuncSetAttribute(k_encrypt<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C>::SMEM_BYTES)));
+        CUK((cudaFuncSetAttribute(k_tally<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C>::SMEM_BYTES)));
+        CUK((cudaFuncSetAttribute(k_pow<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C>::SMEM_BYTES)));
+        if (!getenv("PB200_NO_UMMA")) { key->eng = 2; key->name = "block28u<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">"; }
+    }
     // sliding-window schedule for the exponent n
     std::vector<int2> ops;
     int first_idx = window_schedule(n, ops);
@@ -873,7 +977,7 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     }
     B28Dev& K = key->dev;
     K.n_entry = key->d_nentry;
-    K.consts = key->d_consts; K.ops = key->d_ops; K.n_ops = (int)ops.size(); K.first_idx = first_idx;
+    K.consts = key->d_consts; K.uconsts = key->d_uconsts; K.ops = key->d_ops; K.n_ops = (int)ops.size(); K.first_idx = first_idx;
     K.tg = key->d_tg; K.n_windows = n_windows; K.comb_bits = comb_bits; K.words_in = (int)win; K.words_out = (int)((2 * n_bits + 63) / 64);
     K.sh = sh;
     K.sms = (unsigned)key->sms;
@@ -881,10 +985,10 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     // comb table
     CUK(cudaFuncSetAttribute(k_gtable_bases<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     CUK(cudaFuncSetAttribute(k_gtable_fill<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    CUK((cudaFuncSetAttribute(k_encrypt<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
-    CUK((cudaFuncSetAttribute(k_encrypt<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
-    CUK((cudaFuncSetAttribute(k_tally<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
-    CUK((cudaFuncSetAttribute(k_tally<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    CUK((cudaFuncSetAttribute(k_encrypt<C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    CUK((cudaFuncSetAttribute(k_encrypt<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    CUK((cudaFuncSetAttribute(k_tally<C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    CUK((cudaFuncSetAttribute(k_tally<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
     int4* d_bases = nullptr;
     if (!g_std) {      // the comb table is only needed for a general g
         CUK(cudaMalloc(&d_bases, (size_t)n_windows * C::ENTRY4 * sizeof(int4)));
@@ -911,7 +1015,12 @@ static cudaError_t ensure_slots(Block28Key* key, cudaStream_t st) {
         CUW(cudaStreamSynchronize(st));
         cudaFree(d_n);
         int per_sm = 0;
-        CUW((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encrypt<C, true>, C::THREADS, C::SMEM_BYTES)));
+        CUW((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encrypt<C, 1>, C::THREADS, C::SMEM_BYTES)));
+        if constexpr (UL<C>::SUPPORTED) {
+            int per_u = 0;
+            CUW((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_u, k_encrypt<C, 2>, C::THREADS, UL<C>::SMEM_BYTES)));
+            if (per_u > per_sm) per_sm = per_u;
+        }
         if (per_sm < 1 || per_sm > 32 || h_n == 0) return cudaErrorLaunchOutOfResources;
         key->nsmid = (int)h_n; key->enc_per_sm = per_sm;
         CUW(cudaMalloc(&key->d_slot_masks, h_n * sizeof(unsigned)));
@@ -928,8 +1037,14 @@ static cudaError_t encrypt_cfg(Block28Key* key, const u64* d_m, const u64* d_r, 
     CUW(ensure_slots<C>(key, st));
     const SlotPool pool{key->d_slot_masks, key->enc_per_sm};
     const size_t ctas = (count + 31) / 32;
-    if (key->use_mma) k_encrypt<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
-    else k_encrypt<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
+    bool done = false;
+    if constexpr (UL<C>::SUPPORTED) if (key->eng == 2) {
+        k_encrypt<C, 2><<<(unsigned)ctas, C::THREADS, UL<C>::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
+        done = true;
+    }
+    if (done) {}
+    else if (key->eng >= 1) k_encrypt<C, 1><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
+    else k_encrypt<C, 0><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
     count_launch();
     return cudaGetLastError();
 }
@@ -937,12 +1052,18 @@ static cudaError_t encrypt_cfg(Block28Key* key, const u64* d_m, const u64* d_r, 
 template <class C>
 static cudaError_t pow_cfg(Block28Key* key, const u64* d_base, int base_words, size_t count, u64* d_out, cudaStream_t st) {
     CUW(ensure_slots<C>(key, st));
-    CUW((cudaFuncSetAttribute(k_pow<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
-    CUW((cudaFuncSetAttribute(k_pow<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    CUW((cudaFuncSetAttribute(k_pow<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
+    CUW((cudaFuncSetAttribute(k_pow<C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES)));
     const SlotPool pool{key->d_slot_masks, key->enc_per_sm};
     const size_t ctas = (count + 31) / 32;
-    if (key->use_mma) k_pow<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->pow, d_base, base_words, count, d_out, key->d_scratch, pool);
-    else k_pow<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->pow, d_base, base_words, count, d_out, key->d_scratch, pool);
+    bool done = false;
+    if constexpr (UL<C>::SUPPORTED) if (key->eng == 2) {
+        k_pow<C, 2><<<(unsigned)ctas, C::THREADS, UL<C>::SMEM_BYTES, st>>>(key->dev, key->pow, d_base, base_words, count, d_out, key->d_scratch, pool);
+        done = true;
+    }
+    if (done) {}
+    else if (key->eng >= 1) k_pow<C, 1><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->pow, d_base, base_words, count, d_out, key->d_scratch, pool);
+    else k_pow<C, 0><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, key->pow, d_base, base_words, count, d_out, key->d_scratch, pool);
     count_launch();
     return cudaGetLastError();
 }
@@ -966,8 +1087,14 @@ static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64*
     TallyPeer P = key->peer;
     if (!collective || P.world <= 1) { P.world = 1; P.rank = 0; }
     else { key->peer.epoch += 1; P.epoch = key->peer.epoch; }
-    if (key->use_mma) k_tally<C, true><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
-    else k_tally<C, false><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
+    bool done = false;
+    if constexpr (UL<C>::SUPPORTED) if (key->eng == 2) {
+        k_tally<C, 2><<<(unsigned)ctas, C::THREADS, UL<C>::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
+        done = true;
+    }
+    if (done) {}
+    else if (key->eng >= 1) k_tally<C, 1><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
+    else k_tally<C, 0><<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
     count_launch();
     return cudaGetLastError();
 }
@@ -1069,6 +1196,7 @@ Block28Key* block28_create(const BigInt& n, const BigInt& g, uint32_t n_bits, in
 void block28_destroy(Block28Key* key) {
     if (!key) return;
     if (key->d_consts) cudaFree(key->d_consts);
+    if (key->d_uconsts) cudaFree(key->d_uconsts);
     if (key->d_ops) cudaFree(key->d_ops);
     if (key->d_tg) cudaFree(key->d_tg);
     if (key->d_nentry) cudaFree(key->d_nentry);
@@ -1089,10 +1217,16 @@ void block28_destroy(Block28Key* key) {
     delete key;
 }
 const char* block28_name(const Block28Key* key) { return key->name.c_str(); }
-void block28_set_mma(Block28Key* key, bool on) {
-    key->use_mma = on;
-    key->name = std::string(on ? "block28t<" : "block28<") + std::to_string(key->G) + "," + std::to_string(key->BL) + ">";
+// eng: 0 = every phase on the IMAD pipe, 1 = constant-operand phases on mma.sync, 2 = on tcgen05 (falls back to 1 when this
+// configuration has no block28u variant), -1 = the fastest available
+int block28_set_engine(Block28Key* key, int eng) {
+    if (eng < 0) eng = (key->has_u && !getenv("PB200_NO_UMMA")) ? 2 : 1;
+    if (eng == 2 && !key->has_u) eng = 1;
+    key->eng = eng;
+    key->name = std::string(eng == 2 ? "block28u<" : eng == 1 ? "block28t<" : "block28<") + std::to_string(key->G) + "," + std::to_string(key->BL) + ">";
+    return eng;
 }
+bool block28_has_umma(const Block28Key* key) { return key->has_u; }
 void block28_chain_counts(const Block28Key* key, uint64_t* n_sqr, uint64_t* n_mul) { *n_sqr = key->n_sqr; *n_mul = key->n_mul; }
 cudaError_t block28_encrypt(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st) {
     if (key->G == 4) return encrypt_cfg<Cfg1024>(key, d_m, d_r, count, d_c, st);
@@ -1162,6 +1296,52 @@ cudaError_t block28_tally_peer_connect(Block28Key* key, int rank, int world, u64
     return cudaSuccess;
 }
 
+
+template <class C, int ENG>
+static cudaError_t debug_launch(Block28Key* key, const int4* d_v, const int4* d_y, int reps, int4* d_vout, int4* d_t, unsigned* d_rows, cudaStream_t st) {
+    CUW((cudaFuncSetAttribute(k_mulmod_dbg<C, ENG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)View<C, ENG>::BYTES)));
+    k_mulmod_dbg<C, ENG><<<1, C::THREADS, View<C, ENG>::BYTES, st>>>(key->dev, d_v, d_y, reps, d_vout, d_t, d_rows);
+    count_launch();
+    return cudaGetLastError();
+}
+template <class C>
+static cudaError_t debug_cfg(Block28Key* key, int eng, const int* h_v, const int* h_y, int reps, int* h_vout, int* h_t, unsigned* h_rows, cudaStream_t st) {
+    const size_t vb = (size_t)C::VAL4 * 16;
+    int4 *d_v = nullptr, *d_y = nullptr, *d_vout = nullptr, *d_t = nullptr; unsigned* d_rows = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto run = [&]() -> cudaError_t {
+        CUW(cudaMalloc(&d_v, vb)); CUW(cudaMalloc(&d_y, vb)); CUW(cudaMalloc(&d_vout, vb)); CUW(cudaMalloc(&d_t, 2 * vb));
+        CUW(cudaMalloc(&d_rows, (size_t)32 * C::L * 4));
+        CUW(cudaMemset(d_rows, 0, (size_t)32 * C::L * 4));
+        CUW(cudaMemcpy(d_v, h_v, vb, cudaMemcpyHostToDevice));
+        if (h_y) CUW(cudaMemcpy(d_y, h_y, vb, cudaMemcpyHostToDevice));
+        cudaError_t r = cudaErrorInvalidValue;
+        if (eng == 2) { if constexpr (UL<C>::SUPPORTED) { if (key->has_u) r = debug_launch<C, 2>(key, d_v, h_y ? d_y : nullptr, reps, d_vout, h_t ? d_t : nullptr, d_rows, st); } }
+        else if (eng == 1) r = debug_launch<C, 1>(key, d_v, h_y ? d_y : nullptr, reps, d_vout, h_t ? d_t : nullptr, d_rows, st);
+        else if (eng == 0) r = debug_launch<C, 0>(key, d_v, h_y ? d_y : nullptr, reps, d_vout, h_t ? d_t : nullptr, d_rows, st);
+        CUW(r);
+        CUW(cudaStreamSynchronize(st));
+        if (h_t) CUW(cudaMemcpy(h_t, d_t, 2 * vb, cudaMemcpyDeviceToHost));
+        else {
+            CUW(cudaMemcpy(h_vout, d_vout, vb, cudaMemcpyDeviceToHost));
+            if (h_rows) CUW(cudaMemcpy(h_rows, d_rows, (size_t)32 * C::L * 4, cudaMemcpyDeviceToHost));
+        }
+        return cudaSuccess;
+    };
+    e = run();
+    cudaFree(d_v); cudaFree(d_y); cudaFree(d_vout); cudaFree(d_t); cudaFree(d_rows);
+    return e;
+}
+// eng: 0 block28, 1 block28t, 2 block28u.  h_t non-null: phase A only, the 2L-digit product; else `reps` multiplications, V and q-hat rows
+cudaError_t block28_debug_mulmod(Block28Key* key, int eng, const int* h_v, const int* h_y, int reps, int* h_vout, int* h_t, unsigned* h_rows,
+                                 cudaStream_t st) {
+    if (key->G == 4) return debug_cfg<Cfg1024>(key, eng, h_v, h_y, reps, h_vout, h_t, h_rows, st);
+    if (key->G == 8) return debug_cfg<Cfg2048>(key, eng, h_v, h_y, reps, h_vout, h_t, h_rows, st);
+    if (key->BL == 14) return debug_cfg<Cfg3072>(key, eng, h_v, h_y, reps, h_vout, h_t, h_rows, st);
+    return debug_cfg<Cfg4096>(key, eng, h_v, h_y, reps, h_vout, h_t, h_rows, st);
+}
+void block28_shape(const Block28Key* key, int* G, int* BL) { *G = key->G; *BL = key->BL; }
+
 template <class C>
 static cudaError_t add_cfg(Block28Key* key, const u64* d_c1, const u64* d_c2, int c_words, size_t count, u64* d_out, u64* d_q,
                            int* d_flags, cudaStream_t st) {
@@ -1174,7 +1354,7 @@ static cudaError_t add_cfg(Block28Key* key, const u64* d_c1, const u64* d_c2, in
 
 // The witness engine needs canonical chain values below n^2 from the first step on: n must fill its declared width
 // (then g, r < 2^n_bits <= 2n <= n^2).  Other keys keep the simple64 witness path.
-bool block28_witness_supported(const Block28Key* key) { return key->use_mma && key->n.bits() == key->n_bits && key->n_bits >= 8; }
+bool block28_witness_supported(const Block28Key* key) { return key->eng >= 1 && key->n.bits() == key->n_bits && key->n_bits >= 8; }
 cudaError_t block28_witness_prepare(Block28Key* key, u64* d_gchain, bool gchain_ready, cudaStream_t st) {
     if (key->wit_ready) return cudaSuccess;
     try {

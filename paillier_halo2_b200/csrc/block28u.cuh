@@ -1,0 +1,459 @@
+// block28u.cuh — "block28u": the two constant-operand phases of the block28 modular multiplication on the 5th-generation tensor
+// core (tcgen05.mma kind::i8, accumulators in TMEM), phase A unchanged on the IMAD pipe.
+//
+// Same arithmetic as block28t (block28.cuh, phase_mma / qhat_to_bytes / low_to_value) — the lazy digits it leaves in V are
+// bit-identical, tests/model_block28.py is the model of both — but the GEMM  C[lane][p] = sum_k A7[lane][k] K7[p - k]  is issued by
+// ONE thread and runs asynchronously: while a CTA's phases B and C are on the tensor core its warps sleep on an mbarrier, and the
+// other CTA of the SM has the IMAD pipe for its phase A.
+//
+// How 32 ciphertexts fill a 128-row MMA.  The per-lane s8 rows are stored K-major without swizzle as [16-byte K chunk][lane][16]
+// (512 B per chunk).  A UMMA descriptor with 128 B between 8-row groups then makes MMA rows 32j .. 32j+31 the SAME 32 lanes read
+// j chunks further along K (row group 4j + i lies at (i + 4j) * 128 = chunk + j).  By the Toeplitz structure a row shifted by 16j in
+// k holds the output columns shifted by 16j in p:  D[32j + lane][n] = C[lane][p_hi - n + 16j].  One N = 128 MMA therefore yields 176
+// distinct output columns per lane (for the price of 128), and — what matters more — every TMEM lane quadrant holds all 32
+// ciphertexts, so all warps of the CTA take part in the fold (a warp reads only the quadrant warp % 4).  Zero chunks in front of
+// and behind the rows (FRONT, BACK) stand in for k < 0 and k >= K7.
+//
+// The Toeplitz operand is never materialised: with the tile's columns taken in DECREASING p, core matrix (column group g, K chunk
+// j) of any (tile, k-step) is entry u0 + g + 2j of one per-key table CM[u][r][b] = Rev[8u + r + b] (descriptor strides 128 B along
+// N, 256 B along K) — csrc/microbench/umma_toeplitz.cu measured and verified this form (7 090 int8 MAC/clk/SM).
+//
+// Tiles: 160 output columns (40 digits) each, 8 ranges of 20 columns; warp w folds range 2(3 - w%4) + w/4 from TMEM quadrant w%4
+// and reads the 4 columns below its range itself for the incoming carry, so tiles and ranges are independent of each other.
+// Two TMEM buffers of 128 columns per CTA (256 columns: two CTAs per SM fit), MMAs of tile s+2 are issued as soon as the fold of
+// tile s has left its buffer.
+//
+// Shared memory (Cfg<8,19>: 112 KB, two CTAs per SM): V | B | T(2L) | tail of the q-hat rows | constants | CM(mu) | CM(Nt).
+// The q1 rows overlay V and the head of B (both dead after phase A), the q-hat rows overlay the upper half of T (dead once q1 has
+// been cut out of it); phase A's stash of Hi digits, which block28t keeps in the Q buffer, lives in TMEM columns (tcgen05.st/ld).
+#pragma once
+#include "block28.cuh"
+
+namespace pb200 {
+namespace b28 {
+
+template <class C>
+struct UL {
+    static constexpr int L = C::L, K7 = C::K7, G = C::G;
+    static constexpr int KCH = K7 / 16;                        // 16-byte K chunks per row
+    static constexpr int FRONT = 4, BACK = 3;                  // zero chunks before / after the row (k in [-64, 0) and [K7, K7 + 48))
+    static constexpr int ACH = FRONT + KCH + BACK;
+    static constexpr int A_BYTES = ACH * 512;
+    static constexpr int TN = 128, TCOLS = 160, RCOLS = 20, SHIFTC = 48;
+    static constexpr int P_BASE_H = 4 * (L - 2);               // phase B keeps two guard digits below q-hat
+    static constexpr int NT_H = (4 * (L + 2) + TCOLS - 1) / TCOLS, NT_L = (4 * L + TCOLS - 1) / TCOLS;
+    static constexpr int TMEM_COLS = 256;
+    __host__ __device__ static constexpr int p_top(bool high, int t) { return (high ? P_BASE_H + NT_H * TCOLS : NT_L * TCOLS) - 1 - TCOLS * t; }
+    __host__ __device__ static constexpr int p_hi(bool high, int t) { return p_top(high, t) - SHIFTC; }
+    // k range of a tile in the coordinates of MMA rows 0..31: the band of its 128 columns, extended 48 below zero for the shifted rows
+    __host__ __device__ static constexpr int k_start(int ph) {
+        int k_lo = ph - (TN - 1) - (K7 - 1);
+        if (k_lo < -SHIFTC) k_lo = -SHIFTC;
+        return ((k_lo + 64) / 32) * 32 - 64;
+    }
+    __host__ __device__ static constexpr int n_ksteps(int ph) { return ((ph < K7 - 1 ? ph : K7 - 1) - k_start(ph)) / 32 + 1; }
+    // Rev[z] = K7c[z0 - z]; z0 = 7 (mod 8) like every p_hi, and >= the largest p_hi - k any tile touches
+    __host__ __device__ static constexpr int z0(bool high) {
+        int m = 0;
+        for (int t = 0; t < (high ? NT_H : NT_L); t++) { const int d = p_hi(high, t) - k_start(p_hi(high, t)); if (d > m) m = d; }
+        return m + ((7 - m % 8) + 8) % 8;
+    }
+    __host__ __device__ static constexpr int ncm(bool high) {
+        int m = 0;
+        for (int t = 0; t < (high ? NT_H : NT_L); t++) {
+            const int ph = p_hi(high, t), k_last = k_start(ph) + 32 * (n_ksteps(ph) - 1);
+            const int u = (z0(high) - ph + k_last) / 8 + 18;
+            if (u > m) m = u;
+        }
+        return m;
+    }
+    static constexpr int Z0_H = z0(true), Z0_L = z0(false), NCM_H = ncm(true), NCM_L = ncm(false);
+    // byte offsets in dynamic shared memory
+    static constexpr int OFF_V = 0, OFF_B = C::VAL4 * 16, OFF_T = 2 * C::VAL4 * 16, OFF_ASC = 3 * C::VAL4 * 16;
+    static constexpr int END_ASC = OFF_ASC + A_BYTES;
+    static constexpr int OFF_CONST = ((END_ASC > 4 * C::VAL4 * 16 ? END_ASC : 4 * C::VAL4 * 16) + 127) / 128 * 128;
+    static constexpr int CONST_BYTES = (3 * C::ENTRY4 * 16 + 127) / 128 * 128;
+    static constexpr int OFF_CMH = OFF_CONST + CONST_BYTES, OFF_CML = OFF_CMH + NCM_H * 128, OFF_BAR = OFF_CML + NCM_L * 128;
+    static constexpr int KEY_BYTES = OFF_BAR - OFF_CONST;      // per-key image copied from global memory: constants, CM(mu), CM(Nt)
+    static constexpr size_t SMEM_BYTES = (size_t)OFF_BAR + 64;
+    static constexpr int CTAS_PER_SM = (int)((233472 / (SMEM_BYTES + 1024)) < (512 / C::THREADS) ? (233472 / (SMEM_BYTES + 1024)) : (512 / C::THREADS));
+    // compiled for configurations with whole k-steps per row, an even number of tiles per phase (mbarrier parities return to their
+    // start with every phase), the q1 rows inside V | B and one TMEM quadrant pair per 4 warps
+    static constexpr bool SUPPORTED = (K7 % 32 == 0) && (NT_H % 2 == 0) && (NT_L % 2 == 0) && (A_BYTES <= 2 * C::VAL4 * 16) && (G == 8) &&
+                                      (Z0_H % 8 == 7) && (Z0_L % 8 == 7) && (P_BASE_H % 8 == 0) && CTAS_PER_SM >= 1;
+};
+
+// Shared-memory view of one CTA (block28u).  Member names follow Smem<C> so the kernels are written once.
+template <class C>
+struct SmemU {
+    int4* V; int4* B; int4* T; const int4* mu; const int4* Nt; const int4* two_sh;
+    unsigned char* base;
+    uint32_t tmem;          // TMEM base address of this CTA's 256 columns
+    unsigned pb;            // bit b: parity the next wait on mbarrier b uses
+    __device__ __forceinline__ SmemU(int4* b) {
+        base = (unsigned char*)b;
+        V = b; B = V + C::VAL4; T = B + C::VAL4;
+        const int4* k = (const int4*)(base + UL<C>::OFF_CONST);
+        mu = k; Nt = k + C::ENTRY4; two_sh = k + 2 * C::ENTRY4;
+        tmem = 0; pb = 0;
+    }
+    __device__ __forceinline__ unsigned char* asb() const { return base; }
+    __device__ __forceinline__ unsigned char* asc() const { return base + UL<C>::OFF_ASC; }
+    __device__ __forceinline__ uint64_t* bars() const { return (uint64_t*)(base + UL<C>::OFF_BAR); }
+    __device__ __forceinline__ volatile uint32_t* slots() const { return (volatile uint32_t*)(base + UL<C>::OFF_BAR + 16); }   // [0] TMEM base, [1] dead
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// shared-memory matrix descriptor, K-major, no swizzle: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Bounded wait: a wrong descriptor must not hang the box.  The first time-out marks the CTA dead (every later wait returns at
+// once) and the kernel traps when it ends, so the failure is loud and the launch still terminates.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* dead) {
+    const uint32_t a = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 21); spin++) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return;
+        if (*dead) return;
+    }
+    *dead = 1;
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const int* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const int* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- per-CTA set-up / tear-down -----------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ void umma_setup(SmemU<C>& S) {
+    using U = UL<C>;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { mbar_init(&S.bars()[0], 1); mbar_init(&S.bars()[1], 1); S.slots()[1] = 0; }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32((const void*)S.slots())), "n"(U::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // the zero chunks behind the q-hat rows lie beyond T and are never written again
+    for (int i = threadIdx.x; i < U::BACK * 32; i += C::THREADS)
+        *(int4*)(S.asc() + (U::FRONT + U::KCH) * 512 + i * 16) = make_int4(0, 0, 0, 0);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    S.tmem = S.slots()[0];
+    S.pb = 0;
+}
+template <class C>
+__device__ __forceinline__ void umma_teardown(SmemU<C>& S) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(S.tmem), "n"(UL<C>::TMEM_COLS) : "memory");
+    }
+    if (S.slots()[1]) {
+        if (threadIdx.x == 0) printf("pb200 block28u: tcgen05 completion never arrived (CTA %d)\n", (int)blockIdx.x);
+        __trap();
+    }
+}
+
+// ---- phase A with the stash in TMEM --------------------------------------------------------------------------------------
+// phase_product of block28.cuh; the Hi digits of a warp's first anti-diagonal wait for the merge in TMEM columns
+// [32 (warp / 4), + CH * 4) of the warp's own lane quadrant instead of the Q buffer.
+template <class C>
+__device__ __noinline__ void phase_product_u(int4* smem_base, const int4* Y, int sqr, uint32_t tmem) {
+    constexpr int G = C::G, BL = C::BL;
+    SmemU<C> S(smem_base);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned v_addr = (unsigned)__cvta_generic_to_shared(S.V) + lane * 16;
+    const unsigned y_addr = sqr ? v_addr : (unsigned)__cvta_generic_to_shared(Y) + lane * 16;
+    const uint32_t stash = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 32);
+    Pending<C> pend;
+    pend.blk = -1;
+    int blk0 = -1, spill0 = 0;
+    const int njobs = warp < G - 1 ? 2 : 1;
+#pragma unroll 1
+    for (int half = 0; half < njobs; half++) {
+        const int d = warp + half * G;
+        const int i_lo = half ? d - G + 1 : 0;
+        const int i_hi = sqr ? d / 2 : (half ? G - 1 : d);
+        long long carry;
+        {   // columns 0 .. BL-1 -> Lo digits
+            long long acc[BL];
+#pragma unroll
+            for (int k = 0; k < BL; k++) acc[k] = 0;
+            job_half<C, false>(acc, d, i_lo, i_hi, sqr, v_addr, y_addr);
+            int lo[C::CH * 4];
+            carry = ripple_cols<C>(acc, BL, 0, lo);
+#pragma unroll
+            for (int k = BL; k < C::CH * 4; k++) lo[k] = 0;
+            store_block<C>(blk_ptr<C>(S.T, d, lane), lo);
+        }
+        {   // columns BL .. 2BL-2 -> Hi digits, last digit and spill from the final carry
+            long long acc[BL];
+#pragma unroll
+            for (int k = 0; k < BL; k++) acc[k] = 0;
+            job_half<C, true>(acc, d, i_lo, i_hi, sqr, v_addr, y_addr);
+            carry = ripple_cols<C>(acc, BL - 1, carry, pend.hi);
+            int dtop = sgxt28((int)carry);
+            pend.hi[BL - 1] = dtop;
+            pend.spill = (int)((carry - dtop) >> W);
+#pragma unroll
+            for (int k = BL; k < C::CH * 4; k++) pend.hi[k] = 0;
+        }
+        pend.carry = 0;
+        pend.blk = d;
+        if (half == 0 && njobs == 2) {          // warp-uniform
+            tmem_st16(stash, pend.hi);
+            if (C::CH * 4 > 16) tmem_st4(stash + 16, pend.hi + 16);
+            tmem_wait_st();
+            blk0 = d; spill0 = pend.spill;
+        }
+    }
+    if (warp == G - 1) store_zero_block<C>(S.T, 2 * G - 1, lane);
+    __syncthreads();
+    int carry0 = 0;
+    if (blk0 >= 0) {
+        int h0[C::CH * 4];
+        tmem_ld16(stash, h0);
+        if (C::CH * 4 > 16) tmem_ld4(stash + 16, h0 + 16);
+        tmem_wait_ld();
+        int4* p = blk_ptr<C>(S.T, blk0 + 1, lane);
+        carry0 = add_ripple_block<C>(p, p, h0, 1);
+    }
+    {
+        int4* p = blk_ptr<C>(S.T, pend.blk + 1, lane);
+        pend.carry = add_ripple_block<C>(p, p, pend.hi, 1);
+    }
+    __syncthreads();
+    if (blk0 >= 0) *(int*)blk_ptr<C>(S.T, blk0 + 2, lane) += carry0 + spill0;
+    if (pend.blk + 2 <= 2 * G - 1) *(int*)blk_ptr<C>(S.T, pend.blk + 2, lane) += pend.carry + pend.spill;
+    __syncthreads();
+}
+
+// ---- phases B and C ---------------------------------------------------------------------------------------------------------
+// BL packed words of a lane's row, starting at word w0 of the row, into the chunked layout: 128-bit stores wherever a chunk is whole
+template <int BL, int LEAD>
+__device__ __forceinline__ void store_row_u_aligned(unsigned char* rowbase, int w0, const unsigned (&w)[BL]) {
+#pragma unroll
+    for (int k = 0; k < LEAD; k++) *(unsigned*)(rowbase + ((w0 + k) >> 2) * 512 + ((w0 + k) & 3) * 4) = w[k];
+    constexpr int NV = (BL - LEAD) / 4;
+    const int c0 = (w0 + LEAD) >> 2;
+#pragma unroll
+    for (int c = 0; c < NV; c++)
+        *(uint4*)(rowbase + (c0 + c) * 512) = make_uint4(w[LEAD + 4 * c], w[LEAD + 4 * c + 1], w[LEAD + 4 * c + 2], w[LEAD + 4 * c + 3]);
+#pragma unroll
+    for (int k = LEAD + 4 * NV; k < BL; k++) *(unsigned*)(rowbase + ((w0 + k) >> 2) * 512 + ((w0 + k) & 3) * 4) = w[k];
+}
+template <int BL>
+__device__ __forceinline__ void store_row_u(unsigned char* rowbase, int w0, const unsigned (&w)[BL]) {
+    switch ((4 - (w0 & 3)) & 3) {          // warp-uniform
+        case 0: store_row_u_aligned<BL, 0>(rowbase, w0, w); break;
+        case 1: store_row_u_aligned<BL, 1>(rowbase, w0, w); break;
+        case 2: store_row_u_aligned<BL, 2>(rowbase, w0, w); break;
+        default: store_row_u_aligned<BL, 3>(rowbase, w0, w); break;
+    }
+}
+
+__device__ __forceinline__ void fold4(const int* v, int& lo, int& ca) {     // v[0..3] = columns c3, c2, c1, c0 of one digit
+    const int lowp = v[3] + (v[2] << 7), highp = v[1] + (v[0] << 7);
+    const int tb = lowp + ((highp & 0x3FFF) << 14) + (1 << (W - 1));
+    lo = (tb & ((1 << W) - 1)) - (1 << (W - 1));
+    ca = (tb >> W) + (highp >> 14);                                      // carry into the digit above
+}
+
+// all MMAs of issue slot s (HIGH: tiles from the bottom up, LOW: from the top down — longest k range first) into TMEM buffer s & 1
+template <class C, bool HIGH>
+__device__ __forceinline__ void umma_issue(const SmemU<C>& S, int s) {
+    using U = UL<C>;
+    const int t = HIGH ? U::NT_H - 1 - s : s;
+    const int ph = U::p_hi(HIGH, t), ks0 = U::k_start(ph), nks = U::n_ksteps(ph);
+    const uint32_t a_base = smem_u32(HIGH ? S.asb() : S.asc()), cm_base = smem_u32(S.base + (HIGH ? U::OFF_CMH : U::OFF_CML));
+    const uint32_t d_tmem = S.tmem + (uint32_t)((s & 1) * U::TN);
+    constexpr int Z0 = HIGH ? U::Z0_H : U::Z0_L;
+    constexpr uint32_t idesc = umma_idesc(128, U::TN);
+    for (int ks = 0; ks < nks; ks++) {
+        const int k0 = ks0 + 32 * ks;
+        umma_i8(d_tmem, umma_desc(a_base + (uint32_t)((k0 + 64) >> 4) * 512u, 512, 128),
+                umma_desc(cm_base + (uint32_t)((Z0 - ph + k0) >> 3) * 128u, 256, 128), ks > 0 ? 1u : 0u, idesc);
+    }
+    umma_commit(&S.bars()[s & 1]);
+}
+
+// fold of this warp's range of issue slot s: 5 digits (+ the digit below for its carry)
+template <class C, bool HIGH>
+__device__ __forceinline__ void umma_fold(const SmemU<C>& S, int s, int warp, int lane) {
+    using U = UL<C>;
+    constexpr int L = C::L;
+    const int t = HIGH ? U::NT_H - 1 - s : s;
+    const int j = warp & 3, i = 2 * (3 - j) + (warp >> 2);
+    const uint32_t ta = S.tmem + (uint32_t)((s & 1) * U::TN) + (uint32_t)(U::RCOLS * i - U::SHIFTC + 16 * j) + ((uint32_t)(32 * j) << 16);
+    int va[16], vb[8];
+    tmem_ld16(ta, va);
+    tmem_ld8(ta + 16, vb);
+    tmem_wait_ld();
+    int lo[6], ca[6];
+#pragma unroll
+    for (int e = 0; e < 4; e++) fold4(va + 4 * e, lo[e], ca[e]);
+    fold4(vb, lo[4], ca[4]);
+    fold4(vb + 4, lo[5], ca[5]);
+    const int d_top = 40 * (HIGH ? U::NT_H : U::NT_L) - 1 - 40 * t - 5 * i;      // digit index of e = 0 within the phase
+    if (HIGH) {
+        // q-hat digit jj - 2 = LO[jj] + CA[jj], not rippled (block28.cuh, qhat_to_bytes); the two guard digits only feed a carry
+        const bool bottom = d_top == 4;
+        int carry_g = 0;
+        if (bottom) { const int t1 = lo[3] + ca[4]; carry_g = (t1 - sgxt28(t1)) >> W; }
+        unsigned char* row = S.asc() + U::FRONT * 512 + lane * 16;
+#pragma unroll
+        for (int e = 0; e < 5; e++) {
+            const int qd = d_top - e - 2;
+            if (qd >= 0 && qd < L) {
+                const int d = lo[e] + ca[e + 1] + ((bottom && e == 2) ? carry_g : 0);
+                *(unsigned*)(row + (qd >> 2) * 512 + (qd & 3) * 4) = split7_pack(d);
+            }
+        }
+    } else {
+        // raw digit of V' = lo(T) - lo(q-hat Nt) in place in T (block28.cuh, low_to_value); rippled per block afterwards
+#pragma unroll
+        for (int e = 0; e < 5; e++) {
+            const int p = d_top - e;
+            if (p < L) {
+                int* d = &((int*)(S.T + (p / C::BL) * C::BLK4 + ((p % C::BL) >> 2) * 32 + lane))[(p % C::BL) & 3];
+                *d = *d - lo[e] - ca[e + 1];
+            }
+        }
+    }
+}
+
+// q1 = T digits [L-1, 2L-1) as s8 rows; Q = hi(q1 mu); V = ripple(lo(T) - lo(Q Nt)).  Returns the mbarrier parity bits.
+template <class C>
+__device__ __noinline__ unsigned phases_bc_umma(int4* smem_base, uint32_t tmem, unsigned pb) {
+    using U = UL<C>;
+    SmemU<C> S(smem_base);
+    S.tmem = tmem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    volatile uint32_t* dead = S.slots() + 1;
+    {
+        int a[C::CH * 4];
+        load_q1_block<C>(a, S.T, warp, lane);
+        unsigned w[C::BL];
+#pragma unroll
+        for (int k = 0; k < C::BL; k++) w[k] = split7_pack(a[k]);
+        store_row_u<C::BL>(S.asb() + U::FRONT * 512 + lane * 16, warp * C::BL, w);
+        for (int i = threadIdx.x; i < (U::FRONT + U::BACK) * 32; i += C::THREADS) {
+            const int ch = i >> 5;
+            *(int4*)(S.asb() + (ch < U::FRONT ? ch : U::KCH + ch) * 512 + (i & 31) * 16) = make_int4(0, 0, 0, 0);
+        }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, true>(S, 0); umma_issue<C, true>(S, 1); }
+    // T's upper half is dead now: zero chunks in front of the q-hat rows
+    for (int i = threadIdx.x; i < U::FRONT * 32; i += C::THREADS) *(int4*)(S.asc() + i * 16) = make_int4(0, 0, 0, 0);
+#pragma unroll 1
+    for (int s = 0; s < U::NT_H; s++) {
+        mbar_wait(&S.bars()[s & 1], (pb >> (s & 1)) & 1u, dead);
+        pb ^= 1u << (s & 1);
+        tc_fence_after();
+        umma_fold<C, true>(S, s, warp, lane);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            if (s + 2 < U::NT_H) umma_issue<C, true>(S, s + 2);
+            else if (s + 1 == U::NT_H) { umma_issue<C, false>(S, 0); umma_issue<C, false>(S, 1); }
+        }
+    }
+#pragma unroll 1
+    for (int s = 0; s < U::NT_L; s++) {
+        mbar_wait(&S.bars()[s & 1], (pb >> (s & 1)) & 1u, dead);
+        pb ^= 1u << (s & 1);
+        tc_fence_after();
+        umma_fold<C, false>(S, s, warp, lane);
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0 && s + 2 < U::NT_L) { tc_fence_after(); umma_issue<C, false>(S, s + 2); }
+    }
+    // V block = ripple(raw block), carry into digit 0 of the next block (all MMAs are complete: the q1 rows over V are dead)
+    {
+        int a[C::CH * 4];
+        load_block<C>(a, blk_ptr<C>(S.T, warp, lane), 32);
+        int carry = 0;
+#pragma unroll
+        for (int k = 0; k < C::BL; k++) {
+            const int tt = (a[k] + (1 << (W - 1))) + carry;
+            carry = tt >> W;
+            a[k] = (tt & ((1 << W) - 1)) - (1 << (W - 1));
+        }
+#pragma unroll
+        for (int k = C::BL; k < C::CH * 4; k++) a[k] = 0;
+        store_block<C>(blk_ptr<C>(S.V, warp, lane), a);
+        __syncthreads();
+        if (warp + 1 < C::G) *(int*)blk_ptr<C>(S.V, warp + 1, lane) += carry;
+        __syncthreads();
+    }
+    return pb;
+}
+
+template <class C, bool SQR>
+__device__ __forceinline__ void mulmod_u(SmemU<C>& S, const int4* Y) {
+    phase_product_u<C>(S.V, Y, SQR ? 1 : 0, S.tmem);
+    S.pb = phases_bc_umma<C>(S.V, S.tmem, S.pb);
+}
+
+// host: CM[u][r][b] = K7c[z0 - (8u + r + b)] (zero outside the constant)
+template <class C>
+inline void umma_cm_table(const signed char* k7, bool high, signed char* out /* ncm * 128 */) {
+    using U = UL<C>;
+    const int z0 = high ? U::Z0_H : U::Z0_L, n = high ? U::NCM_H : U::NCM_L;
+    for (int u = 0; u < n; u++)
+        for (int r = 0; r < 8; r++)
+            for (int b = 0; b < 16; b++) {
+                const int d = z0 - (8 * u + r + b);
+                out[(u * 8 + r) * 16 + b] = (d >= 0 && d < U::K7) ? k7[d] : (signed char)0;
+            }
+}
+
+}  // namespace b28
+}  // namespace pb200

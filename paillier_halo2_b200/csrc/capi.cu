@@ -67,7 +67,7 @@ struct pb200_key {
     int* d_flags = nullptr;
     Block28Key* fast = nullptr;
     std::string fast_why;
-    int engine = 0;                 // 0 auto, 1 simple64, 2 block28
+    int engine = 0;                 // 0 auto, 1 simple64, 2 block28, 3 block28t, 4 block28u
     DevBuf in_a, in_b, out_a, out_b, scratch, offs;
     std::string engine_name;
     // K4 cell expansion: per lookup_bits layout + device constants (n^2 limbs, word_max, q_acc, mod_acc), refresh spill vector
@@ -213,10 +213,11 @@ const char* pb200_key_engine(const pb200_key* k) {
     return use_fast(k) ? k->engine_name.c_str() : "simple64";
 }
 int pb200_key_set_engine(pb200_key* k, int engine) try {
-    if (!k || engine < 0 || engine > 3) return PB200_ERR_INVALID_ARG;
+    if (!k || engine < 0 || engine > 4) return PB200_ERR_INVALID_ARG;
     if (engine >= 2 && !k->fast) return PB200_ERR_UNSUPPORTED;
+    if (engine == 4 && !block28_has_umma(k->fast)) return PB200_ERR_UNSUPPORTED;
     k->engine = engine;
-    if (k->fast) { block28_set_mma(k->fast, engine != 2); k->engine_name = block28_name(k->fast); }
+    if (k->fast) { block28_set_engine(k->fast, engine <= 1 ? -1 : engine - 2); k->engine_name = block28_name(k->fast); }
     return PB200_OK;
 } PB200_CATCH
 void* pb200_key_stream(const pb200_key* k) { return k ? (void*)k->stream : nullptr; }
@@ -265,6 +266,23 @@ int pb200_key_take_flags(pb200_key* k, uint32_t* flags_out) try {
     *flags_out = (uint32_t)f;
     return PB200_OK;
 } PB200_CATCH
+
+// Diagnostic entry: one CTA (32 lanes) of the fast engine's modular multiplication on raw lazy digits, on engine 2 / 3 / 4.
+int pb200_debug_mulmod(pb200_key* k, int engine, const int32_t* v_in, const int32_t* y_in, int reps, int32_t* v_out, int32_t* t_out,
+                       uint32_t* qhat_rows) try {
+    if (!k || !v_in || engine < 2 || engine > 4 || (!v_out && !t_out) || reps < 1) return PB200_ERR_INVALID_ARG;
+    if (!k->fast) return PB200_ERR_UNSUPPORTED;
+    if (engine == 4 && !block28_has_umma(k->fast)) return PB200_ERR_UNSUPPORTED;
+    USE_DEVICE(k);
+    CU(block28_debug_mulmod(k->fast, engine - 2, v_in, y_in, reps, v_out, t_out, qhat_rows, k->stream));
+    return PB200_OK;
+} PB200_CATCH
+int pb200_key_shape(const pb200_key* k, int* g_out, int* bl_out) {
+    if (!k || !g_out || !bl_out) return PB200_ERR_INVALID_ARG;
+    if (!k->fast) return PB200_ERR_UNSUPPORTED;
+    block28_shape(k->fast, g_out, bl_out);
+    return PB200_OK;
+}
 
 // per-key g-chain records: by the witness engine when it serves this key (it builds its table in the same pass), else by
 // simple64 (one thread, the reference's chain)

@@ -40,7 +40,10 @@ Block28Key* block28_create(const BigInt& n, const BigInt& g, uint32_t n_bits, in
                            std::string* why, cudaError_t* cuda_err);
 void block28_destroy(Block28Key*);
 const char* block28_name(const Block28Key*);
-void block28_set_mma(Block28Key*, bool on);   // constant-operand phases on the tensor pipe (IMMA) or on IMAD
+// 0: every phase on IMAD (block28), 1: constant-operand phases on mma.sync (block28t), 2: on tcgen05 + TMEM (block28u; falls back
+// to 1 where no such variant is compiled), -1: fastest available.  Returns the engine in effect.
+int block28_set_engine(Block28Key*, int eng);
+bool block28_has_umma(const Block28Key*);
 void block28_chain_counts(const Block28Key*, uint64_t* n_sqr, uint64_t* n_mul);
 cudaError_t block28_encrypt(Block28Key*, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st);
 cudaError_t block28_tally(Block28Key*, const u64* d_c, size_t count, u64* d_out, cudaStream_t st);
@@ -65,5 +68,10 @@ cudaError_t block28_witness(Block28Key*, const u64* d_m, const u64* d_r, size_t 
 // one exact mul_mod per pair on the witness engine (requires block28_witness_prepare); range flag bit 0 when q does not fit
 cudaError_t block28_add(Block28Key*, const u64* d_c1, const u64* d_c2, int c_words, size_t count, u64* d_out, u64* d_q /*nullable*/,
                         int* d_flags, cudaStream_t st);
+
+// diagnostic: one CTA's modular multiplication on raw lazy digits (shared-memory image layout), see k_mulmod_dbg
+cudaError_t block28_debug_mulmod(Block28Key*, int eng, const int* h_v, const int* h_y, int reps, int* h_vout, int* h_t, unsigned* h_rows,
+                                 cudaStream_t st);
+void block28_shape(const Block28Key*, int* G, int* BL);
 
 }  // namespace pb200
