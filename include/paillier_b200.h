@@ -110,6 +110,9 @@ int pb200_key_take_flags(pb200_key* key, uint32_t* flags_out);
 int pb200_key_shape(const pb200_key* key, int* g_out, int* bl_out);
 int pb200_debug_mulmod(pb200_key* key, int engine, const int32_t* v_in, const int32_t* y_in, int reps, int32_t* v_out, int32_t* t_out,
                        uint32_t* qhat_rows);
+/* `reps` lazy squarings on each of `ctas` CTAs (engine 3 or 4, |n| = 2048 configuration); cycles_out[3 cta + {0, 1, 2}] = SM cycles
+ * spent in phase A, in phases B + C, in the whole loop.  stagger_cycles > 0 delays every second CTA by that many cycles first. */
+int pb200_debug_mulmod_cycles(pb200_key* key, int engine, const int32_t* v_in, int ctas, int reps, int stagger_cycles, int64_t* cycles_out);
 
 /* ---- encrypt --------------------------------------------------------------------------------
  * Replaces: paillier_enc_native (src/paillier.rs:87-92) for `count` independent (m, r) pairs, and

@@ -59,6 +59,7 @@ SYMBOLS = {
     "pb200_key_engine": (C.c_char_p, [C.c_void_p]),
     "pb200_key_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
     "pb200_key_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pb200_debug_mulmod_cycles": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pb200_debug_mulmod": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pb200_key_stream": (C.c_void_p, [C.c_void_p]),
     "pb200_key_sync": (C.c_int, [C.c_void_p]),

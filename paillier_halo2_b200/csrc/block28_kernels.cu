@@ -25,6 +25,7 @@ constexpr int SCRATCH_ENTRIES = TABN + 2;   // + r^2 (table build) + rn (kept wh
 
 struct B28Dev {            // per-key device-side descriptor (same for every configuration)
     const int4* consts;    // mu, Nt, two_sh : 3 * ENTRY4 int4
+    unsigned* utok;        // block28u: one word per SM id, the tensor-phase token of the CTAs resident there (null: no alternation)
     const int4* uconsts;   // block28u: constants + CM tables (UL<C>::KEY_BYTES), null when the configuration has no tcgen05 variant
     const int2* ops;       // r-chain schedule: (number of squarings, table index or -1)
     int n_ops;
@@ -40,6 +41,7 @@ struct B28Dev {            // per-key device-side descriptor (same for every con
 };
 
 // ---- device helpers --------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 template <class C>
 __device__ __forceinline__ int& digit_ref(int4* buf, int p, int lane) {
     int blk = p / C::BL, k = p % C::BL;
@@ -171,6 +173,7 @@ __device__ __forceinline__ void cta_begin(SV& S, int4* smem_base, const B28Dev& 
         int4* dst = (int4*)((unsigned char*)smem_base + UL<C>::OFF_CONST);
         for (int i = threadIdx.x; i < UL<C>::KEY_BYTES / 16; i += C::THREADS) dst[i] = K.uconsts[i];
         umma_setup<C>(S);
+        S.tok = K.utok ? K.utok + smid() : nullptr;
     } else load_consts<C>(smem_base, K);
 }
 template <class C, int ENG, class SV>
@@ -292,7 +295,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_gtable_fill(B28Dev K, const i
 // SM it runs on (a bit of masks[%smid], atomicCAS) and gives it back when it ends.  per_sm is the occupancy the runtime reports
 // for the kernel, so a free bit always exists; the loop still re-reads the mask should that ever not hold.
 struct SlotPool { unsigned* masks; int per_sm; };
-__device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 __device__ __forceinline__ int slot_acquire(const SlotPool& P) {
     unsigned* mk = P.masks + smid();
     const unsigned full = P.per_sm >= 32 ? 0xffffffffu : ((1u << P.per_sm) - 1u);
@@ -600,6 +602,53 @@ __global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_mulmod_dbg
     cta_end<C, ENG>(S);
 }
 
+
+// diagnostic: `reps` modular squarings per CTA on a grid of CTAs, cycles of phase A and of phases B + C accumulated by thread 0
+// (cyc[cta] = {phase A, phases B and C, whole loop}); every CTA works on the same input
+template <class C, int ENG>
+__global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_mulmod_time(B28Dev K, const int4* v_in, int reps, int stagger, long long* cyc, unsigned* sm_count) {
+    extern __shared__ int4 smem[];
+    typename View<C, ENG>::type S(smem);
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    cta_begin<C, ENG>(S, smem, K);
+    copy_from_global<C>(S.V, v_in, role, lane);
+    __shared__ unsigned s_order;
+    if (threadIdx.x == 0) s_order = atomicAdd(sm_count + smid(), 1u);
+    __syncthreads();
+    if (stagger > 0 && (s_order & 1)) {             // delay the second CTA of every SM (diagnostic of the A / tensor ping-pong between co-resident CTAs)
+        const long long t0 = clock64();
+        while (clock64() - t0 < stagger) __nanosleep(200);
+        __syncthreads();
+    }
+    long long ta = 0, tb = 0;
+    const long long t_begin = clock64();
+    // stagger -2: the first CTA of an SM runs phase A only, the second phases B + C only (interference between the two, no dependency);
+    // -3: phase A only everywhere; -4: phases B + C only everywhere
+    const bool do_a = stagger == -3 || (stagger == -2 && !(s_order & 1)) || stagger >= 0;
+    const bool do_bc = stagger == -4 || (stagger == -2 && (s_order & 1)) || stagger >= 0;
+    for (int r = 0; r < reps; r++) {
+        const long long t0 = clock64();
+        if (do_a) {
+            if constexpr (ENG == 2) phase_product_u<C>(S.V, nullptr, 1, S.tmem);
+            else phase_product<C>(S.V, nullptr, 1);
+        }
+        const long long t1 = clock64();
+        if (!do_bc) { ta += t1 - t0; continue; }
+        if constexpr (ENG == 2) S.pb = phases_bc_umma<C>(S.V, S.tmem, S.pb, (stagger & 1) || stagger < 0 ? nullptr : S.tok);
+        else {
+            q1_to_bytes<C>(S, role, lane);
+            phase_mma<C, true>(S.V);
+            qhat_to_bytes<C>(S, role, lane);
+            phase_mma<C, false>(S.V);
+            low_to_value<C>(S, role, lane);
+        }
+        const long long t2 = clock64();
+        ta += t1 - t0; tb += t2 - t1;
+    }
+    if (threadIdx.x == 0) { cyc[3 * blockIdx.x] = ta; cyc[3 * blockIdx.x + 1] = tb; cyc[3 * blockIdx.x + 2] = clock64() - t_begin; }
+    cta_end<C, ENG>(S);
+}
+
 // ---- witness kernels (reference chain with exact (q, rem) per mul_mod) ---------------------------------
 struct WitDev {
     const int4* gtab;          // [n_bits][ENTRY4]: strict digits of (g^(2^i) mod n^2) * 2^s   (i = 0: g itself)
@@ -840,7 +889,7 @@ struct Block28Key {
     uint64_t n_sqr = 0, n_mul = 0;   // modular squarings / multiplications per encryption
     int eng = 1;                     // 0: all phases on IMAD (block28), 1: phases B, C on mma.sync (block28t), 2: on tcgen05 (block28u)
     bool has_u = false;              // a block28u variant is compiled for this configuration
-    int4* d_uconsts = nullptr;
+    int4* d_uconsts = nullptr; unsigned* d_utok = nullptr;
     // witness engine (lazy: block28_witness_prepare)
     BigInt n; uint32_t n_bits = 0;
     bool wit_ready = false;
@@ -944,6 +993,10 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
         umma_cm_table<C>(k7.data(), false, img.data() + (UL<C>::OFF_CML - UL<C>::OFF_CONST));
         CUK(cudaMalloc(&key->d_uconsts, img.size()));
         CUK(cudaMemcpyAsync(key->d_uconsts, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+        if (getenv("PB200_UTOKEN")) {       // A/B switch: the CTAs of an SM take turns on the tensor core (measured slower: 130 k against 136 k enc/s)
+            CUK(cudaMalloc(&key->d_utok, 1024 * sizeof(unsigned)));
+            CUK(cudaMemsetAsync(key->d_utok, 0, 1024 * sizeof(unsigned), st));
+        }
         CUK(cudaStreamSynchronize(st));
         key->has_u = true;
         CUK((cudaFuncSetAttribute(k_encrypt<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C>::SMEM_BYTES)));
@@ -977,7 +1030,7 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     }
     B28Dev& K = key->dev;
     K.n_entry = key->d_nentry;
-    K.consts = key->d_consts; K.uconsts = key->d_uconsts; K.ops = key->d_ops; K.n_ops = (int)ops.size(); K.first_idx = first_idx;
+    K.consts = key->d_consts; K.uconsts = key->d_uconsts; K.utok = key->d_utok; K.ops = key->d_ops; K.n_ops = (int)ops.size(); K.first_idx = first_idx;
     K.tg = key->d_tg; K.n_windows = n_windows; K.comb_bits = comb_bits; K.words_in = (int)win; K.words_out = (int)((2 * n_bits + 63) / 64);
     K.sh = sh;
     K.sms = (unsigned)key->sms;
@@ -1197,6 +1250,7 @@ void block28_destroy(Block28Key* key) {
     if (!key) return;
     if (key->d_consts) cudaFree(key->d_consts);
     if (key->d_uconsts) cudaFree(key->d_uconsts);
+    if (key->d_utok) cudaFree(key->d_utok);
     if (key->d_ops) cudaFree(key->d_ops);
     if (key->d_tg) cudaFree(key->d_tg);
     if (key->d_nentry) cudaFree(key->d_nentry);
@@ -1341,6 +1395,37 @@ cudaError_t block28_debug_mulmod(Block28Key* key, int eng, const int* h_v, const
     return debug_cfg<Cfg4096>(key, eng, h_v, h_y, reps, h_vout, h_t, h_rows, st);
 }
 void block28_shape(const Block28Key* key, int* G, int* BL) { *G = key->G; *BL = key->BL; }
+
+
+template <class C, int ENG>
+static cudaError_t time_launch(Block28Key* key, const int4* d_v, int ctas, int reps, int stagger, long long* d_cyc, unsigned* d_cnt, cudaStream_t st) {
+    CUW((cudaFuncSetAttribute(k_mulmod_time<C, ENG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)View<C, ENG>::BYTES)));
+    k_mulmod_time<C, ENG><<<ctas, C::THREADS, View<C, ENG>::BYTES, st>>>(key->dev, d_v, reps, stagger, d_cyc, d_cnt);
+    count_launch();
+    return cudaGetLastError();
+}
+// eng 1 / 2; h_cyc: 3 * ctas values
+cudaError_t block28_debug_time(Block28Key* key, int eng, const int* h_v, int ctas, int reps, int stagger, long long* h_cyc, cudaStream_t st) {
+    if (key->G != 8) return cudaErrorInvalidValue;
+    typedef Cfg2048 C;
+    const size_t vb = (size_t)C::VAL4 * 16;
+    int4* d_v = nullptr; long long* d_cyc = nullptr; unsigned* d_cnt = nullptr;
+    auto run = [&]() -> cudaError_t {
+        CUW(cudaMalloc(&d_v, vb)); CUW(cudaMalloc(&d_cyc, (size_t)ctas * 3 * sizeof(long long)));
+        CUW(cudaMalloc(&d_cnt, 1024 * sizeof(unsigned))); CUW(cudaMemset(d_cnt, 0, 1024 * sizeof(unsigned)));
+        CUW(cudaMemcpy(d_v, h_v, vb, cudaMemcpyHostToDevice));
+        cudaError_t r = cudaErrorInvalidValue;
+        if (eng == 2) { if (key->has_u) r = time_launch<C, 2>(key, d_v, ctas, reps, stagger, d_cyc, d_cnt, st); }
+        else if (eng == 1) r = time_launch<C, 1>(key, d_v, ctas, reps, stagger, d_cyc, d_cnt, st);
+        CUW(r);
+        CUW(cudaStreamSynchronize(st));
+        CUW(cudaMemcpy(h_cyc, d_cyc, (size_t)ctas * 3 * sizeof(long long), cudaMemcpyDeviceToHost));
+        return cudaSuccess;
+    };
+    cudaError_t e = run();
+    cudaFree(d_v); cudaFree(d_cyc); cudaFree(d_cnt);
+    return e;
+}
 
 template <class C>
 static cudaError_t add_cfg(Block28Key* key, const u64* d_c1, const u64* d_c2, int c_words, size_t count, u64* d_out, u64* d_q,

@@ -28,6 +28,7 @@
 // been cut out of it); phase A's stash of Hi digits, which block28t keeps in the Q buffer, lives in TMEM columns (tcgen05.st/ld).
 #pragma once
 #include "block28.cuh"
+#include <type_traits>
 
 namespace pb200 {
 namespace b28 {
@@ -77,9 +78,9 @@ struct UL {
     static constexpr int KEY_BYTES = OFF_BAR - OFF_CONST;      // per-key image copied from global memory: constants, CM(mu), CM(Nt)
     static constexpr size_t SMEM_BYTES = (size_t)OFF_BAR + 64;
     static constexpr int CTAS_PER_SM = (int)((233472 / (SMEM_BYTES + 1024)) < (512 / C::THREADS) ? (233472 / (SMEM_BYTES + 1024)) : (512 / C::THREADS));
-    // compiled for configurations with whole k-steps per row, an even number of tiles per phase (mbarrier parities return to their
-    // start with every phase), the q1 rows inside V | B and one TMEM quadrant pair per 4 warps
-    static constexpr bool SUPPORTED = (K7 % 32 == 0) && (NT_H % 2 == 0) && (NT_L % 2 == 0) && (A_BYTES <= 2 * C::VAL4 * 16) && (G == 8) &&
+    // compiled for configurations with whole k-steps per row, four tiles per phase (every mbarrier completes an even number of times
+    // per multiplication, so the wait parities are compile-time constants), the q1 rows inside V | B and 8 warps (two per TMEM quadrant)
+    static constexpr bool SUPPORTED = (K7 % 32 == 0) && (NT_H == 4) && (NT_L == 4) && (A_BYTES <= 2 * C::VAL4 * 16) && (G == 8) &&
                                       (Z0_H % 8 == 7) && (Z0_L % 8 == 7) && (P_BASE_H % 8 == 0) && CTAS_PER_SM >= 1;
 };
 
@@ -90,17 +91,18 @@ struct SmemU {
     unsigned char* base;
     uint32_t tmem;          // TMEM base address of this CTA's 256 columns
     unsigned pb;            // bit b: parity the next wait on mbarrier b uses
+    unsigned* tok;          // this SM's tensor-phase token (global memory), null = no alternation between the CTAs of an SM
     __device__ __forceinline__ SmemU(int4* b) {
         base = (unsigned char*)b;
         V = b; B = V + C::VAL4; T = B + C::VAL4;
         const int4* k = (const int4*)(base + UL<C>::OFF_CONST);
         mu = k; Nt = k + C::ENTRY4; two_sh = k + 2 * C::ENTRY4;
-        tmem = 0; pb = 0;
+        tmem = 0; pb = 0; tok = nullptr;
     }
     __device__ __forceinline__ unsigned char* asb() const { return base; }
     __device__ __forceinline__ unsigned char* asc() const { return base + UL<C>::OFF_ASC; }
     __device__ __forceinline__ uint64_t* bars() const { return (uint64_t*)(base + UL<C>::OFF_BAR); }
-    __device__ __forceinline__ volatile uint32_t* slots() const { return (volatile uint32_t*)(base + UL<C>::OFF_BAR + 16); }   // [0] TMEM base, [1] dead
+    __device__ __forceinline__ volatile uint32_t* slots() const { return (volatile uint32_t*)(base + UL<C>::OFF_BAR + 32); }   // [0] TMEM base, [1] dead
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------------
@@ -121,6 +123,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -167,7 +172,8 @@ template <class C>
 __device__ __forceinline__ void umma_setup(SmemU<C>& S) {
     using U = UL<C>;
     const int warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { mbar_init(&S.bars()[0], 1); mbar_init(&S.bars()[1], 1); S.slots()[1] = 0; }
+    // bars 0, 1: the MMAs of a TMEM buffer are complete (tcgen05.commit);  2, 3: every warp has read the buffer out (one arrival per warp)
+    if (threadIdx.x == 0) { mbar_init(&S.bars()[0], 1); mbar_init(&S.bars()[1], 1); mbar_init(&S.bars()[2], C::G); mbar_init(&S.bars()[3], C::G); S.slots()[1] = 0; }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32((const void*)S.slots())), "n"(U::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -295,11 +301,44 @@ __device__ __forceinline__ void store_row_u(unsigned char* rowbase, int w0, cons
     }
 }
 
-__device__ __forceinline__ void fold4(const int* v, int& lo, int& ca) {     // v[0..3] = columns c3, c2, c1, c0 of one digit
-    const int lowp = v[3] + (v[2] << 7), highp = v[1] + (v[0] << 7);
-    const int tb = lowp + ((highp & 0x3FFF) << 14) + (1 << (W - 1));
-    lo = (tb & ((1 << W) - 1)) - (1 << (W - 1));
-    ca = (tb >> W) + (highp >> 14);                                      // carry into the digit above
+// Opaque operands.  Phases B and C share the SM with the other CTA's phase A, which saturates the FMA pipes with IMAD.WIDE, and ptxas
+// likes to turn constant left shifts, two-input adds and moves into IMAD.SHL / IMAD.IADD / IMAD.MOV — every one of them then queues
+// behind eight warps of IMAD.WIDE (measured: phases B + C 16.7 k clk alone, 29 k next to a phase-A CTA).  A shift count or a zero
+// addend read from constant memory cannot be folded away, so these become SHF and IADD3 on the ALU pipe.
+static __constant__ int c_opq[8] = {0, 1, 2, 3, 7, 9, 14, 24};
+#define OPQ_Z (c_opq[0])
+#define OPQ_1 (c_opq[1])
+#define OPQ_2 (c_opq[2])
+#define OPQ_3 (c_opq[3])
+#define OPQ_7 (c_opq[4])
+#define OPQ_9 (c_opq[5])
+#define OPQ_14 (c_opq[6])
+#define OPQ_24 (c_opq[7])
+__device__ __forceinline__ unsigned lop3_sel(unsigned a, unsigned b, unsigned m) {          // (a & ~m) | (b & m)
+    unsigned d; asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(m), "r"(b), "r"(a)); return d;      // m ? b : a
+}
+__device__ __forceinline__ unsigned lop3_xor_or(unsigned a, unsigned b, unsigned c) {       // (a ^ b) | c
+    unsigned d; asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+// split7_pack of block28.cuh on dp = d + (64 | 64 << 7 | 64 << 14), shifts and adds on the ALU pipe
+__device__ __forceinline__ unsigned split7_pack_biased(unsigned dp) {
+    const unsigned s1 = dp << OPQ_1, s2 = dp << OPQ_2, s3 = dp << OPQ_3;
+    unsigned x = lop3_sel(dp, s1, 0x7F00u);
+    x = lop3_sel(x, s2, 0x7F0000u) & 0x7F7F7Fu;
+    const unsigned y = x + 0x404040u + (unsigned)OPQ_Z;
+    return lop3_xor_or(y, 0x808080u, s3 & 0xFF000000u);
+}
+constexpr unsigned SPLIT_BIAS = 64u | (64u << 7) | (64u << 14);
+
+// v[0..3] = columns c3, c2, c1, c0 of one digit:  c0 + c1 2^7 + c2 2^14 + c3 2^21 = (lob - 2^27) + ca 2^28,  lob in [0, 2^28)
+__device__ __forceinline__ void fold4(const int* v, int& lob, int& ca) {
+    const int z = OPQ_Z;
+    const int t2 = v[3] + (v[2] << OPQ_7) + (1 << (W - 1));
+    const int highp = v[1] + (v[0] << OPQ_7) + z;
+    const int t5 = (highp << OPQ_14) & 0x0FFFC000;
+    const int tb = t2 + t5 + z;
+    lob = tb & ((1 << W) - 1);
+    ca = (tb >> W) + (highp >> 14) + z;                                  // carry into the digit above
 }
 
 // all MMAs of issue slot s (HIGH: tiles from the bottom up, LOW: from the top down — longest k range first) into TMEM buffer s & 1
@@ -312,62 +351,62 @@ __device__ __forceinline__ void umma_issue(const SmemU<C>& S, int s) {
     const uint32_t d_tmem = S.tmem + (uint32_t)((s & 1) * U::TN);
     constexpr int Z0 = HIGH ? U::Z0_H : U::Z0_L;
     constexpr uint32_t idesc = umma_idesc(128, U::TN);
-    for (int ks = 0; ks < nks; ks++) {
-        const int k0 = ks0 + 32 * ks;
-        umma_i8(d_tmem, umma_desc(a_base + (uint32_t)((k0 + 64) >> 4) * 512u, 512, 128),
-                umma_desc(cm_base + (uint32_t)((Z0 - ph + k0) >> 3) * 128u, 256, 128), ks > 0 ? 1u : 0u, idesc);
+    // descriptors of the first k-step; a k-step further is two K chunks of A (1024 B) and four table entries of B (512 B)
+    uint64_t a_desc = umma_desc(a_base + (uint32_t)((ks0 + 64) >> 4) * 512u, 512, 128);
+    uint64_t b_desc = umma_desc(cm_base + (uint32_t)((Z0 - ph + ks0) >> 3) * 128u, 256, 128);
+    umma_i8(d_tmem, a_desc, b_desc, 0u, idesc);
+#pragma unroll 4
+    for (int ks = 1; ks < nks; ks++) {
+        a_desc += 1024 >> 4; b_desc += 512 >> 4;
+        umma_i8(d_tmem, a_desc, b_desc, 1u, idesc);
     }
     umma_commit(&S.bars()[s & 1]);
 }
 
-// fold of this warp's range of issue slot s: 5 digits (+ the digit below for its carry)
+// fold of this warp's range of issue slot s: 5 digits (+ the digit below for its carry).  HIGH: packed q-hat words into the rows
+// of phase C;  LOW: lo(q-hat Nt) digit sums into the flat array F[digit][lane] (the B buffer), subtracted from T by the ripple pass.
+// dst: the address of this warp's top digit of the tile (HIGH: word 0 of its 16-byte chunk in this lane's row; LOW: its F entry)
 template <class C, bool HIGH>
-__device__ __forceinline__ void umma_fold(const SmemU<C>& S, int s, int warp, int lane) {
-    using U = UL<C>;
+__device__ __forceinline__ void umma_fold(const int* va, const int* vb, unsigned char* dst, int d_top, int r /* HIGH: (d_top - 2) & 3, warp-uniform */) {
     constexpr int L = C::L;
-    const int t = HIGH ? U::NT_H - 1 - s : s;
-    const int j = warp & 3, i = 2 * (3 - j) + (warp >> 2);
-    const uint32_t ta = S.tmem + (uint32_t)((s & 1) * U::TN) + (uint32_t)(U::RCOLS * i - U::SHIFTC + 16 * j) + ((uint32_t)(32 * j) << 16);
-    int va[16], vb[8];
-    tmem_ld16(ta, va);
-    tmem_ld8(ta + 16, vb);
-    tmem_wait_ld();
-    int lo[6], ca[6];
+    int lob[6], ca[6];
 #pragma unroll
-    for (int e = 0; e < 4; e++) fold4(va + 4 * e, lo[e], ca[e]);
-    fold4(vb, lo[4], ca[4]);
-    fold4(vb + 4, lo[5], ca[5]);
-    const int d_top = 40 * (HIGH ? U::NT_H : U::NT_L) - 1 - 40 * t - 5 * i;      // digit index of e = 0 within the phase
+    for (int e = 0; e < 4; e++) fold4(va + 4 * e, lob[e], ca[e]);
+    fold4(vb, lob[4], ca[4]);
+    fold4(vb + 4, lob[5], ca[5]);
     if (HIGH) {
         // q-hat digit jj - 2 = LO[jj] + CA[jj], not rippled (block28.cuh, qhat_to_bytes); the two guard digits only feed a carry
-        const bool bottom = d_top == 4;
         int carry_g = 0;
-        if (bottom) { const int t1 = lo[3] + ca[4]; carry_g = (t1 - sgxt28(t1)) >> W; }
-        unsigned char* row = S.asc() + U::FRONT * 512 + lane * 16;
+        if (d_top == 4) { const int t1 = lob[3] + ca[4] - (1 << (W - 1)); carry_g = (t1 - sgxt28(t1)) >> W; }
+        unsigned w[5];
 #pragma unroll
-        for (int e = 0; e < 5; e++) {
-            const int qd = d_top - e - 2;
-            if (qd >= 0 && qd < L) {
-                const int d = lo[e] + ca[e + 1] + ((bottom && e == 2) ? carry_g : 0);
-                *(unsigned*)(row + (qd >> 2) * 512 + (qd & 3) * 4) = split7_pack(d);
+        for (int e = 0; e < 5; e++)
+            w[e] = split7_pack_biased((unsigned)(lob[e] + ca[e + 1] + (int)(SPLIT_BIAS - (1u << (W - 1))) + (e == 2 ? carry_g : 0)));
+        const int qd0 = d_top - 2;
+        auto put = [&](auto RC) {
+            constexpr int R = decltype(RC)::value;
+#pragma unroll
+            for (int e = 0; e < 5; e++) {
+                const int wd = R - e, ch = wd >= 0 ? wd / 4 : -((3 - wd) / 4), word = wd - 4 * ch;
+                if ((unsigned)(qd0 - e) < (unsigned)L) *(unsigned*)(dst + ch * 512 + word * 4) = w[e];
             }
+        };
+        switch (r) {          // warp-uniform: every store gets an immediate offset
+            case 0: put(std::integral_constant<int, 0>{}); break;
+            case 1: put(std::integral_constant<int, 1>{}); break;
+            case 2: put(std::integral_constant<int, 2>{}); break;
+            default: put(std::integral_constant<int, 3>{}); break;
         }
     } else {
-        // raw digit of V' = lo(T) - lo(q-hat Nt) in place in T (block28.cuh, low_to_value); rippled per block afterwards
 #pragma unroll
-        for (int e = 0; e < 5; e++) {
-            const int p = d_top - e;
-            if (p < L) {
-                int* d = &((int*)(S.T + (p / C::BL) * C::BLK4 + ((p % C::BL) >> 2) * 32 + lane))[(p % C::BL) & 3];
-                *d = *d - lo[e] - ca[e + 1];
-            }
-        }
+        for (int e = 0; e < 5; e++)
+            if (d_top - e < L) *(int*)(dst - e * 128) = lob[e] + ca[e + 1] - (1 << (W - 1));
     }
 }
 
 // q1 = T digits [L-1, 2L-1) as s8 rows; Q = hi(q1 mu); V = ripple(lo(T) - lo(Q Nt)).  Returns the mbarrier parity bits.
 template <class C>
-__device__ __noinline__ unsigned phases_bc_umma(int4* smem_base, uint32_t tmem, unsigned pb) {
+__device__ __noinline__ unsigned phases_bc_umma(int4* smem_base, uint32_t tmem, unsigned pb, unsigned* tok) {
     using U = UL<C>;
     SmemU<C> S(smem_base);
     S.tmem = tmem;
@@ -378,7 +417,7 @@ __device__ __noinline__ unsigned phases_bc_umma(int4* smem_base, uint32_t tmem, 
         load_q1_block<C>(a, S.T, warp, lane);
         unsigned w[C::BL];
 #pragma unroll
-        for (int k = 0; k < C::BL; k++) w[k] = split7_pack(a[k]);
+        for (int k = 0; k < C::BL; k++) w[k] = split7_pack_biased((unsigned)(a[k] + (int)SPLIT_BIAS + OPQ_Z));
         store_row_u<C::BL>(S.asb() + U::FRONT * 512 + lane * 16, warp * C::BL, w);
         for (int i = threadIdx.x; i < (U::FRONT + U::BACK) * 32; i += C::THREADS) {
             const int ch = i >> 5;
@@ -386,43 +425,89 @@ __device__ __noinline__ unsigned phases_bc_umma(int4* smem_base, uint32_t tmem, 
         }
     }
     fence_async_smem();
+    // optional: the CTAs of an SM take turns on the tensor core (per-SM token in global memory)
+    if (tok && threadIdx.x == 0) {
+        int spins = 0;
+        while (atomicCAS(tok, 0u, 1u) != 0u) { __nanosleep(64); if (++spins > (1 << 22)) break; }
+    }
     __syncthreads();
     if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, true>(S, 0); umma_issue<C, true>(S, 1); }
     // T's upper half is dead now: zero chunks in front of the q-hat rows
     for (int i = threadIdx.x; i < U::FRONT * 32; i += C::THREADS) *(int4*)(S.asc() + i * 16) = make_int4(0, 0, 0, 0);
-#pragma unroll 1
-    for (int s = 0; s < U::NT_H; s++) {
-        mbar_wait(&S.bars()[s & 1], (pb >> (s & 1)) & 1u, dead);
-        pb ^= 1u << (s & 1);
-        tc_fence_after();
-        umma_fold<C, true>(S, s, warp, lane);
+    // per-thread addressing of the folds: TMEM quadrant j = warp % 4 holds the columns shifted by 16 j; range ri of a tile
+    const int j = warp & 3, ri = 2 * (3 - j) + (warp >> 2);
+    const uint32_t ta0 = S.tmem + (uint32_t)(U::RCOLS * ri - U::SHIFTC + 16 * j) + ((uint32_t)(32 * j) << 16);
+    // Tiles are not separated by CTA barriers: a warp that has read its columns out of a TMEM buffer arrives on the buffer's "empty"
+    // mbarrier and goes on folding; thread 0 alone waits for the eight arrivals, issues the MMAs of the tile after next into the
+    // buffer, then folds its own columns.  Every mbarrier completes an even number of times per multiplication (four tiles per
+    // phase), so all wait parities are constants.
+    {
+        // HIGH, issue slot s is tile t = NT_H - 1 - s: top digit of this warp's range d_top = 40 (s + 1) - 1 - 5 ri
+        const int d_top0 = 39 - 5 * ri;
+        const int r = (d_top0 - 2) & 3;
+        unsigned char* dst0 = S.asc() + U::FRONT * 512 + lane * 16 + (((d_top0 - 2) >> 2) << OPQ_9);      // (d_top0 - 2) >> 2 may be -1: floor
+#pragma unroll
+        for (int s = 0; s < U::NT_H; s++) {
+            mbar_wait(&S.bars()[s & 1], (uint32_t)((s >> 1) & 1), dead);
+            tc_fence_after();
+            int va[16], vb[8];
+            tmem_ld16(ta0 + (uint32_t)((s & 1) * U::TN), va);
+            tmem_ld8(ta0 + (uint32_t)((s & 1) * U::TN) + 16, vb);
+            tmem_wait_ld();
+            if (s + 2 < U::NT_H) {
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&S.bars()[2 + (s & 1)]);
+                if (threadIdx.x == 0) {
+                    mbar_wait(&S.bars()[2 + (s & 1)], 0u, dead);
+                    tc_fence_after();
+                    umma_issue<C, true>(S, s + 2);
+                }
+                __syncwarp();
+            }
+            umma_fold<C, true>(va, vb, dst0 + s * (10 * 512), d_top0 + 40 * s, r);
+        }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        __syncthreads();                    // q-hat rows complete
+        if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, false>(S, 0); umma_issue<C, false>(S, 1); }
+    }
+    {
+        // LOW, issue slot s is tile t = s: d_top = 40 (NT_L - s) - 1 - 5 ri
+        const int d_top0 = 40 * U::NT_L - 1 - 5 * ri;
+        unsigned char* dst0 = (unsigned char*)S.B + lane * 4 + (d_top0 << OPQ_7);
+#pragma unroll
+        for (int s = 0; s < U::NT_L; s++) {
+            mbar_wait(&S.bars()[s & 1], (uint32_t)((U::NT_H / 2 + (s >> 1)) & 1), dead);
+            if (tok && s + 1 == U::NT_L && threadIdx.x == 0) atomicExch(tok, 0u);      // all MMAs of this multiplication are complete
             tc_fence_after();
-            if (s + 2 < U::NT_H) umma_issue<C, true>(S, s + 2);
-            else if (s + 1 == U::NT_H) { umma_issue<C, false>(S, 0); umma_issue<C, false>(S, 1); }
+            int va[16], vb[8];
+            tmem_ld16(ta0 + (uint32_t)((s & 1) * U::TN), va);
+            tmem_ld8(ta0 + (uint32_t)((s & 1) * U::TN) + 16, vb);
+            tmem_wait_ld();
+            if (s + 2 < U::NT_L) {
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&S.bars()[2 + (s & 1)]);
+                if (threadIdx.x == 0) {
+                    mbar_wait(&S.bars()[2 + (s & 1)], 1u, dead);
+                    tc_fence_after();
+                    umma_issue<C, false>(S, s + 2);
+                }
+                __syncwarp();
+            }
+            umma_fold<C, false>(va, vb, dst0 - s * (40 * 128), d_top0 - 40 * s, 0);
         }
-    }
-#pragma unroll 1
-    for (int s = 0; s < U::NT_L; s++) {
-        mbar_wait(&S.bars()[s & 1], (pb >> (s & 1)) & 1u, dead);
-        pb ^= 1u << (s & 1);
-        tc_fence_after();
-        umma_fold<C, false>(S, s, warp, lane);
         tc_fence_before();
-        __syncthreads();
-        if (threadIdx.x == 0 && s + 2 < U::NT_L) { tc_fence_after(); umma_issue<C, false>(S, s + 2); }
+        __syncthreads();                    // F complete, TMEM free for the next phase A's stash
     }
-    // V block = ripple(raw block), carry into digit 0 of the next block (all MMAs are complete: the q1 rows over V are dead)
+    // V block = ripple(T block - F), carry into digit 0 of the next block (all MMAs are complete: the q1 rows over V are dead)
     {
         int a[C::CH * 4];
         load_block<C>(a, blk_ptr<C>(S.T, warp, lane), 32);
+        const int* F = (const int*)S.B + (warp * C::BL) * 32 + lane;
         int carry = 0;
 #pragma unroll
         for (int k = 0; k < C::BL; k++) {
-            const int tt = (a[k] + (1 << (W - 1))) + carry;
+            const int tt = (a[k] - F[k * 32] + (1 << (W - 1))) + carry;
             carry = tt >> W;
             a[k] = (tt & ((1 << W) - 1)) - (1 << (W - 1));
         }
@@ -439,7 +524,7 @@ __device__ __noinline__ unsigned phases_bc_umma(int4* smem_base, uint32_t tmem, 
 template <class C, bool SQR>
 __device__ __forceinline__ void mulmod_u(SmemU<C>& S, const int4* Y) {
     phase_product_u<C>(S.V, Y, SQR ? 1 : 0, S.tmem);
-    S.pb = phases_bc_umma<C>(S.V, S.tmem, S.pb);
+    S.pb = phases_bc_umma<C>(S.V, S.tmem, S.pb, S.tok);
 }
 
 // host: CM[u][r][b] = K7c[z0 - (8u + r + b)] (zero outside the constant)

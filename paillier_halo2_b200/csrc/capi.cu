@@ -277,6 +277,14 @@ int pb200_debug_mulmod(pb200_key* k, int engine, const int32_t* v_in, const int3
     CU(block28_debug_mulmod(k->fast, engine - 2, v_in, y_in, reps, v_out, t_out, qhat_rows, k->stream));
     return PB200_OK;
 } PB200_CATCH
+int pb200_debug_mulmod_cycles(pb200_key* k, int engine, const int32_t* v_in, int ctas, int reps, int stagger_cycles, int64_t* cycles_out) try {
+    if (!k || !v_in || !cycles_out || engine < 3 || engine > 4 || ctas < 1 || reps < 1) return PB200_ERR_INVALID_ARG;
+    if (!k->fast) return PB200_ERR_UNSUPPORTED;
+    if (engine == 4 && !block28_has_umma(k->fast)) return PB200_ERR_UNSUPPORTED;
+    USE_DEVICE(k);
+    CU(block28_debug_time(k->fast, engine - 2, v_in, ctas, reps, stagger_cycles, (long long*)cycles_out, k->stream));
+    return PB200_OK;
+} PB200_CATCH
 int pb200_key_shape(const pb200_key* k, int* g_out, int* bl_out) {
     if (!k || !g_out || !bl_out) return PB200_ERR_INVALID_ARG;
     if (!k->fast) return PB200_ERR_UNSUPPORTED;
