@@ -44,6 +44,23 @@ METRIC = "paillier_enc_per_s_n2048"
 UNIT = "enc/s"
 
 
+def imad_pipe(key, n_sqr, n_mul, units, kernel_s, peak):
+    """IMAD.WIDE instructions per lane the fast engines EXECUTE for the per-ciphertext product (phase A): L^2 per multiplication,
+    L (L + 1) / 2 per squaring over L = G * BL signed 28-bit digits; None for the other engines"""
+    try:
+        import ctypes as _C
+        g, bl = _C.c_int(), _C.c_int()
+        if key._lib.pb200_key_shape(key.handle, _C.byref(g), _C.byref(bl)) != 0 or not key.engine.startswith("block28"):
+            return None
+        L = g.value * bl.value
+        per_enc = n_sqr * (L * (L + 1) // 2) + n_mul * L * L
+        rate = units * per_enc / kernel_s
+        return {"digits": L, "wide_mac_executed_per_enc": per_enc, "rate_TMAC_s": rate / 1e12, "frac_of_peak": rate / peak,
+                "counts": "phase A only (all of it for block28t / block28u; block28 runs the other two products on IMAD as well)"}
+    except Exception:      # a reporting extra must never cost the bench line
+        return None
+
+
 def mac_counts(n_bits: int):
     """Algorithmic 32x32->64 MACs per modular multiplication / squaring over n^2:
     W_mul = 2*L32^2 + L32, W_sqr = (L32^2 + L32)/2 + L32^2 + L32, L32 = 2|n|/32."""
@@ -765,7 +782,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int64 columns over signed 28-bit digits (IMAD.WIDE) + s8 x s8 -> s32 (IMMA) for the constant-operand phases", "data": "synthetic",
+            "dtype": "int64 columns over signed 28-bit digits (IMAD.WIDE) + s8 x s8 -> s32 on the tensor core ("
+                     + ("tcgen05.mma kind::i8, TMEM accumulators" if key.engine.startswith("block28u") else "mma.sync" if key.engine.startswith("block28t") else "none")
+                     + ") for the constant-operand phases", "data": "synthetic",
             "config": {"workload": f"batched encrypt |n|={N_BITS} (4096-bit n^2), {units} units per GPU per step, "
                                    f"{'random g' if args.g == 'rand' else 'g = n+1'}, full-width m and r (BASELINE.json configs[1])",
                        "engine": key.engine, "l2": "flushed between timed steps (256 MiB write)",
@@ -783,9 +802,12 @@ def main():
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC/s (32x32->64 multiply-accumulate)",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get((N_BITS, units)), "peak_source": peak_src,
                          "note": "algorithmic MACs = units x (mod_sqr x W_sqr + mod_mul x W_mul), W for 32-bit limbs over n^2 "
-                                 "(SURVEY.md 8d), against the measured IMAD.WIDE rate; the block28t engine runs the per-ciphertext "
-                                 "products on the IMAD pipe and the two constant-operand Barrett products on the tensor pipe (IMMA), "
-                                 "so the fraction can exceed what the IMAD pipe alone could deliver; HBM is idle by design"},
+                                 "(SURVEY.md 8d), against the measured IMAD.WIDE rate; the block28u / block28t engines run the per-ciphertext "
+                                 "product on the IMAD pipe and the two constant-operand Barrett products on the tensor core (tcgen05 / "
+                                 "mma.sync), so the fraction can exceed what the IMAD pipe alone could deliver; imad_pipe is the share of "
+                                 "the measured IMAD.WIDE peak that the 28-bit-digit products of phase A actually executed occupy; "
+                                 "HBM is idle by design",
+                         "imad_pipe": imad_pipe(key, n_sqr, n_mul, units, kernel_s, peak)},
         }
         if not args.no_cpu and world >= 1:
             from oracle import cpu_ref

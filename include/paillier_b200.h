@@ -89,7 +89,9 @@ const char* pb200_key_engine(const pb200_key* key);
 /* choose the engine explicitly: 0 = automatic (fastest available), 1 = simple64 (thread per
  * ciphertext, always available, used as the on-GPU cross-check), 2 = block28 (warp-role Barrett, all
  * products on the IMAD pipe), 3 = block28t (same, constant-operand Barrett phases on the tensor pipe with mma.sync), 4 = block28u
- * (the same phases on tcgen05.mma with TMEM accumulators; PB200_ERR_UNSUPPORTED for key sizes without that variant) */
+ * (the same phases on tcgen05.mma with TMEM accumulators, 32 ciphertexts per CTA; the automatic choice where it exists), 5 = block28u2
+ * (tcgen05 with 64 ciphertexts per CTA and half the tensor-core work per ciphertext; kept for A/B).  4 and 5 return
+ * PB200_ERR_UNSUPPORTED for key sizes without that variant */
 int pb200_key_set_engine(pb200_key* key, int engine);
 void* pb200_key_stream(const pb200_key* key);        /* cudaStream_t the key enqueues on */
 /* modular squarings and multiplications the selected engine executes per encryption (the chain the
@@ -103,14 +105,14 @@ int pb200_key_take_flags(pb200_key* key, uint32_t* flags_out);
 
 /* Diagnostics of the fast engine (block28 family).  pb200_key_shape: G blocks of BL signed 28-bit digits per value.
  * pb200_debug_mulmod: ONE CTA's (32 lanes) lazy modular multiplication V <- V * Y (y_in null: V^2), repeated `reps` times, on
- * engine 2, 3 or 4, on raw digit images in the engine's shared-memory layout ([block][chunk of 4 digits][lane][4] int32,
+ * engine 2, 3, 4 or 5, on raw digit images in the engine's shared-memory layout ([block][chunk of 4 digits][lane][4] int32,
  * G * ceil(BL / 4) * 32 * 4 words).  t_out non-null: phase A only, the 2L-digit product image (twice that many words).  Otherwise
  * v_out receives the lazy result and qhat_rows (nullable, 32 * G * BL words) the quotient estimate's packed s8 digits.  The
  * engines are specified to agree digit for digit; the parity tests check exactly that. */
 int pb200_key_shape(const pb200_key* key, int* g_out, int* bl_out);
 int pb200_debug_mulmod(pb200_key* key, int engine, const int32_t* v_in, const int32_t* y_in, int reps, int32_t* v_out, int32_t* t_out,
                        uint32_t* qhat_rows);
-/* `reps` lazy squarings on each of `ctas` CTAs (engine 3 or 4, |n| = 2048 configuration); cycles_out[3 cta + {0, 1, 2}] = SM cycles
+/* `reps` lazy squarings on each of `ctas` CTAs (engine 3, 4 or 5, |n| = 2048 configuration); cycles_out[3 cta + {0, 1, 2}] = SM cycles
  * spent in phase A, in phases B + C, in the whole loop.  stagger_cycles > 0 delays every second CTA by that many cycles first. */
 int pb200_debug_mulmod_cycles(pb200_key* key, int engine, const int32_t* v_in, int ctas, int reps, int stagger_cycles, int64_t* cycles_out);
 

@@ -25,7 +25,7 @@ constexpr int SCRATCH_ENTRIES = TABN + 2;   // + r^2 (table build) + rn (kept wh
 
 struct B28Dev {            // per-key device-side descriptor (same for every configuration)
     const int4* consts;    // mu, Nt, two_sh : 3 * ENTRY4 int4
-    unsigned* utok;        // block28u: one word per SM id, the tensor-phase token of the CTAs resident there (null: no alternation)
+    const int4* uconsts2;  // the same for the two-lane-group variant
     const int4* uconsts;   // block28u: constants + CM tables (UL<C>::KEY_BYTES), null when the configuration has no tcgen05 variant
     const int2* ops;       // r-chain schedule: (number of squarings, table index or -1)
     int n_ops;
@@ -155,30 +155,39 @@ template <class C, int ENG> struct View {
     typedef Smem<C> type;
     static constexpr size_t BYTES = C::SMEM_BYTES;
     static constexpr int PER_SM = C::CTAS_PER_SM;
+    static constexpr int LG = 1, THREADS = C::THREADS;
 };
-template <class C> struct View<C, 2> {
-    typedef SmemU<C> type;
-    static constexpr size_t BYTES = UL<C>::SMEM_BYTES;
-    static constexpr int PER_SM = UL<C>::CTAS_PER_SM;
+template <class C> struct View<C, 2> {            // block28u, one lane group per CTA
+    typedef SmemU<C, 1> type;
+    static constexpr size_t BYTES = UL<C, 1>::SMEM_BYTES;
+    static constexpr int PER_SM = UL<C, 1>::CTAS_PER_SM;
+    static constexpr int LG = 1, THREADS = C::THREADS;
+};
+template <class C> struct View<C, 3> {            // block28u, two lane groups (64 ciphertexts) per CTA
+    typedef SmemU<C, 2> type;
+    static constexpr size_t BYTES = UL<C, 2>::SMEM_BYTES;
+    static constexpr int PER_SM = UL<C, 2>::CTAS_PER_SM;
+    static constexpr int LG = 2, THREADS = 2 * C::THREADS;
 };
 template <class C, bool SQR, int ENG, class SV>
 __device__ __forceinline__ void mm(SV& S, const int4* Y, int role, int lane) {
-    if constexpr (ENG == 2) mulmod_u<C, SQR>(S, Y);
+    if constexpr (ENG >= 2) mulmod_u<C, View<C, ENG>::LG, SQR>(S, Y);
     else mulmod<C, SQR, ENG == 1>(S, Y, role, lane);
 }
 // per-key constants into shared memory (+ TMEM and mbarriers for block28u)
 template <class C, int ENG, class SV>
 __device__ __forceinline__ void cta_begin(SV& S, int4* smem_base, const B28Dev& K) {
-    if constexpr (ENG == 2) {
-        int4* dst = (int4*)((unsigned char*)smem_base + UL<C>::OFF_CONST);
-        for (int i = threadIdx.x; i < UL<C>::KEY_BYTES / 16; i += C::THREADS) dst[i] = K.uconsts[i];
-        umma_setup<C>(S);
-        S.tok = K.utok ? K.utok + smid() : nullptr;
+    if constexpr (ENG >= 2) {
+        typedef UL<C, View<C, ENG>::LG> U;
+        int4* dst = (int4*)((unsigned char*)smem_base + U::OFF_CONST);
+        const int4* src = ENG == 2 ? K.uconsts : K.uconsts2;
+        for (int i = threadIdx.x; i < U::KEY_BYTES / 16; i += U::THREADS) dst[i] = src[i];
+        umma_setup<C, View<C, ENG>::LG>(S);
     } else load_consts<C>(smem_base, K);
 }
 template <class C, int ENG, class SV>
 __device__ __forceinline__ void cta_end(SV& S) {
-    if constexpr (ENG == 2) umma_teardown<C>(S);
+    if constexpr (ENG >= 2) umma_teardown<C, View<C, ENG>::LG>(S);
 }
 
 // V <- V * (constant in shared memory, ENTRY4 int4, broadcast)
@@ -312,16 +321,17 @@ __device__ __forceinline__ void slot_release(const SlotPool& P, int slot) {
 __global__ void k_nsmid(unsigned* out) { unsigned v; asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v)); *out = v; }
 
 template <class C, int ENG>
-__global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_encrypt(B28Dev K, const u64* __restrict__ m, const u64* __restrict__ r,
+__global__ void __launch_bounds__(View<C, ENG>::THREADS, View<C, ENG>::PER_SM) k_encrypt(B28Dev K, const u64* __restrict__ m, const u64* __restrict__ r,
                                                             size_t count, u64* __restrict__ c_out, int4* scratch, SlotPool pool) {
     extern __shared__ int4 smem[];
-    __shared__ int s_slot;
+    __shared__ int s_slot[2];
+    constexpr int LG = View<C, ENG>::LG;
     typename View<C, ENG>::type S(smem);
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_slot = slot_acquire(pool);
+    const int lane = threadIdx.x & 31, role = (threadIdx.x >> 5) % C::G, grp = (threadIdx.x >> 5) / C::G;      // grp: lane group (LG per CTA)
+    if (threadIdx.x == 0) for (int g = 0; g < LG; g++) s_slot[g] = slot_acquire(pool);
     cta_begin<C, ENG>(S, smem, K);
-    const int slot = s_slot;
-    size_t unit = (size_t)blockIdx.x * 32 + lane;
+    const int slot = s_slot[grp];
+    size_t unit = (size_t)blockIdx.x * (32 * LG) + grp * 32 + lane;
     const bool active = unit < count;
     if (!active) unit = count - 1;
     int4* tab = scratch + (size_t)slot * SCRATCH_ENTRIES * C::VAL4;
@@ -375,7 +385,7 @@ __global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_encrypt(B2
     copy_from_global<C>(S.B, tab + (size_t)(TABN + 1) * C::VAL4, role, lane);
     mm<C, false, ENG>(S, S.B, role, lane);
     finalize<C, ENG>(S, K, c_out + unit * K.words_out, active, role, lane);
-    if (threadIdx.x == 0) slot_release(pool, slot);
+    if (threadIdx.x == 0) for (int g = 0; g < LG; g++) slot_release(pool, s_slot[g]);
     cta_end<C, ENG>(S);
 }
 
@@ -383,16 +393,17 @@ __global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_encrypt(B2
 // schedule computed once per key) with its own schedule.  Decryption's c^lambda mod n^2.
 struct PowSched { const int2* ops; int n_ops; int first_idx; };
 template <class C, int ENG>
-__global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_pow(B28Dev K, PowSched E, const u64* __restrict__ base, int base_words,
+__global__ void __launch_bounds__(View<C, ENG>::THREADS, View<C, ENG>::PER_SM) k_pow(B28Dev K, PowSched E, const u64* __restrict__ base, int base_words,
                                                                     size_t count, u64* __restrict__ out, int4* scratch, SlotPool pool) {
     extern __shared__ int4 smem[];
-    __shared__ int s_slot;
+    __shared__ int s_slot[2];
+    constexpr int LG = View<C, ENG>::LG;
     typename View<C, ENG>::type S(smem);
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_slot = slot_acquire(pool);
+    const int lane = threadIdx.x & 31, role = (threadIdx.x >> 5) % C::G, grp = (threadIdx.x >> 5) / C::G;      // grp: lane group (LG per CTA)
+    if (threadIdx.x == 0) for (int g = 0; g < LG; g++) s_slot[g] = slot_acquire(pool);
     cta_begin<C, ENG>(S, smem, K);
-    const int slot = s_slot;
-    size_t unit = (size_t)blockIdx.x * 32 + lane;
+    const int slot = s_slot[grp];
+    size_t unit = (size_t)blockIdx.x * (32 * LG) + grp * 32 + lane;
     const bool active = unit < count;
     if (!active) unit = count - 1;
     int4* tab = scratch + (size_t)slot * SCRATCH_ENTRIES * C::VAL4;
@@ -419,7 +430,7 @@ __global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_pow(B28Dev
         }
     }
     finalize<C, ENG>(S, K, out + unit * K.words_out, active, role, lane);
-    if (threadIdx.x == 0) slot_release(pool, slot);
+    if (threadIdx.x == 0) for (int g = 0; g < LG; g++) slot_release(pool, s_slot[g]);
     cta_end<C, ENG>(S);
 }
 
@@ -567,32 +578,35 @@ __global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_tally(B28D
 // product after phase A (2 VAL4 int4); rows_out: the q-hat digits as packed s8 words, [lane][L].  Used by the parity tests to compare
 // the engines digit for digit (the lazy digits of block28t and block28u are specified to be identical).
 template <class C, int ENG>
-__global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_mulmod_dbg(B28Dev K, const int4* v_in, const int4* y_in, int reps,
+__global__ void __launch_bounds__(View<C, ENG>::THREADS, View<C, ENG>::PER_SM) k_mulmod_dbg(B28Dev K, const int4* v_in, const int4* y_in, int reps,
                                                                                  int4* v_out, int4* t_out, unsigned* rows_out) {
     extern __shared__ int4 smem[];
     typename View<C, ENG>::type S(smem);
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    constexpr int LG = View<C, ENG>::LG;
+    const int lane = threadIdx.x & 31, role = (threadIdx.x >> 5) % C::G, grp = (threadIdx.x >> 5) / C::G;      // every lane group works on the same input
     cta_begin<C, ENG>(S, smem, K);
     copy_from_global<C>(S.V, v_in, role, lane);
     if (t_out) {            // phase A alone
         if (y_in) copy_from_global<C>(S.B, y_in, role, lane);
-        if constexpr (ENG == 2) phase_product_u<C>(S.V, S.B, y_in ? 0 : 1, S.tmem);
+        if constexpr (ENG >= 2) phase_product_u<C, LG>(smem, S.B, y_in ? 0 : 1, S.tmem);
         else if constexpr (ENG == 1) phase_product<C>(S.V, S.B, y_in ? 0 : 1);
         else run_phase<C>(S.V, S.B, y_in ? PH_MUL : PH_SQR);
-        for (int i = threadIdx.x; i < 2 * C::VAL4; i += C::THREADS) t_out[i] = S.T[i];
+        if constexpr (ENG >= 2) {
+            if (grp == LG - 1) for (int i = threadIdx.x % C::THREADS; i < 2 * C::VAL4; i += C::THREADS) t_out[i] = *(S.tblk(i / C::BLK4, 0) + i % C::BLK4);
+        } else for (int i = threadIdx.x; i < 2 * C::VAL4; i += C::THREADS) t_out[i] = S.T[i];
         __syncthreads();
     } else {
         for (int r = 0; r < reps; r++) {
             if (y_in) { copy_from_global<C>(S.B, y_in, role, lane); mm<C, false, ENG>(S, S.B, role, lane); }
             else mm<C, true, ENG>(S, nullptr, role, lane);
         }
-        copy_to_global<C>(v_out, S.V, role, lane);
-        if (rows_out) {
+        if (grp == LG - 1) copy_to_global<C>(v_out, S.V, role, lane);
+        if (rows_out && grp == LG - 1) {
 #pragma unroll 1
             for (int k = 0; k < C::BL; k++) {
                 const int qd = role * C::BL + k;
                 unsigned w = 0;
-                if constexpr (ENG == 2) w = *(const unsigned*)(S.asc() + (UL<C>::FRONT + (qd >> 2)) * 512 + lane * 16 + (qd & 3) * 4);
+                if constexpr (ENG >= 2) w = *(const unsigned*)(S.asc() + (UL<C, LG>::FRONT + (qd >> 2)) * UL<C, LG>::CHB + (grp * 32 + lane) * 16 + (qd & 3) * 4);
                 else if constexpr (ENG == 1) w = ((const unsigned*)(as_ptr<C>(S) + lane * C::RS))[qd];
                 rows_out[lane * C::L + qd] = w;
             }
@@ -606,10 +620,11 @@ __global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_mulmod_dbg
 // diagnostic: `reps` modular squarings per CTA on a grid of CTAs, cycles of phase A and of phases B + C accumulated by thread 0
 // (cyc[cta] = {phase A, phases B and C, whole loop}); every CTA works on the same input
 template <class C, int ENG>
-__global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_mulmod_time(B28Dev K, const int4* v_in, int reps, int stagger, long long* cyc, unsigned* sm_count) {
+__global__ void __launch_bounds__(View<C, ENG>::THREADS, View<C, ENG>::PER_SM) k_mulmod_time(B28Dev K, const int4* v_in, int reps, int stagger, long long* cyc, unsigned* sm_count) {
     extern __shared__ int4 smem[];
     typename View<C, ENG>::type S(smem);
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    constexpr int LG = View<C, ENG>::LG;
+    const int lane = threadIdx.x & 31, role = (threadIdx.x >> 5) % C::G;
     cta_begin<C, ENG>(S, smem, K);
     copy_from_global<C>(S.V, v_in, role, lane);
     __shared__ unsigned s_order;
@@ -629,12 +644,12 @@ __global__ void __launch_bounds__(C::THREADS, View<C, ENG>::PER_SM) k_mulmod_tim
     for (int r = 0; r < reps; r++) {
         const long long t0 = clock64();
         if (do_a) {
-            if constexpr (ENG == 2) phase_product_u<C>(S.V, nullptr, 1, S.tmem);
+            if constexpr (ENG >= 2) phase_product_u<C, LG>(smem, nullptr, 1, S.tmem);
             else phase_product<C>(S.V, nullptr, 1);
         }
         const long long t1 = clock64();
         if (!do_bc) { ta += t1 - t0; continue; }
-        if constexpr (ENG == 2) S.pb = phases_bc_umma<C>(S.V, S.tmem, S.pb, (stagger & 1) || stagger < 0 ? nullptr : S.tok);
+        if constexpr (ENG >= 2) phases_bc_umma<C, LG>(smem, S.tmem);
         else {
             q1_to_bytes<C>(S, role, lane);
             phase_mma<C, true>(S.V);
@@ -887,9 +902,10 @@ struct Block28Key {
     bool pow_ready = false;
     int sms = 148;
     uint64_t n_sqr = 0, n_mul = 0;   // modular squarings / multiplications per encryption
-    int eng = 1;                     // 0: all phases on IMAD (block28), 1: phases B, C on mma.sync (block28t), 2: on tcgen05 (block28u)
+    int eng = 1;                     // 0: all phases on IMAD (block28), 1: phases B, C on mma.sync (block28t), 2: on tcgen05, 32 ciphertexts per
+                                     // CTA (block28u), 3: on tcgen05, 64 per CTA (block28u2; the tally and keys without that variant run as 2)
     bool has_u = false;              // a block28u variant is compiled for this configuration
-    int4* d_uconsts = nullptr; unsigned* d_utok = nullptr;
+    int4* d_uconsts = nullptr; int4* d_uconsts2 = nullptr; bool has_u2 = false;
     // witness engine (lazy: block28_witness_prepare)
     BigInt n; uint32_t n_bits = 0;
     bool wit_ready = false;
@@ -962,7 +978,7 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     Block28Key* key = new Block28Key();
     key->G = C::G; key->BL = C::BL;
     key->n = n; key->n_bits = n_bits; key->device = device;
-    key->name = "block28t<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">";      // block28u when the tcgen05 variant exists (below)
+    key->name = "block28t<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">";      // block28_set_engine(-1) below picks the fastest
     cudaDeviceProp prop;
     CUK(cudaGetDeviceProperties(&prop, device));
     key->sms = prop.multiProcessorCount;
@@ -982,28 +998,38 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     all.insert(all.end(), r_nt.begin(), r_nt.end());
     CUK(cudaMalloc(&key->d_consts, all.size() * sizeof(int)));
     CUK(cudaMemcpyAsync(key->d_consts, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    if constexpr (UL<C>::SUPPORTED) {
-        // block28u: the same constants followed by the two Toeplitz core-matrix tables (image of shared memory from OFF_CONST on)
-        std::vector<signed char> img(UL<C>::KEY_BYTES, 0);
+    // block28u: the same constants followed by the two Toeplitz core-matrix tables (image of shared memory from OFF_CONST on), for
+    // one and for two lane groups per CTA
+    auto u_image = [&](auto LGC, int4** d_out) -> cudaError_t {
+        constexpr int LG = decltype(LGC)::value;
+        typedef UL<C, LG> U;
+        std::vector<signed char> img(U::KEY_BYTES, 0);
         memcpy(img.data(), all.data(), 3 * C::ENTRY4 * 16);
         std::vector<signed char> k7(C::K7);
         to_k7<C>(e_mu, k7);
-        umma_cm_table<C>(k7.data(), true, img.data() + (UL<C>::OFF_CMH - UL<C>::OFF_CONST));
+        umma_cm_table<C, LG>(k7.data(), true, img.data() + (U::OFF_CMH - U::OFF_CONST));
         to_k7<C>(e_nt, k7);
-        umma_cm_table<C>(k7.data(), false, img.data() + (UL<C>::OFF_CML - UL<C>::OFF_CONST));
-        CUK(cudaMalloc(&key->d_uconsts, img.size()));
-        CUK(cudaMemcpyAsync(key->d_uconsts, img.data(), img.size(), cudaMemcpyHostToDevice, st));
-        if (getenv("PB200_UTOKEN")) {       // A/B switch: the CTAs of an SM take turns on the tensor core (measured slower: 130 k against 136 k enc/s)
-            CUK(cudaMalloc(&key->d_utok, 1024 * sizeof(unsigned)));
-            CUK(cudaMemsetAsync(key->d_utok, 0, 1024 * sizeof(unsigned), st));
-        }
-        CUK(cudaStreamSynchronize(st));
+        umma_cm_table<C, LG>(k7.data(), false, img.data() + (U::OFF_CML - U::OFF_CONST));
+        cudaError_t e = cudaMalloc(d_out, img.size());
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(*d_out, img.data(), img.size(), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(st);
+    };
+    if constexpr (UL<C, 1>::SUPPORTED) {
+        CUK(u_image(std::integral_constant<int, 1>{}, &key->d_uconsts));
         key->has_u = true;
-        CUK((cudaFuncSetAttribute(k_encrypt<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C>::SMEM_BYTES)));
-        CUK((cudaFuncSetAttribute(k_tally<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C>::SMEM_BYTES)));
-        CUK((cudaFuncSetAttribute(k_pow<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C>::SMEM_BYTES)));
-        if (!getenv("PB200_NO_UMMA")) { key->eng = 2; key->name = "block28u<" + std::to_string(C::G) + "," + std::to_string(C::BL) + ">"; }
+        CUK((cudaFuncSetAttribute(k_encrypt<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C, 1>::SMEM_BYTES)));
+        CUK((cudaFuncSetAttribute(k_tally<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C, 1>::SMEM_BYTES)));
+        CUK((cudaFuncSetAttribute(k_pow<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C, 1>::SMEM_BYTES)));
     }
+    if constexpr (UL<C, 1>::SUPPORTED && UL<C, 2>::SUPPORTED) {
+        CUK(u_image(std::integral_constant<int, 2>{}, &key->d_uconsts2));
+        key->has_u2 = true;
+        CUK((cudaFuncSetAttribute(k_encrypt<C, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C, 2>::SMEM_BYTES)));
+        CUK((cudaFuncSetAttribute(k_pow<C, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C, 2>::SMEM_BYTES)));
+    }
+    block28_set_engine(key, -1);
     // sliding-window schedule for the exponent n
     std::vector<int2> ops;
     int first_idx = window_schedule(n, ops);
@@ -1030,7 +1056,7 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
     }
     B28Dev& K = key->dev;
     K.n_entry = key->d_nentry;
-    K.consts = key->d_consts; K.uconsts = key->d_uconsts; K.utok = key->d_utok; K.ops = key->d_ops; K.n_ops = (int)ops.size(); K.first_idx = first_idx;
+    K.consts = key->d_consts; K.uconsts = key->d_uconsts; K.uconsts2 = key->d_uconsts2; K.ops = key->d_ops; K.n_ops = (int)ops.size(); K.first_idx = first_idx;
     K.tg = key->d_tg; K.n_windows = n_windows; K.comb_bits = comb_bits; K.words_in = (int)win; K.words_out = (int)((2 * n_bits + 63) / 64);
     K.sh = sh;
     K.sms = (unsigned)key->sms;
@@ -1069,10 +1095,11 @@ static cudaError_t ensure_slots(Block28Key* key, cudaStream_t st) {
         cudaFree(d_n);
         int per_sm = 0;
         CUW((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encrypt<C, 1>, C::THREADS, C::SMEM_BYTES)));
-        if constexpr (UL<C>::SUPPORTED) {
+        if constexpr (UL<C, 1>::SUPPORTED) {
             int per_u = 0;
-            CUW((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_u, k_encrypt<C, 2>, C::THREADS, UL<C>::SMEM_BYTES)));
+            CUW((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_u, k_encrypt<C, 2>, C::THREADS, UL<C, 1>::SMEM_BYTES)));
             if (per_u > per_sm) per_sm = per_u;
+            if (per_sm < 2) per_sm = 2;       // a CTA of two lane groups takes two slots
         }
         if (per_sm < 1 || per_sm > 32 || h_n == 0) return cudaErrorLaunchOutOfResources;
         key->nsmid = (int)h_n; key->enc_per_sm = per_sm;
@@ -1091,8 +1118,12 @@ static cudaError_t encrypt_cfg(Block28Key* key, const u64* d_m, const u64* d_r, 
     const SlotPool pool{key->d_slot_masks, key->enc_per_sm};
     const size_t ctas = (count + 31) / 32;
     bool done = false;
-    if constexpr (UL<C>::SUPPORTED) if (key->eng == 2) {
-        k_encrypt<C, 2><<<(unsigned)ctas, C::THREADS, UL<C>::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
+    if constexpr (UL<C, 1>::SUPPORTED && UL<C, 2>::SUPPORTED) if (key->eng == 3 && key->has_u2) {
+        k_encrypt<C, 3><<<(unsigned)((count + 63) / 64), 2 * C::THREADS, UL<C, 2>::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
+        done = true;
+    }
+    if constexpr (UL<C, 1>::SUPPORTED) if (!done && key->eng >= 2 && key->has_u) {
+        k_encrypt<C, 2><<<(unsigned)ctas, C::THREADS, UL<C, 1>::SMEM_BYTES, st>>>(key->dev, d_m, d_r, count, d_c, key->d_scratch, pool);
         done = true;
     }
     if (done) {}
@@ -1110,8 +1141,12 @@ static cudaError_t pow_cfg(Block28Key* key, const u64* d_base, int base_words, s
     const SlotPool pool{key->d_slot_masks, key->enc_per_sm};
     const size_t ctas = (count + 31) / 32;
     bool done = false;
-    if constexpr (UL<C>::SUPPORTED) if (key->eng == 2) {
-        k_pow<C, 2><<<(unsigned)ctas, C::THREADS, UL<C>::SMEM_BYTES, st>>>(key->dev, key->pow, d_base, base_words, count, d_out, key->d_scratch, pool);
+    if constexpr (UL<C, 1>::SUPPORTED && UL<C, 2>::SUPPORTED) if (key->eng == 3 && key->has_u2) {
+        k_pow<C, 3><<<(unsigned)((count + 63) / 64), 2 * C::THREADS, UL<C, 2>::SMEM_BYTES, st>>>(key->dev, key->pow, d_base, base_words, count, d_out, key->d_scratch, pool);
+        done = true;
+    }
+    if constexpr (UL<C, 1>::SUPPORTED) if (!done && key->eng >= 2 && key->has_u) {
+        k_pow<C, 2><<<(unsigned)ctas, C::THREADS, UL<C, 1>::SMEM_BYTES, st>>>(key->dev, key->pow, d_base, base_words, count, d_out, key->d_scratch, pool);
         done = true;
     }
     if (done) {}
@@ -1141,8 +1176,8 @@ static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64*
     if (!collective || P.world <= 1) { P.world = 1; P.rank = 0; }
     else { key->peer.epoch += 1; P.epoch = key->peer.epoch; }
     bool done = false;
-    if constexpr (UL<C>::SUPPORTED) if (key->eng == 2) {
-        k_tally<C, 2><<<(unsigned)ctas, C::THREADS, UL<C>::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
+    if constexpr (UL<C, 1>::SUPPORTED) if (key->eng >= 2 && key->has_u) {
+        k_tally<C, 2><<<(unsigned)ctas, C::THREADS, UL<C, 1>::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
         done = true;
     }
     if (done) {}
@@ -1250,7 +1285,7 @@ void block28_destroy(Block28Key* key) {
     if (!key) return;
     if (key->d_consts) cudaFree(key->d_consts);
     if (key->d_uconsts) cudaFree(key->d_uconsts);
-    if (key->d_utok) cudaFree(key->d_utok);
+    if (key->d_uconsts2) cudaFree(key->d_uconsts2);
     if (key->d_ops) cudaFree(key->d_ops);
     if (key->d_tg) cudaFree(key->d_tg);
     if (key->d_nentry) cudaFree(key->d_nentry);
@@ -1271,16 +1306,19 @@ void block28_destroy(Block28Key* key) {
     delete key;
 }
 const char* block28_name(const Block28Key* key) { return key->name.c_str(); }
-// eng: 0 = every phase on the IMAD pipe, 1 = constant-operand phases on mma.sync, 2 = on tcgen05 (falls back to 1 when this
-// configuration has no block28u variant), -1 = the fastest available
+// eng: 0 = every phase on the IMAD pipe, 1 = constant-operand phases on mma.sync, 2 = on tcgen05 with 32 ciphertexts per CTA,
+// 3 = on tcgen05 with 64 per CTA (each falls back to the next lower one this configuration has), -1 = the fastest available (2)
 int block28_set_engine(Block28Key* key, int eng) {
-    if (eng < 0) eng = (key->has_u && !getenv("PB200_NO_UMMA")) ? 2 : 1;
+    if (eng < 0) eng = getenv("PB200_NO_UMMA") ? 1 : (getenv("PB200_UMMA_LG2") ? 3 : 2);      // measured: 134.9 k enc/s (2) against 129.9 k (3)
+    if (eng == 3 && !key->has_u2) eng = 2;
     if (eng == 2 && !key->has_u) eng = 1;
     key->eng = eng;
-    key->name = std::string(eng == 2 ? "block28u<" : eng == 1 ? "block28t<" : "block28<") + std::to_string(key->G) + "," + std::to_string(key->BL) + ">";
+    key->name = std::string(eng == 3 ? "block28u2<" : eng == 2 ? "block28u<" : eng == 1 ? "block28t<" : "block28<") + std::to_string(key->G) + "," +
+                std::to_string(key->BL) + ">";
     return eng;
 }
 bool block28_has_umma(const Block28Key* key) { return key->has_u; }
+bool block28_has_umma2(const Block28Key* key) { return key->has_u2; }
 void block28_chain_counts(const Block28Key* key, uint64_t* n_sqr, uint64_t* n_mul) { *n_sqr = key->n_sqr; *n_mul = key->n_mul; }
 cudaError_t block28_encrypt(Block28Key* key, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st) {
     if (key->G == 4) return encrypt_cfg<Cfg1024>(key, d_m, d_r, count, d_c, st);
@@ -1354,7 +1392,7 @@ cudaError_t block28_tally_peer_connect(Block28Key* key, int rank, int world, u64
 template <class C, int ENG>
 static cudaError_t debug_launch(Block28Key* key, const int4* d_v, const int4* d_y, int reps, int4* d_vout, int4* d_t, unsigned* d_rows, cudaStream_t st) {
     CUW((cudaFuncSetAttribute(k_mulmod_dbg<C, ENG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)View<C, ENG>::BYTES)));
-    k_mulmod_dbg<C, ENG><<<1, C::THREADS, View<C, ENG>::BYTES, st>>>(key->dev, d_v, d_y, reps, d_vout, d_t, d_rows);
+    k_mulmod_dbg<C, ENG><<<1, View<C, ENG>::THREADS, View<C, ENG>::BYTES, st>>>(key->dev, d_v, d_y, reps, d_vout, d_t, d_rows);
     count_launch();
     return cudaGetLastError();
 }
@@ -1370,7 +1408,8 @@ static cudaError_t debug_cfg(Block28Key* key, int eng, const int* h_v, const int
         CUW(cudaMemcpy(d_v, h_v, vb, cudaMemcpyHostToDevice));
         if (h_y) CUW(cudaMemcpy(d_y, h_y, vb, cudaMemcpyHostToDevice));
         cudaError_t r = cudaErrorInvalidValue;
-        if (eng == 2) { if constexpr (UL<C>::SUPPORTED) { if (key->has_u) r = debug_launch<C, 2>(key, d_v, h_y ? d_y : nullptr, reps, d_vout, h_t ? d_t : nullptr, d_rows, st); } }
+        if (eng == 3) { if constexpr (UL<C, 1>::SUPPORTED && UL<C, 2>::SUPPORTED) { if (key->has_u2) r = debug_launch<C, 3>(key, d_v, h_y ? d_y : nullptr, reps, d_vout, h_t ? d_t : nullptr, d_rows, st); } }
+        else if (eng == 2) { if constexpr (UL<C, 1>::SUPPORTED) { if (key->has_u) r = debug_launch<C, 2>(key, d_v, h_y ? d_y : nullptr, reps, d_vout, h_t ? d_t : nullptr, d_rows, st); } }
         else if (eng == 1) r = debug_launch<C, 1>(key, d_v, h_y ? d_y : nullptr, reps, d_vout, h_t ? d_t : nullptr, d_rows, st);
         else if (eng == 0) r = debug_launch<C, 0>(key, d_v, h_y ? d_y : nullptr, reps, d_vout, h_t ? d_t : nullptr, d_rows, st);
         CUW(r);
@@ -1400,7 +1439,7 @@ void block28_shape(const Block28Key* key, int* G, int* BL) { *G = key->G; *BL = 
 template <class C, int ENG>
 static cudaError_t time_launch(Block28Key* key, const int4* d_v, int ctas, int reps, int stagger, long long* d_cyc, unsigned* d_cnt, cudaStream_t st) {
     CUW((cudaFuncSetAttribute(k_mulmod_time<C, ENG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)View<C, ENG>::BYTES)));
-    k_mulmod_time<C, ENG><<<ctas, C::THREADS, View<C, ENG>::BYTES, st>>>(key->dev, d_v, reps, stagger, d_cyc, d_cnt);
+    k_mulmod_time<C, ENG><<<ctas, View<C, ENG>::THREADS, View<C, ENG>::BYTES, st>>>(key->dev, d_v, reps, stagger, d_cyc, d_cnt);
     count_launch();
     return cudaGetLastError();
 }
@@ -1415,7 +1454,8 @@ cudaError_t block28_debug_time(Block28Key* key, int eng, const int* h_v, int cta
         CUW(cudaMalloc(&d_cnt, 1024 * sizeof(unsigned))); CUW(cudaMemset(d_cnt, 0, 1024 * sizeof(unsigned)));
         CUW(cudaMemcpy(d_v, h_v, vb, cudaMemcpyHostToDevice));
         cudaError_t r = cudaErrorInvalidValue;
-        if (eng == 2) { if (key->has_u) r = time_launch<C, 2>(key, d_v, ctas, reps, stagger, d_cyc, d_cnt, st); }
+        if (eng == 3) { if (key->has_u2) r = time_launch<C, 3>(key, d_v, ctas, reps, stagger, d_cyc, d_cnt, st); }
+        else if (eng == 2) { if (key->has_u) r = time_launch<C, 2>(key, d_v, ctas, reps, stagger, d_cyc, d_cnt, st); }
         else if (eng == 1) r = time_launch<C, 1>(key, d_v, ctas, reps, stagger, d_cyc, d_cnt, st);
         CUW(r);
         CUW(cudaStreamSynchronize(st));

@@ -3,29 +3,32 @@
 //
 // Same arithmetic as block28t (block28.cuh, phase_mma / qhat_to_bytes / low_to_value) — the lazy digits it leaves in V are
 // bit-identical, tests/model_block28.py is the model of both — but the GEMM  C[lane][p] = sum_k A7[lane][k] K7[p - k]  is issued by
-// ONE thread and runs asynchronously: while a CTA's phases B and C are on the tensor core its warps sleep on an mbarrier, and the
-// other CTA of the SM has the IMAD pipe for its phase A.
+// ONE thread and runs asynchronously on the tensor core.
 //
-// How 32 ciphertexts fill a 128-row MMA.  The per-lane s8 rows are stored K-major without swizzle as [16-byte K chunk][lane][16]
-// (512 B per chunk).  A UMMA descriptor with 128 B between 8-row groups then makes MMA rows 32j .. 32j+31 the SAME 32 lanes read
-// j chunks further along K (row group 4j + i lies at (i + 4j) * 128 = chunk + j).  By the Toeplitz structure a row shifted by 16j in
-// k holds the output columns shifted by 16j in p:  D[32j + lane][n] = C[lane][p_hi - n + 16j].  One N = 128 MMA therefore yields 176
-// distinct output columns per lane (for the price of 128), and — what matters more — every TMEM lane quadrant holds all 32
-// ciphertexts, so all warps of the CTA take part in the fold (a warp reads only the quadrant warp % 4).  Zero chunks in front of
-// and behind the rows (FRONT, BACK) stand in for k < 0 and k >= K7.
+// How 32 or 64 ciphertexts fill a 128-row MMA.  The per-lane s8 rows are stored K-major without swizzle as
+// [16-byte K chunk][row][16], ROWS = 32 LG rows per chunk (LG = lane groups of 32 ciphertexts per CTA: 1 or 2).  A UMMA descriptor
+// with 128 B between 8-row groups then makes MMA rows ROWS j .. ROWS j + ROWS - 1 the SAME rows read j chunks further along K.  By
+// the Toeplitz structure a row shifted by 16 j in k holds the output columns shifted by 16 j in p:
+// D[ROWS j + row][n] = C[row][p_hi - n + 16 j].  One MMA therefore yields TN + 16 (NSH - 1) distinct output columns per ciphertext
+// (NSH = 128 / ROWS copies: 4 or 2) and every TMEM lane quadrant holds ciphertexts, so all warps of the CTA take part in the fold
+// (a warp reads only the quadrant warp % 4).  Zero chunks in front of and behind the rows stand in for k < 0 and k >= K7.
+// LG = 2 halves the tensor-core time and the shared-memory traffic per ciphertext (the B operand and the instruction are shared
+// by 64 ciphertexts): measured, the MMAs run at the speed the tensor core can fetch its operands from shared memory (~90 B/clk).
 //
 // The Toeplitz operand is never materialised: with the tile's columns taken in DECREASING p, core matrix (column group g, K chunk
 // j) of any (tile, k-step) is entry u0 + g + 2j of one per-key table CM[u][r][b] = Rev[8u + r + b] (descriptor strides 128 B along
-// N, 256 B along K) — csrc/microbench/umma_toeplitz.cu measured and verified this form (7 090 int8 MAC/clk/SM).
+// N, 256 B along K) — csrc/microbench/umma_toeplitz.cu measured and verified this form.
 //
-// Tiles: 160 output columns (40 digits) each, 8 ranges of 20 columns; warp w folds range 2(3 - w%4) + w/4 from TMEM quadrant w%4
+// Tiles: 160 output columns (40 digits) each, 8 ranges of 20 columns per ciphertext; a warp folds one range from its TMEM quadrant
 // and reads the 4 columns below its range itself for the incoming carry, so tiles and ranges are independent of each other.
-// Two TMEM buffers of 128 columns per CTA (256 columns: two CTAs per SM fit), MMAs of tile s+2 are issued as soon as the fold of
-// tile s has left its buffer.
+// Two TMEM buffers per CTA; a warp that has read its columns out arrives on the buffer's "empty" mbarrier, thread 0 waits for the
+// arrivals and issues the MMAs of the tile after next — no CTA barrier between tiles.
 //
-// Shared memory (Cfg<8,19>: 112 KB, two CTAs per SM): V | B | T(2L) | tail of the q-hat rows | constants | CM(mu) | CM(Nt).
-// The q1 rows overlay V and the head of B (both dead after phase A), the q-hat rows overlay the upper half of T (dead once q1 has
-// been cut out of it); phase A's stash of Hi digits, which block28t keeps in the Q buffer, lives in TMEM columns (tcgen05.st/ld).
+// Shared memory, LG = 1 (112 KB, two CTAs per SM): V | B | T(2L) | tail of the q-hat rows | constants | CM(mu) | CM(Nt).
+// LG = 2 (190 KB, one CTA of 16 warps per SM): V0 B0 V1 B1 | T0lo T1lo T0hi T1hi | tail | constants | CM | CM.  The q1 rows overlay
+// V, B (dead after phase A), the q-hat rows overlay the upper halves of T (dead once q1 has been cut out); phase A's stash of Hi
+// digits, which block28t keeps in the Q buffer, lives in TMEM columns (tcgen05.st / ld); the low-part sums of phase C go to a flat
+// array in B.  Everything the phases B / C execute on the CUDA cores avoids the FMA pipes (see "Opaque operands").
 #pragma once
 #include "block28.cuh"
 #include <type_traits>
@@ -33,24 +36,31 @@
 namespace pb200 {
 namespace b28 {
 
-template <class C>
+template <class C, int LG>
 struct UL {
     static constexpr int L = C::L, K7 = C::K7, G = C::G;
     static constexpr int KCH = K7 / 16;                        // 16-byte K chunks per row
-    static constexpr int FRONT = 4, BACK = 3;                  // zero chunks before / after the row (k in [-64, 0) and [K7, K7 + 48))
+    static constexpr int ROWS = 32 * LG, CHB = 16 * ROWS;      // rows and bytes per chunk
+    static constexpr int NSH = 128 / ROWS;                     // shifted copies of the rows in one MMA
+    static constexpr int SHIFTC = 16 * (NSH - 1);              // extra output columns the copies bring
+    static constexpr int FRONT = 2 * ((SHIFTC + 31) / 32), BACK = NSH - 1;      // zero chunks before / after the row
+    static constexpr int KOFF = 16 * FRONT;
     static constexpr int ACH = FRONT + KCH + BACK;
-    static constexpr int A_BYTES = ACH * 512;
-    static constexpr int TN = 128, TCOLS = 160, RCOLS = 20, SHIFTC = 48;
+    static constexpr int A_BYTES = ACH * CHB;
+    static constexpr int TCOLS = 160, RCOLS = 20;
+    static constexpr int TN = ((TCOLS - SHIFTC + 4) + 15) / 16 * 16;      // MMA N: the columns the unshifted rows must see
+    static constexpr int NWARPS = C::G * LG, THREADS = 32 * NWARPS;
+    static constexpr int RPS = 8 / NSH;                        // ranges per (ciphertext group, shift) = warps per TMEM quadrant
     static constexpr int P_BASE_H = 4 * (L - 2);               // phase B keeps two guard digits below q-hat
     static constexpr int NT_H = (4 * (L + 2) + TCOLS - 1) / TCOLS, NT_L = (4 * L + TCOLS - 1) / TCOLS;
-    static constexpr int TMEM_COLS = 256;
+    static constexpr int TMEM_COLS = 256 * LG;
     __host__ __device__ static constexpr int p_top(bool high, int t) { return (high ? P_BASE_H + NT_H * TCOLS : NT_L * TCOLS) - 1 - TCOLS * t; }
     __host__ __device__ static constexpr int p_hi(bool high, int t) { return p_top(high, t) - SHIFTC; }
-    // k range of a tile in the coordinates of MMA rows 0..31: the band of its 128 columns, extended 48 below zero for the shifted rows
+    // k range of a tile in the coordinates of the unshifted rows: the band of its TN columns, extended below zero for the shifted rows
     __host__ __device__ static constexpr int k_start(int ph) {
         int k_lo = ph - (TN - 1) - (K7 - 1);
         if (k_lo < -SHIFTC) k_lo = -SHIFTC;
-        return ((k_lo + 64) / 32) * 32 - 64;
+        return ((k_lo + KOFF) / 32) * 32 - KOFF;
     }
     __host__ __device__ static constexpr int n_ksteps(int ph) { return ((ph < K7 - 1 ? ph : K7 - 1) - k_start(ph)) / 32 + 1; }
     // Rev[z] = K7c[z0 - z]; z0 = 7 (mod 8) like every p_hi, and >= the largest p_hi - k any tile touches
@@ -63,46 +73,53 @@ struct UL {
         int m = 0;
         for (int t = 0; t < (high ? NT_H : NT_L); t++) {
             const int ph = p_hi(high, t), k_last = k_start(ph) + 32 * (n_ksteps(ph) - 1);
-            const int u = (z0(high) - ph + k_last) / 8 + 18;
+            const int u = (z0(high) - ph + k_last) / 8 + TN / 8 + 2;
             if (u > m) m = u;
         }
         return m;
     }
     static constexpr int Z0_H = z0(true), Z0_L = z0(false), NCM_H = ncm(true), NCM_L = ncm(false);
     // byte offsets in dynamic shared memory
-    static constexpr int OFF_V = 0, OFF_B = C::VAL4 * 16, OFF_T = 2 * C::VAL4 * 16, OFF_ASC = 3 * C::VAL4 * 16;
+    static constexpr int VALB = C::VAL4 * 16;
+    static constexpr int OFF_T = 2 * LG * VALB, OFF_ASC = OFF_T + LG * VALB;       // T low halves of all groups, then the high halves
+    static constexpr int T_HI_JUMP = (LG - 1) * VALB;                                // block d >= G of a group lies this much further
     static constexpr int END_ASC = OFF_ASC + A_BYTES;
-    static constexpr int OFF_CONST = ((END_ASC > 4 * C::VAL4 * 16 ? END_ASC : 4 * C::VAL4 * 16) + 127) / 128 * 128;
+    static constexpr int OFF_CONST = ((END_ASC > OFF_T + 2 * LG * VALB ? END_ASC : OFF_T + 2 * LG * VALB) + 127) / 128 * 128;
     static constexpr int CONST_BYTES = (3 * C::ENTRY4 * 16 + 127) / 128 * 128;
     static constexpr int OFF_CMH = OFF_CONST + CONST_BYTES, OFF_CML = OFF_CMH + NCM_H * 128, OFF_BAR = OFF_CML + NCM_L * 128;
     static constexpr int KEY_BYTES = OFF_BAR - OFF_CONST;      // per-key image copied from global memory: constants, CM(mu), CM(Nt)
     static constexpr size_t SMEM_BYTES = (size_t)OFF_BAR + 64;
-    static constexpr int CTAS_PER_SM = (int)((233472 / (SMEM_BYTES + 1024)) < (512 / C::THREADS) ? (233472 / (SMEM_BYTES + 1024)) : (512 / C::THREADS));
+    static constexpr int CTAS_PER_SM = (int)((233472 / (SMEM_BYTES + 1024)) < (512 / THREADS) ? (233472 / (SMEM_BYTES + 1024)) : (512 / THREADS));
     // compiled for configurations with whole k-steps per row, four tiles per phase (every mbarrier completes an even number of times
-    // per multiplication, so the wait parities are compile-time constants), the q1 rows inside V | B and 8 warps (two per TMEM quadrant)
-    static constexpr bool SUPPORTED = (K7 % 32 == 0) && (NT_H == 4) && (NT_L == 4) && (A_BYTES <= 2 * C::VAL4 * 16) && (G == 8) &&
-                                      (Z0_H % 8 == 7) && (Z0_L % 8 == 7) && (P_BASE_H % 8 == 0) && CTAS_PER_SM >= 1;
+    // per multiplication, so the wait parities are compile-time constants), the q1 rows inside V | B and 8 warps per lane group
+    static constexpr bool SUPPORTED = (K7 % 32 == 0) && (NT_H == 4) && (NT_L == 4) && (A_BYTES <= 2 * LG * VALB) && (G == 8) &&
+                                      (Z0_H % 8 == 7) && (Z0_L % 8 == 7) && (P_BASE_H % 8 == 0) && (TN <= 128 * LG + 32 * (LG - 1)) &&
+                                      (2 * TN <= TMEM_COLS) && CTAS_PER_SM >= 1 && SMEM_BYTES <= 232448;
 };
 
-// Shared-memory view of one CTA (block28u).  Member names follow Smem<C> so the kernels are written once.
-template <class C>
+// Shared-memory view of one thread's lane group.  Member names follow Smem<C> so the kernels are written once.
+template <class C, int LG>
 struct SmemU {
     int4* V; int4* B; int4* T; const int4* mu; const int4* Nt; const int4* two_sh;
     unsigned char* base;
-    uint32_t tmem;          // TMEM base address of this CTA's 256 columns
-    unsigned pb;            // bit b: parity the next wait on mbarrier b uses
-    unsigned* tok;          // this SM's tensor-phase token (global memory), null = no alternation between the CTAs of an SM
+    uint32_t tmem;          // TMEM base address of this CTA's columns
+    int group;              // lane group of this thread in phase A and in the kernels' value handling: warp / G
     __device__ __forceinline__ SmemU(int4* b) {
+        typedef UL<C, LG> U;
         base = (unsigned char*)b;
-        V = b; B = V + C::VAL4; T = B + C::VAL4;
-        const int4* k = (const int4*)(base + UL<C>::OFF_CONST);
+        group = LG == 1 ? 0 : (int)(threadIdx.x >> 5) / C::G;
+        V = b + group * 2 * C::VAL4; B = V + C::VAL4;
+        T = (int4*)(base + U::OFF_T) + group * C::VAL4;
+        const int4* k = (const int4*)(base + U::OFF_CONST);
         mu = k; Nt = k + C::ENTRY4; two_sh = k + 2 * C::ENTRY4;
-        tmem = 0; pb = 0; tok = nullptr;
+        tmem = 0;
     }
+    // block d of this group's 2L-digit product
+    __device__ __forceinline__ int4* tblk(int d, int lane) const { return T + d * C::BLK4 + (d >= C::G ? UL<C, LG>::T_HI_JUMP / 16 : 0) + lane; }
     __device__ __forceinline__ unsigned char* asb() const { return base; }
-    __device__ __forceinline__ unsigned char* asc() const { return base + UL<C>::OFF_ASC; }
-    __device__ __forceinline__ uint64_t* bars() const { return (uint64_t*)(base + UL<C>::OFF_BAR); }
-    __device__ __forceinline__ volatile uint32_t* slots() const { return (volatile uint32_t*)(base + UL<C>::OFF_BAR + 32); }   // [0] TMEM base, [1] dead
+    __device__ __forceinline__ unsigned char* asc() const { return base + UL<C, LG>::OFF_ASC; }
+    __device__ __forceinline__ uint64_t* bars() const { return (uint64_t*)(base + UL<C, LG>::OFF_BAR); }
+    __device__ __forceinline__ volatile uint32_t* slots() const { return (volatile uint32_t*)(base + UL<C, LG>::OFF_BAR + 32); }   // [0] TMEM base, [1] dead
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------------
@@ -167,35 +184,44 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const int* v) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// barrier of one lane group (8 warps); with one group per CTA it is the CTA barrier
+template <int LG, int NTHREADS>
+__device__ __forceinline__ void group_sync(int group) {
+    if (LG == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "n"(NTHREADS) : "memory");
+}
+
 // ---- per-CTA set-up / tear-down -----------------------------------------------------------------------------------------
-template <class C>
-__device__ __forceinline__ void umma_setup(SmemU<C>& S) {
-    using U = UL<C>;
+template <class C, int LG>
+__device__ __forceinline__ void umma_setup(SmemU<C, LG>& S) {
+    using U = UL<C, LG>;
     const int warp = threadIdx.x >> 5;
     // bars 0, 1: the MMAs of a TMEM buffer are complete (tcgen05.commit);  2, 3: every warp has read the buffer out (one arrival per warp)
-    if (threadIdx.x == 0) { mbar_init(&S.bars()[0], 1); mbar_init(&S.bars()[1], 1); mbar_init(&S.bars()[2], C::G); mbar_init(&S.bars()[3], C::G); S.slots()[1] = 0; }
+    if (threadIdx.x == 0) {
+        mbar_init(&S.bars()[0], 1); mbar_init(&S.bars()[1], 1); mbar_init(&S.bars()[2], U::NWARPS); mbar_init(&S.bars()[3], U::NWARPS);
+        S.slots()[1] = 0;
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32((const void*)S.slots())), "n"(U::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // the zero chunks behind the q-hat rows lie beyond T and are never written again
-    for (int i = threadIdx.x; i < U::BACK * 32; i += C::THREADS)
-        *(int4*)(S.asc() + (U::FRONT + U::KCH) * 512 + i * 16) = make_int4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < U::BACK * U::ROWS; i += U::THREADS)
+        *(int4*)(S.asc() + (U::FRONT + U::KCH) * U::CHB + i * 16) = make_int4(0, 0, 0, 0);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     S.tmem = S.slots()[0];
-    S.pb = 0;
 }
-template <class C>
-__device__ __forceinline__ void umma_teardown(SmemU<C>& S) {
+template <class C, int LG>
+__device__ __forceinline__ void umma_teardown(SmemU<C, LG>& S) {
     tc_fence_before();
     __syncthreads();
     if ((threadIdx.x >> 5) == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(S.tmem), "n"(UL<C>::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(S.tmem), "n"(UL<C, LG>::TMEM_COLS) : "memory");
     }
     if (S.slots()[1]) {
         if (threadIdx.x == 0) printf("pb200 block28u: tcgen05 completion never arrived (CTA %d)\n", (int)blockIdx.x);
@@ -204,16 +230,16 @@ __device__ __forceinline__ void umma_teardown(SmemU<C>& S) {
 }
 
 // ---- phase A with the stash in TMEM --------------------------------------------------------------------------------------
-// phase_product of block28.cuh; the Hi digits of a warp's first anti-diagonal wait for the merge in TMEM columns
-// [32 (warp / 4), + CH * 4) of the warp's own lane quadrant instead of the Q buffer.
-template <class C>
+// phase_product of block28.cuh for this thread's lane group; the Hi digits of a warp's first anti-diagonal wait for the merge in
+// TMEM columns [32 (warp / 4), + CH * 4) of the warp's own lane quadrant instead of the Q buffer.
+template <class C, int LG>
 __device__ __noinline__ void phase_product_u(int4* smem_base, const int4* Y, int sqr, uint32_t tmem) {
     constexpr int G = C::G, BL = C::BL;
-    SmemU<C> S(smem_base);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SmemU<C, LG> S(smem_base);
+    const int lane = threadIdx.x & 31, cwarp = threadIdx.x >> 5, warp = cwarp % G;      // warp: role within the lane group
     const unsigned v_addr = (unsigned)__cvta_generic_to_shared(S.V) + lane * 16;
     const unsigned y_addr = sqr ? v_addr : (unsigned)__cvta_generic_to_shared(Y) + lane * 16;
-    const uint32_t stash = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 32);
+    const uint32_t stash = tmem + ((uint32_t)((cwarp & 3) * 32) << 16) + (uint32_t)((cwarp >> 2) * 32);
     Pending<C> pend;
     pend.blk = -1;
     int blk0 = -1, spill0 = 0;
@@ -233,7 +259,7 @@ __device__ __noinline__ void phase_product_u(int4* smem_base, const int4* Y, int
             carry = ripple_cols<C>(acc, BL, 0, lo);
 #pragma unroll
             for (int k = BL; k < C::CH * 4; k++) lo[k] = 0;
-            store_block<C>(blk_ptr<C>(S.T, d, lane), lo);
+            store_block<C>(S.tblk(d, lane), lo);
         }
         {   // columns BL .. 2BL-2 -> Hi digits, last digit and spill from the final carry
             long long acc[BL];
@@ -256,48 +282,53 @@ __device__ __noinline__ void phase_product_u(int4* smem_base, const int4* Y, int
             blk0 = d; spill0 = pend.spill;
         }
     }
-    if (warp == G - 1) store_zero_block<C>(S.T, 2 * G - 1, lane);
-    __syncthreads();
+    if (warp == G - 1) {                        // block 2G-1 has no Lo contribution
+        int z[C::CH * 4];
+#pragma unroll
+        for (int k = 0; k < C::CH * 4; k++) z[k] = 0;
+        store_block<C>(S.tblk(2 * G - 1, lane), z);
+    }
+    group_sync<LG, C::THREADS>(S.group);          // the lane groups of a CTA run phase A independently of each other
     int carry0 = 0;
     if (blk0 >= 0) {
         int h0[C::CH * 4];
         tmem_ld16(stash, h0);
         if (C::CH * 4 > 16) tmem_ld4(stash + 16, h0 + 16);
         tmem_wait_ld();
-        int4* p = blk_ptr<C>(S.T, blk0 + 1, lane);
+        int4* p = S.tblk(blk0 + 1, lane);
         carry0 = add_ripple_block<C>(p, p, h0, 1);
     }
     {
-        int4* p = blk_ptr<C>(S.T, pend.blk + 1, lane);
+        int4* p = S.tblk(pend.blk + 1, lane);
         pend.carry = add_ripple_block<C>(p, p, pend.hi, 1);
     }
-    __syncthreads();
-    if (blk0 >= 0) *(int*)blk_ptr<C>(S.T, blk0 + 2, lane) += carry0 + spill0;
-    if (pend.blk + 2 <= 2 * G - 1) *(int*)blk_ptr<C>(S.T, pend.blk + 2, lane) += pend.carry + pend.spill;
-    __syncthreads();
+    group_sync<LG, C::THREADS>(S.group);
+    if (blk0 >= 0) *(int*)S.tblk(blk0 + 2, lane) += carry0 + spill0;
+    if (pend.blk + 2 <= 2 * G - 1) *(int*)S.tblk(pend.blk + 2, lane) += pend.carry + pend.spill;
+    __syncthreads();          // CTA-wide: the q1 rows that phases_bc_umma writes next overlay V and B of every lane group
 }
 
 // ---- phases B and C ---------------------------------------------------------------------------------------------------------
-// BL packed words of a lane's row, starting at word w0 of the row, into the chunked layout: 128-bit stores wherever a chunk is whole
-template <int BL, int LEAD>
+// BL packed words of a row, starting at word w0 of the row, into the chunked layout: 128-bit stores wherever a chunk is whole
+template <int BL, int LEAD, int CHB>
 __device__ __forceinline__ void store_row_u_aligned(unsigned char* rowbase, int w0, const unsigned (&w)[BL]) {
 #pragma unroll
-    for (int k = 0; k < LEAD; k++) *(unsigned*)(rowbase + ((w0 + k) >> 2) * 512 + ((w0 + k) & 3) * 4) = w[k];
+    for (int k = 0; k < LEAD; k++) *(unsigned*)(rowbase + ((w0 + k) >> 2) * CHB + ((w0 + k) & 3) * 4) = w[k];
     constexpr int NV = (BL - LEAD) / 4;
     const int c0 = (w0 + LEAD) >> 2;
 #pragma unroll
     for (int c = 0; c < NV; c++)
-        *(uint4*)(rowbase + (c0 + c) * 512) = make_uint4(w[LEAD + 4 * c], w[LEAD + 4 * c + 1], w[LEAD + 4 * c + 2], w[LEAD + 4 * c + 3]);
+        *(uint4*)(rowbase + (c0 + c) * CHB) = make_uint4(w[LEAD + 4 * c], w[LEAD + 4 * c + 1], w[LEAD + 4 * c + 2], w[LEAD + 4 * c + 3]);
 #pragma unroll
-    for (int k = LEAD + 4 * NV; k < BL; k++) *(unsigned*)(rowbase + ((w0 + k) >> 2) * 512 + ((w0 + k) & 3) * 4) = w[k];
+    for (int k = LEAD + 4 * NV; k < BL; k++) *(unsigned*)(rowbase + ((w0 + k) >> 2) * CHB + ((w0 + k) & 3) * 4) = w[k];
 }
-template <int BL>
+template <int BL, int CHB>
 __device__ __forceinline__ void store_row_u(unsigned char* rowbase, int w0, const unsigned (&w)[BL]) {
     switch ((4 - (w0 & 3)) & 3) {          // warp-uniform
-        case 0: store_row_u_aligned<BL, 0>(rowbase, w0, w); break;
-        case 1: store_row_u_aligned<BL, 1>(rowbase, w0, w); break;
-        case 2: store_row_u_aligned<BL, 2>(rowbase, w0, w); break;
-        default: store_row_u_aligned<BL, 3>(rowbase, w0, w); break;
+        case 0: store_row_u_aligned<BL, 0, CHB>(rowbase, w0, w); break;
+        case 1: store_row_u_aligned<BL, 1, CHB>(rowbase, w0, w); break;
+        case 2: store_row_u_aligned<BL, 2, CHB>(rowbase, w0, w); break;
+        default: store_row_u_aligned<BL, 3, CHB>(rowbase, w0, w); break;
     }
 }
 
@@ -305,7 +336,7 @@ __device__ __forceinline__ void store_row_u(unsigned char* rowbase, int w0, cons
 // likes to turn constant left shifts, two-input adds and moves into IMAD.SHL / IMAD.IADD / IMAD.MOV — every one of them then queues
 // behind eight warps of IMAD.WIDE (measured: phases B + C 16.7 k clk alone, 29 k next to a phase-A CTA).  A shift count or a zero
 // addend read from constant memory cannot be folded away, so these become SHF and IADD3 on the ALU pipe.
-static __constant__ int c_opq[8] = {0, 1, 2, 3, 7, 9, 14, 24};
+static __constant__ int c_opq[8] = {0, 1, 2, 3, 7, 9, 14, 28};
 #define OPQ_Z (c_opq[0])
 #define OPQ_1 (c_opq[1])
 #define OPQ_2 (c_opq[2])
@@ -313,7 +344,7 @@ static __constant__ int c_opq[8] = {0, 1, 2, 3, 7, 9, 14, 24};
 #define OPQ_7 (c_opq[4])
 #define OPQ_9 (c_opq[5])
 #define OPQ_14 (c_opq[6])
-#define OPQ_24 (c_opq[7])
+#define OPQ_28 (c_opq[7])
 __device__ __forceinline__ unsigned lop3_sel(unsigned a, unsigned b, unsigned m) {          // (a & ~m) | (b & m)
     unsigned d; asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(m), "r"(b), "r"(a)); return d;      // m ? b : a
 }
@@ -342,31 +373,31 @@ __device__ __forceinline__ void fold4(const int* v, int& lob, int& ca) {
 }
 
 // all MMAs of issue slot s (HIGH: tiles from the bottom up, LOW: from the top down — longest k range first) into TMEM buffer s & 1
-template <class C, bool HIGH>
-__device__ __forceinline__ void umma_issue(const SmemU<C>& S, int s) {
-    using U = UL<C>;
+template <class C, int LG, bool HIGH>
+__device__ __forceinline__ void umma_issue(const SmemU<C, LG>& S, int s) {
+    using U = UL<C, LG>;
     const int t = HIGH ? U::NT_H - 1 - s : s;
     const int ph = U::p_hi(HIGH, t), ks0 = U::k_start(ph), nks = U::n_ksteps(ph);
     const uint32_t a_base = smem_u32(HIGH ? S.asb() : S.asc()), cm_base = smem_u32(S.base + (HIGH ? U::OFF_CMH : U::OFF_CML));
     const uint32_t d_tmem = S.tmem + (uint32_t)((s & 1) * U::TN);
     constexpr int Z0 = HIGH ? U::Z0_H : U::Z0_L;
     constexpr uint32_t idesc = umma_idesc(128, U::TN);
-    // descriptors of the first k-step; a k-step further is two K chunks of A (1024 B) and four table entries of B (512 B)
-    uint64_t a_desc = umma_desc(a_base + (uint32_t)((ks0 + 64) >> 4) * 512u, 512, 128);
+    // descriptors of the first k-step; a k-step further is two K chunks of A and four table entries of B (512 B)
+    uint64_t a_desc = umma_desc(a_base + (uint32_t)((ks0 + U::KOFF) >> 4) * (uint32_t)U::CHB, U::CHB, 128);
     uint64_t b_desc = umma_desc(cm_base + (uint32_t)((Z0 - ph + ks0) >> 3) * 128u, 256, 128);
     umma_i8(d_tmem, a_desc, b_desc, 0u, idesc);
 #pragma unroll 4
     for (int ks = 1; ks < nks; ks++) {
-        a_desc += 1024 >> 4; b_desc += 512 >> 4;
+        a_desc += (2 * U::CHB) >> 4; b_desc += 512 >> 4;
         umma_i8(d_tmem, a_desc, b_desc, 1u, idesc);
     }
     umma_commit(&S.bars()[s & 1]);
 }
 
-// fold of this warp's range of issue slot s: 5 digits (+ the digit below for its carry).  HIGH: packed q-hat words into the rows
-// of phase C;  LOW: lo(q-hat Nt) digit sums into the flat array F[digit][lane] (the B buffer), subtracted from T by the ripple pass.
-// dst: the address of this warp's top digit of the tile (HIGH: word 0 of its 16-byte chunk in this lane's row; LOW: its F entry)
-template <class C, bool HIGH>
+// fold of one range of a tile: 5 digits (+ the digit below for its carry).  HIGH: packed q-hat words into the rows of phase C;
+// LOW: lo(q-hat Nt) digit sums into the flat array F[digit][lane] (the group's B buffer), subtracted from T by the ripple pass.
+// dst: the address of the range's top digit (HIGH: word 0 of its 16-byte chunk in this row; LOW: its F entry)
+template <class C, int CHB, bool HIGH>
 __device__ __forceinline__ void umma_fold(const int* va, const int* vb, unsigned char* dst, int d_top, int r /* HIGH: (d_top - 2) & 3, warp-uniform */) {
     constexpr int L = C::L;
     int lob[6], ca[6];
@@ -388,7 +419,7 @@ __device__ __forceinline__ void umma_fold(const int* va, const int* vb, unsigned
 #pragma unroll
             for (int e = 0; e < 5; e++) {
                 const int wd = R - e, ch = wd >= 0 ? wd / 4 : -((3 - wd) / 4), word = wd - 4 * ch;
-                if ((unsigned)(qd0 - e) < (unsigned)L) *(unsigned*)(dst + ch * 512 + word * 4) = w[e];
+                if ((unsigned)(qd0 - e) < (unsigned)L) *(unsigned*)(dst + ch * CHB + word * 4) = w[e];
             }
         };
         switch (r) {          // warp-uniform: every store gets an immediate offset
@@ -404,48 +435,52 @@ __device__ __forceinline__ void umma_fold(const int* va, const int* vb, unsigned
     }
 }
 
-// q1 = T digits [L-1, 2L-1) as s8 rows; Q = hi(q1 mu); V = ripple(lo(T) - lo(Q Nt)).  Returns the mbarrier parity bits.
-template <class C>
-__device__ __noinline__ unsigned phases_bc_umma(int4* smem_base, uint32_t tmem, unsigned pb, unsigned* tok) {
-    using U = UL<C>;
-    SmemU<C> S(smem_base);
+// q1 = T digits [L-1, 2L-1) as s8 rows; Q = hi(q1 mu); V = ripple(lo(T) - lo(Q Nt)).
+template <class C, int LG>
+__device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
+    using U = UL<C, LG>;
+    constexpr int G = C::G, BL = C::BL;
+    SmemU<C, LG> S(smem_base);
     S.tmem = tmem;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, cwarp = threadIdx.x >> 5, warp = cwarp % G;
     volatile uint32_t* dead = S.slots() + 1;
     {
-        int a[C::CH * 4];
-        load_q1_block<C>(a, S.T, warp, lane);
-        unsigned w[C::BL];
+        // block `warp` of q1: digit 0 from the top of T block G + warp - 1, the rest from block G + warp (load_q1_block of block28.cuh)
+        int t[C::CH * 4], a[BL];
+        load_block<C>(t, S.tblk(G + warp, lane), 32);
+        const int* below = (const int*)S.tblk(G + warp - 1, lane);
+        a[0] = below[((BL - 1) / 4) * 32 * 4 + ((BL - 1) % 4)];
 #pragma unroll
-        for (int k = 0; k < C::BL; k++) w[k] = split7_pack_biased((unsigned)(a[k] + (int)SPLIT_BIAS + OPQ_Z));
-        store_row_u<C::BL>(S.asb() + U::FRONT * 512 + lane * 16, warp * C::BL, w);
-        for (int i = threadIdx.x; i < (U::FRONT + U::BACK) * 32; i += C::THREADS) {
-            const int ch = i >> 5;
-            *(int4*)(S.asb() + (ch < U::FRONT ? ch : U::KCH + ch) * 512 + (i & 31) * 16) = make_int4(0, 0, 0, 0);
+        for (int k = 1; k < BL; k++) a[k] = t[k - 1];
+        if (warp == G - 1) a[BL - 1] += t[BL - 1] << OPQ_28;       // fold digit 2L-1 (|.| <= 1) into digit 2L-2
+        unsigned w[BL];
+#pragma unroll
+        for (int k = 0; k < BL; k++) w[k] = split7_pack_biased((unsigned)(a[k] + (int)SPLIT_BIAS + OPQ_Z));
+        store_row_u<BL, U::CHB>(S.asb() + U::FRONT * U::CHB + (S.group * 32 + lane) * 16, warp * BL, w);
+        for (int i = threadIdx.x; i < (U::FRONT + U::BACK) * U::ROWS; i += U::THREADS) {
+            const int ch = i / U::ROWS;
+            *(int4*)(S.asb() + (ch < U::FRONT ? ch : U::KCH + ch) * U::CHB + (i % U::ROWS) * 16) = make_int4(0, 0, 0, 0);
         }
     }
     fence_async_smem();
-    // optional: the CTAs of an SM take turns on the tensor core (per-SM token in global memory)
-    if (tok && threadIdx.x == 0) {
-        int spins = 0;
-        while (atomicCAS(tok, 0u, 1u) != 0u) { __nanosleep(64); if (++spins > (1 << 22)) break; }
-    }
     __syncthreads();
-    if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, true>(S, 0); umma_issue<C, true>(S, 1); }
-    // T's upper half is dead now: zero chunks in front of the q-hat rows
-    for (int i = threadIdx.x; i < U::FRONT * 32; i += C::THREADS) *(int4*)(S.asc() + i * 16) = make_int4(0, 0, 0, 0);
-    // per-thread addressing of the folds: TMEM quadrant j = warp % 4 holds the columns shifted by 16 j; range ri of a tile
-    const int j = warp & 3, ri = 2 * (3 - j) + (warp >> 2);
-    const uint32_t ta0 = S.tmem + (uint32_t)(U::RCOLS * ri - U::SHIFTC + 16 * j) + ((uint32_t)(32 * j) << 16);
+    if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, LG, true>(S, 0); umma_issue<C, LG, true>(S, 1); }
+    // T's upper halves are dead now: zero chunks in front of the q-hat rows
+    for (int i = threadIdx.x; i < U::FRONT * U::ROWS; i += U::THREADS) *(int4*)(S.asc() + i * 16) = make_int4(0, 0, 0, 0);
+    // per-thread addressing of the folds.  TMEM quadrant q = warp % 4 holds MMA rows 32 q ..: ciphertext group ge, shift j; the
+    // warps of a quadrant share the ranges of (ge, j): range ri of a tile (0 = top)
+    const int q = cwarp & 3, ge = LG == 1 ? 0 : (q & 1), j = LG == 1 ? q : (q >> 1);
+    const int ri = (U::NSH - 1 - j) * U::RPS + (cwarp >> 2);
+    const uint32_t ta0 = S.tmem + (uint32_t)(U::RCOLS * ri - U::SHIFTC + 16 * j) + ((uint32_t)(32 * q) << 16);
     // Tiles are not separated by CTA barriers: a warp that has read its columns out of a TMEM buffer arrives on the buffer's "empty"
-    // mbarrier and goes on folding; thread 0 alone waits for the eight arrivals, issues the MMAs of the tile after next into the
-    // buffer, then folds its own columns.  Every mbarrier completes an even number of times per multiplication (four tiles per
-    // phase), so all wait parities are constants.
+    // mbarrier and goes on folding; thread 0 alone waits for the arrivals, issues the MMAs of the tile after next into the buffer,
+    // then folds its own columns.  Every mbarrier completes an even number of times per multiplication (four tiles per phase), so
+    // all wait parities are constants.
     {
         // HIGH, issue slot s is tile t = NT_H - 1 - s: top digit of this warp's range d_top = 40 (s + 1) - 1 - 5 ri
         const int d_top0 = 39 - 5 * ri;
         const int r = (d_top0 - 2) & 3;
-        unsigned char* dst0 = S.asc() + U::FRONT * 512 + lane * 16 + (((d_top0 - 2) >> 2) << OPQ_9);      // (d_top0 - 2) >> 2 may be -1: floor
+        unsigned char* dst0 = S.asc() + U::FRONT * U::CHB + (ge * 32 + lane) * 16 + (((d_top0 - 2) >> 2) * U::CHB);      // (d_top0 - 2) >> 2 may be -1: floor
 #pragma unroll
         for (int s = 0; s < U::NT_H; s++) {
             mbar_wait(&S.bars()[s & 1], (uint32_t)((s >> 1) & 1), dead);
@@ -460,25 +495,24 @@ __device__ __noinline__ unsigned phases_bc_umma(int4* smem_base, uint32_t tmem, 
                 if (threadIdx.x == 0) {
                     mbar_wait(&S.bars()[2 + (s & 1)], 0u, dead);
                     tc_fence_after();
-                    umma_issue<C, true>(S, s + 2);
+                    umma_issue<C, LG, true>(S, s + 2);
                 }
                 __syncwarp();
             }
-            umma_fold<C, true>(va, vb, dst0 + s * (10 * 512), d_top0 + 40 * s, r);
+            umma_fold<C, U::CHB, true>(va, vb, dst0 + s * (10 * U::CHB), d_top0 + 40 * s, r);
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();                    // q-hat rows complete
-        if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, false>(S, 0); umma_issue<C, false>(S, 1); }
+        if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, LG, false>(S, 0); umma_issue<C, LG, false>(S, 1); }
     }
     {
-        // LOW, issue slot s is tile t = s: d_top = 40 (NT_L - s) - 1 - 5 ri
+        // LOW, issue slot s is tile t = s: d_top = 40 (NT_L - s) - 1 - 5 ri;  F of ciphertext group ge is that group's B buffer
         const int d_top0 = 40 * U::NT_L - 1 - 5 * ri;
-        unsigned char* dst0 = (unsigned char*)S.B + lane * 4 + (d_top0 << OPQ_7);
+        unsigned char* dst0 = S.base + (2 * ge + 1) * U::VALB + lane * 4 + d_top0 * 128;
 #pragma unroll
         for (int s = 0; s < U::NT_L; s++) {
             mbar_wait(&S.bars()[s & 1], (uint32_t)((U::NT_H / 2 + (s >> 1)) & 1), dead);
-            if (tok && s + 1 == U::NT_L && threadIdx.x == 0) atomicExch(tok, 0u);      // all MMAs of this multiplication are complete
             tc_fence_after();
             int va[16], vb[8];
             tmem_ld16(ta0 + (uint32_t)((s & 1) * U::TN), va);
@@ -490,11 +524,11 @@ __device__ __noinline__ unsigned phases_bc_umma(int4* smem_base, uint32_t tmem, 
                 if (threadIdx.x == 0) {
                     mbar_wait(&S.bars()[2 + (s & 1)], 1u, dead);
                     tc_fence_after();
-                    umma_issue<C, false>(S, s + 2);
+                    umma_issue<C, LG, false>(S, s + 2);
                 }
                 __syncwarp();
             }
-            umma_fold<C, false>(va, vb, dst0 - s * (40 * 128), d_top0 - 40 * s, 0);
+            umma_fold<C, U::CHB, false>(va, vb, dst0 - s * (40 * 128), d_top0 - 40 * s, 0);
         }
         tc_fence_before();
         __syncthreads();                    // F complete, TMEM free for the next phase A's stash
@@ -502,35 +536,34 @@ __device__ __noinline__ unsigned phases_bc_umma(int4* smem_base, uint32_t tmem, 
     // V block = ripple(T block - F), carry into digit 0 of the next block (all MMAs are complete: the q1 rows over V are dead)
     {
         int a[C::CH * 4];
-        load_block<C>(a, blk_ptr<C>(S.T, warp, lane), 32);
-        const int* F = (const int*)S.B + (warp * C::BL) * 32 + lane;
+        load_block<C>(a, S.tblk(warp, lane), 32);
+        const int* F = (const int*)S.B + (warp * BL) * 32 + lane;
         int carry = 0;
 #pragma unroll
-        for (int k = 0; k < C::BL; k++) {
+        for (int k = 0; k < BL; k++) {
             const int tt = (a[k] - F[k * 32] + (1 << (W - 1))) + carry;
             carry = tt >> W;
             a[k] = (tt & ((1 << W) - 1)) - (1 << (W - 1));
         }
 #pragma unroll
-        for (int k = C::BL; k < C::CH * 4; k++) a[k] = 0;
+        for (int k = BL; k < C::CH * 4; k++) a[k] = 0;
         store_block<C>(blk_ptr<C>(S.V, warp, lane), a);
         __syncthreads();
-        if (warp + 1 < C::G) *(int*)blk_ptr<C>(S.V, warp + 1, lane) += carry;
+        if (warp + 1 < G) *(int*)blk_ptr<C>(S.V, warp + 1, lane) += carry;
         __syncthreads();
     }
-    return pb;
 }
 
-template <class C, bool SQR>
-__device__ __forceinline__ void mulmod_u(SmemU<C>& S, const int4* Y) {
-    phase_product_u<C>(S.V, Y, SQR ? 1 : 0, S.tmem);
-    S.pb = phases_bc_umma<C>(S.V, S.tmem, S.pb, S.tok);
+template <class C, int LG, bool SQR>
+__device__ __forceinline__ void mulmod_u(SmemU<C, LG>& S, const int4* Y) {
+    phase_product_u<C, LG>((int4*)S.base, Y, SQR ? 1 : 0, S.tmem);
+    phases_bc_umma<C, LG>((int4*)S.base, S.tmem);
 }
 
 // host: CM[u][r][b] = K7c[z0 - (8u + r + b)] (zero outside the constant)
-template <class C>
+template <class C, int LG>
 inline void umma_cm_table(const signed char* k7, bool high, signed char* out /* ncm * 128 */) {
-    using U = UL<C>;
+    using U = UL<C, LG>;
     const int z0 = high ? U::Z0_H : U::Z0_L, n = high ? U::NCM_H : U::NCM_L;
     for (int u = 0; u < n; u++)
         for (int r = 0; r < 8; r++)

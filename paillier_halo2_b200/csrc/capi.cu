@@ -67,7 +67,7 @@ struct pb200_key {
     int* d_flags = nullptr;
     Block28Key* fast = nullptr;
     std::string fast_why;
-    int engine = 0;                 // 0 auto, 1 simple64, 2 block28, 3 block28t, 4 block28u
+    int engine = 0;                 // 0 auto, 1 simple64, 2 block28, 3 block28t, 4 block28u, 5 block28u2
     DevBuf in_a, in_b, out_a, out_b, scratch, offs;
     std::string engine_name;
     // K4 cell expansion: per lookup_bits layout + device constants (n^2 limbs, word_max, q_acc, mod_acc), refresh spill vector
@@ -213,10 +213,12 @@ const char* pb200_key_engine(const pb200_key* k) {
     return use_fast(k) ? k->engine_name.c_str() : "simple64";
 }
 int pb200_key_set_engine(pb200_key* k, int engine) try {
-    if (!k || engine < 0 || engine > 4) return PB200_ERR_INVALID_ARG;
+    if (!k || engine < 0 || engine > 5) return PB200_ERR_INVALID_ARG;
     if (engine >= 2 && !k->fast) return PB200_ERR_UNSUPPORTED;
     if (engine == 4 && !block28_has_umma(k->fast)) return PB200_ERR_UNSUPPORTED;
+    if (engine == 5 && !block28_has_umma2(k->fast)) return PB200_ERR_UNSUPPORTED;
     k->engine = engine;
+    // internal numbering of the block28 family: 0 block28, 1 block28t, 2 block28u (32 ciphertexts per CTA), 3 block28u2 (64)
     if (k->fast) { block28_set_engine(k->fast, engine <= 1 ? -1 : engine - 2); k->engine_name = block28_name(k->fast); }
     return PB200_OK;
 } PB200_CATCH
@@ -270,17 +272,19 @@ int pb200_key_take_flags(pb200_key* k, uint32_t* flags_out) try {
 // Diagnostic entry: one CTA (32 lanes) of the fast engine's modular multiplication on raw lazy digits, on engine 2 / 3 / 4.
 int pb200_debug_mulmod(pb200_key* k, int engine, const int32_t* v_in, const int32_t* y_in, int reps, int32_t* v_out, int32_t* t_out,
                        uint32_t* qhat_rows) try {
-    if (!k || !v_in || engine < 2 || engine > 4 || (!v_out && !t_out) || reps < 1) return PB200_ERR_INVALID_ARG;
+    if (!k || !v_in || engine < 2 || engine > 5 || (!v_out && !t_out) || reps < 1) return PB200_ERR_INVALID_ARG;
     if (!k->fast) return PB200_ERR_UNSUPPORTED;
     if (engine == 4 && !block28_has_umma(k->fast)) return PB200_ERR_UNSUPPORTED;
+    if (engine == 5 && !block28_has_umma2(k->fast)) return PB200_ERR_UNSUPPORTED;
     USE_DEVICE(k);
     CU(block28_debug_mulmod(k->fast, engine - 2, v_in, y_in, reps, v_out, t_out, qhat_rows, k->stream));
     return PB200_OK;
 } PB200_CATCH
 int pb200_debug_mulmod_cycles(pb200_key* k, int engine, const int32_t* v_in, int ctas, int reps, int stagger_cycles, int64_t* cycles_out) try {
-    if (!k || !v_in || !cycles_out || engine < 3 || engine > 4 || ctas < 1 || reps < 1) return PB200_ERR_INVALID_ARG;
+    if (!k || !v_in || !cycles_out || engine < 3 || engine > 5 || ctas < 1 || reps < 1) return PB200_ERR_INVALID_ARG;
     if (!k->fast) return PB200_ERR_UNSUPPORTED;
     if (engine == 4 && !block28_has_umma(k->fast)) return PB200_ERR_UNSUPPORTED;
+    if (engine == 5 && !block28_has_umma2(k->fast)) return PB200_ERR_UNSUPPORTED;
     USE_DEVICE(k);
     CU(block28_debug_time(k->fast, engine - 2, v_in, ctas, reps, stagger_cycles, (long long*)cycles_out, k->stream));
     return PB200_OK;

@@ -40,10 +40,12 @@ Block28Key* block28_create(const BigInt& n, const BigInt& g, uint32_t n_bits, in
                            std::string* why, cudaError_t* cuda_err);
 void block28_destroy(Block28Key*);
 const char* block28_name(const Block28Key*);
-// 0: every phase on IMAD (block28), 1: constant-operand phases on mma.sync (block28t), 2: on tcgen05 + TMEM (block28u; falls back
-// to 1 where no such variant is compiled), -1: fastest available.  Returns the engine in effect.
+// 0: every phase on IMAD (block28), 1: constant-operand phases on mma.sync (block28t), 2: on tcgen05 + TMEM with 32 ciphertexts per
+// CTA (block28u), 3: with 64 per CTA (block28u2); each falls back to the next lower one the key size has; -1: fastest available.
+// Returns the engine in effect.
 int block28_set_engine(Block28Key*, int eng);
 bool block28_has_umma(const Block28Key*);
+bool block28_has_umma2(const Block28Key*);
 void block28_chain_counts(const Block28Key*, uint64_t* n_sqr, uint64_t* n_mul);
 cudaError_t block28_encrypt(Block28Key*, const u64* d_m, const u64* d_r, size_t count, u64* d_c, cudaStream_t st);
 cudaError_t block28_tally(Block28Key*, const u64* d_c, size_t count, u64* d_out, cudaStream_t st);

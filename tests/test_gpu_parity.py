@@ -12,7 +12,7 @@ from util import h, kat
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = [1, 2, 3, 4]  # simple64, block28 (IMAD only), block28t (IMAD + mma.sync), block28u (IMAD + tcgen05); 2-4 skipped when the size is not covered
+ENGINES = [1, 2, 3, 4, 5]  # simple64, block28 (IMAD only), block28t (IMAD + mma.sync), block28u / block28u2 (IMAD + tcgen05, 32 / 64 ciphertexts per CTA); 2-5 skipped when the size is not covered
 
 
 def _key(n, g, n_bits, limb_bits, engine):

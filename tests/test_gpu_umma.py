@@ -17,11 +17,11 @@ from tools.umma_debug import image
 pytestmark = pytest.mark.gpu
 
 
-def _key_u(n_bits=2048, g="g_rand"):
+def _key_u(n_bits=2048, g="g_rand", engine=4):
     kd = workload.load_key(n_bits)
     key = PaillierKey(kd["n"], kd[g], n_bits)
     try:
-        key.set_engine(4)
+        key.set_engine(engine)
     except Pb200Error as e:
         key.close()
         if e.status == _lib.PB200_ERR_UNSUPPORTED:
@@ -43,10 +43,11 @@ def _lazy_values(rng, L, edge):
     return out
 
 
+@pytest.mark.parametrize("engine", [4, 5])
 @pytest.mark.parametrize("mode", ["sqr", "mul"])
 @pytest.mark.parametrize("edge", [False, True])
-def test_block28u_digits_equal_block28t(built_lib, mode, edge):
-    key, _ = _key_u()
+def test_block28u_digits_equal_block28t(built_lib, mode, edge, engine):
+    key, _ = _key_u(engine=engine)
     with key:
         lib = key._lib
         g, bl = C.c_int(), C.c_int()
@@ -58,7 +59,7 @@ def test_block28u_digits_equal_block28t(built_lib, mode, edge):
         y = image(_lazy_values(rng, L, edge), G, BL) if mode == "mul" else None
         yp = y.ctypes.data if y is not None else None
         outs = {}
-        for eng in (3, 4):
+        for eng in (3, engine):
             t = np.zeros((2 * G, CH, 32, 4), dtype=np.int32)
             assert lib.pb200_debug_mulmod(key.handle, eng, v.ctypes.data, yp, 1, None, t.ctypes.data, None) == 0
             vo = np.zeros_like(v)
@@ -67,7 +68,7 @@ def test_block28u_digits_equal_block28t(built_lib, mode, edge):
             v9 = np.zeros_like(v)
             assert lib.pb200_debug_mulmod(key.handle, eng, v.ctypes.data, yp, 9, v9.ctypes.data, None, None) == 0
             outs[eng] = (t, vo, rows, v9)
-        for a, b in zip(outs[3], outs[4]):
+        for a, b in zip(outs[3], outs[engine]):
             assert np.array_equal(a, b)
         # the product itself against Python ints (every lane)
         def val(img, lane, blocks):
@@ -75,20 +76,21 @@ def test_block28u_digits_equal_block28t(built_lib, mode, edge):
         for lane in range(32):
             a = val(v, lane, G)
             b = val(y, lane, G) if y is not None else a
-            assert val(outs[4][0], lane, 2 * G) == a * b
+            assert val(outs[engine][0], lane, 2 * G) == a * b
         # and the lazy result is congruent to it modulo n^2 (the modulus of the engine is a multiple of n^2)
         n2 = key.n * key.n
         for lane in range(0, 32, 5):
             a = val(v, lane, G)
             b = val(y, lane, G) if y is not None else a
-            assert (val(outs[4][1], lane, G) - a * b) % n2 == 0
+            assert (val(outs[engine][1], lane, G) - a * b) % n2 == 0
 
 
+@pytest.mark.parametrize("engine", [4, 5])
 @pytest.mark.parametrize("g", ["g_rand", "g_std"])
-def test_block28u_batch_vs_cpu_and_block28t(built_lib, g):
-    """ragged batch (not a multiple of 32), every unit against the OpenSSL port of the oracle and against block28t"""
-    count = 2500
-    key, kd = _key_u(2048, g)
+def test_block28u_batch_vs_cpu_and_block28t(built_lib, g, engine):
+    """ragged batch (not a multiple of 32 or 64), every unit against the OpenSSL port of the oracle and against block28t"""
+    count = 2500 + 33 * (engine == 5)
+    key, kd = _key_u(2048, g, engine)
     with key:
         assert key.engine.startswith("block28u")
         m_w, r_w = workload.units(2048, count, seed_offset=5)
@@ -103,15 +105,16 @@ def test_block28u_batch_vs_cpu_and_block28t(built_lib, g):
         assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("count", [1, 31, 33, 1000, 20011])
-def test_block28u_tally_and_decrypt(built_lib, count):
-    key, kd = _key_u()
+@pytest.mark.parametrize("engine", [4, 5])
+@pytest.mark.parametrize("count", [1, 31, 33, 65, 1000, 20011])
+def test_block28u_tally_and_decrypt(built_lib, count, engine):
+    key, kd = _key_u(engine=engine)
     with key:
         n = kd["n"]
         cs_w = workload.ciphertexts(2048, count, n)
         got = words_to_ints(key.tally_words(cs_w).reshape(1, -1))[0]
         assert got == tally_native(n, words_to_ints(cs_w))
-    key, kd = _key_u(2048, "g_std")
+    key, kd = _key_u(2048, "g_std", engine)
     with key:
         p, q, n = kd["p"], kd["q"], kd["n"]
         lam = (p - 1) * (q - 1)

@@ -20,15 +20,15 @@ def main():
     vals = [int.from_bytes(rng.bytes(525), "little") for _ in range(32)]
     v = image(vals, 8, 19)
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-    engines = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [3, 4]
+    engines = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [3, 4, 5]
     for eng in engines:
-        for ctas, mode in ((148, 1), (296, 1), (296, 0), (148, -3), (148, -4), (296, -3), (296, -4), (296, -2)):
+        for ctas, mode in (((148, 1), (148, -3), (148, -4)) if eng == 5 else ((148, 1), (296, 1), (148, -3), (148, -4), (296, -3), (296, -4), (296, -2))):
             cyc = np.zeros((ctas, 3), dtype=np.int64)
             rc = lib.pb200_debug_mulmod_cycles(key.handle, eng, v.ctypes.data, ctas, reps, mode, cyc.ctypes.data)
             nz = lambda col: float(col[col > 0].mean()) / reps if (col > 0).any() else 0.0  # noqa: E731
             a, b, t = nz(cyc[:, 0]), nz(cyc[:, 1]), nz(cyc[:, 2])
             print(json.dumps({"engine": eng, "ctas": ctas, "mode": mode, "rc": rc, "phaseA_clk": round(a), "phasesBC_clk": round(b),
-                              "loop_clk_per_mulmod": round(t)}))
+                              "loop_clk_per_mulmod": round(t), "sm_clk_per_lane_mulmod": round(t / (64 if eng == 5 else 32) / (ctas / 148), 1)}))
 
 
 if __name__ == "__main__":

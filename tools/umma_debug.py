@@ -74,7 +74,7 @@ def main():
         v = image(rnd_vals(), G, BL)
         y = image(rnd_vals(), G, BL) if mode == "mul" else None
         outs = {}
-        for eng in (3, 4):
+        for eng in (3, 4, 5):
             t = np.zeros((2 * G, CH, 32, 4), dtype=np.int32)
             rc = lib.pb200_debug_mulmod(key.handle, eng, v.ctypes.data, y.ctypes.data if y is not None else None, 1, None, t.ctypes.data, None)
             if rc:
@@ -91,9 +91,11 @@ def main():
                 bad = True
                 continue
             outs[eng] = (t, vo, rows, v5)
-        if 3 in outs and 4 in outs:
+        for other in (4, 5):
+          if 3 in outs and other in outs:
             for name, idx in (("phaseA_T", 0), ("v_out", 1), ("qhat_rows", 2), ("v_out_5reps", 3)):
-                a, b = outs[3][idx], outs[4][idx]
+                name = f"eng{other}_{name}"
+                a, b = outs[3][idx], outs[other][idx]
                 neq = a != b
                 n = int(neq.sum())
                 res[f"{mode}_{name}_mismatch"] = n
@@ -103,9 +105,10 @@ def main():
                     res[f"{mode}_{name}_first"] = [[int(x) for x in w] for w in where[:6]]
                     res[f"{mode}_{name}_a"] = [int(a[tuple(w)]) for w in where[:6]]
                     res[f"{mode}_{name}_b"] = [int(b[tuple(w)]) for w in where[:6]]
-                    if name == "qhat_rows":
+                    if name.endswith("qhat_rows"):
                         res[f"{mode}_qhat_bad_digits"] = sorted(set(int(w[1]) for w in where))[:40]
                         res[f"{mode}_qhat_bad_lanes"] = sorted(set(int(w[0]) for w in where))[:40]
+        if 3 in outs:
             # the product itself against Python: T == v * y for lane 0..3 (engine 3 is the reference of the comparison)
             t3 = outs[3][0]
             ok = True
@@ -117,18 +120,19 @@ def main():
             res[f"{mode}_phaseA_vs_python"] = ok
             bad |= not ok
     # small encrypt batch on every fast engine
-    m, r = workload.units(n_bits, 96)
+    m, r = workload.units(n_bits, 101)
     cs = {}
-    for eng in (2, 3, 4):
+    for eng in (2, 3, 4, 5):
         try:
             key.set_engine(eng)
             cs[eng] = key.encrypt_words(m, r)
         except Exception as e:  # noqa: BLE001
             res[f"encrypt_eng{eng}_error"] = str(e)[:200]
             bad = True
-    if 3 in cs and 4 in cs:
-        res["encrypt_eng4_vs_eng3_mismatch_units"] = int((cs[3] != cs[4]).any(axis=1).sum())
-        bad |= res["encrypt_eng4_vs_eng3_mismatch_units"] != 0
+    for other in (4, 5):
+        if 3 in cs and other in cs:
+            res[f"encrypt_eng{other}_vs_eng3_mismatch_units"] = int((cs[3] != cs[other]).any(axis=1).sum())
+            bad |= res[f"encrypt_eng{other}_vs_eng3_mismatch_units"] != 0
     if 2 in cs and 3 in cs:
         res["encrypt_eng3_vs_eng2_mismatch_units"] = int((cs[2] != cs[3]).any(axis=1).sum())
     res["ok"] = not bad
