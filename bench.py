@@ -39,7 +39,7 @@ def emit(line: dict) -> None:
 N_BITS = 2048
 UNITS = 1 << 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_encrypt launch (ncu --set full, profiles/), keyed by (|n|, units)
-TRAFFIC_BYTES = {(2048, 1 << 16): 6121053000 + 806334464}   # profiles/ncu_k_encrypt_r01_fused_summary.txt
+TRAFFIC_BYTES = {(2048, 1 << 16): 12073794000 + 1481068000}   # profiles/ncu_k_encrypt_r02_block28u_summary.txt (comb-table gathers + r-power scratch)
 METRIC = "paillier_enc_per_s_n2048"
 UNIT = "enc/s"
 
