@@ -369,7 +369,7 @@ def leg_witness(cx, key, kd, g, n_bits, m_w, r_w, d_m, d_r, reps=2):
     (w_ms,) = cx.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / len(evs))
     n_sqr, n_mul, a_wit = witness_chain_macs(kd, m_w, n_bits)
     peak_w, _ = imad_peak()
-    out = {"value": cx.world * units / (w_ms * 1e-3), "unit": "units/s", "engine": key.witness_engine, "ms_per_launch": w_ms,
+    out = {"value": cx.world * units / (w_ms * 1e-3), "unit": "units/s", "engine": key.witness_engine, "arithmetic": key.engine, "ms_per_launch": w_ms,
            "units_per_gpu": units, "records_per_unit": n_sqr + n_mul, "mul_mod_per_s": cx.world * units * (n_sqr + n_mul) / (w_ms * 1e-3),
            "witness_stream_GBps": cx.world * units * (n_sqr + n_mul) * 2 * key.words_out * 8 / (w_ms * 1e-3) / 1e9,
            "chain": {"mod_sqr": n_sqr, "mod_mul": n_mul, "mac_per_unit": a_wit},
@@ -613,7 +613,7 @@ def run_witness(args):
         peak, src = imad_peak()
         line = {"metric": f"paillier_witness_units_per_s_n{N_BITS}", "value": res["value"], "unit": "units/s", "n_gpus": cx.world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_launch"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "int64 columns over signed 28-bit digits + s8 IMMA, exact (q, rem) tail", "data": "synthetic",
+                "vs_baseline": None, "dtype": "int64 columns over signed 28-bit digits + s8 tensor-core phases, exact (q, rem) tail", "data": "synthetic",
                 "config": {"workload": f"batched encrypt + (q, rem) limb witness of every mul_mod, |n|={N_BITS}, {units} units per GPU per step"},
                 "gpu_launches": res["gpu_launches"], "clocks": res["clocks"], "parity": res["parity"], "witness": res,
                 "roofline": {"bound": "imad", "achieved": res["frac_of_imad_peak"] * peak / 1e12, "peak": peak / 1e12, "unit": "TMAC/s",

@@ -711,6 +711,38 @@ __device__ __forceinline__ void load_value_shl(int4* buf, const u64* src, int nw
     __syncthreads();
 }
 
+// ---- witness engine selection: 0 = block28t arithmetic (mma.sync phases), 1 = block28u arithmetic (tcgen05 phases) ---------------
+template <class C, int WENG> struct WView {
+    typedef Smem<C> type;
+    static constexpr size_t BYTES = C::SMEM_W_BYTES;
+    static constexpr int PER_SM = C::CTAS_PER_SM;
+};
+template <class C> struct WView<C, 1> {
+    typedef SmemU<C, 1, true> type;
+    static constexpr size_t BYTES = UL<C, 1, true>::SMEM_BYTES;
+    static constexpr int PER_SM = UL<C, 1, true>::CTAS_PER_SM;
+};
+template <class C, int WENG, class SV>
+__device__ __forceinline__ void w_begin(SV& S, int4* smem_base, const B28Dev& K) {
+    if constexpr (WENG == 1) {
+        typedef UL<C, 1, true> U;
+        int4* dst = (int4*)((unsigned char*)smem_base + U::OFF_CONST);
+        for (int i = threadIdx.x; i < U::KEY_BYTES / 16; i += C::THREADS) dst[i] = K.uconsts[i];
+        umma_setup<C, 1, true>(S);
+    } else load_consts<C>(smem_base, K);
+}
+template <class C, int WENG, class SV>
+__device__ __forceinline__ void w_end(SV& S) {
+    if constexpr (WENG == 1) umma_teardown<C, 1, true>(S);
+}
+// one witnessed mul_mod (contract of mulmod_w, block28.cuh)
+template <class C, int WENG, class SV>
+__device__ __forceinline__ u64 wmm(int4* smem_base, SV& S, const int4* Y, int sqr, int4* next_dst, WStep out, int sh, int words_out,
+                                   double inv, const u64* cpow) {
+    if constexpr (WENG == 1) return mulmod_wu<C>(smem_base, S.tmem, Y, sqr, next_dst, out, sh, words_out, inv, cpow);
+    else return mulmod_w<C>(smem_base, Y, sqr, next_dst, out, sh, words_out, inv, cpow);
+}
+
 // table entries of the witness chain from 64-bit words: entry i = strict digits of (value_i << shl), one thread per entry.
 // value_0 = g (words_in words); value_i = rem of g-chain record i-1 (words_out words at gchain + (i-1)*2*wo + wo)
 template <class C>
@@ -742,19 +774,20 @@ __global__ void k_wtab(const u64* __restrict__ g_words, int words_in, const u64*
 
 // per-key g-chain on the witness engine: record i = (q, rem) of (g^(2^i))^2, i < n_bits, and the table entries
 // gtab[i] = strict digits of g^(2^i) * 2^s.  One CTA; every lane computes the same value, lane 0 writes.
-template <class C>
+template <class C, int WENG>
 __global__ void __launch_bounds__(C::THREADS, 1) k_gchain_w(B28Dev K, WitDev Wd, const u64* __restrict__ g_words, int n_bits,
                                                             u64* __restrict__ gchain, int4* __restrict__ gtab) {
     extern __shared__ int4 smem[];
-    Smem<C> S(smem);
+    typename WView<C, WENG>::type S(smem);
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    load_consts<C>(smem, K);
+    w_begin<C, WENG>(S, smem, K);
     load_value_shl<C>(S.V, g_words, K.words_in, Wd.sh >> 1, role, lane);
     for (int i = 0; i < n_bits; i++) {
         if (lane == 0) scatter_entry<C>(gtab + (size_t)i * C::ENTRY4, S.V, role, lane);
         WStep o; o.rec = lane == 0 ? gchain + (size_t)i * 2 * K.words_out : nullptr; o.rem_out = nullptr;
-        mulmod_w<C>(smem, nullptr, 1, S.V, o, Wd.sh, K.words_out, Wd.inv, Wd.cpow);
+        wmm<C, WENG>(smem, S, nullptr, 1, S.V, o, Wd.sh, K.words_out, Wd.inv, Wd.cpow);
     }
+    w_end<C, WENG>(S);
 }
 
 template <class C>
@@ -770,12 +803,12 @@ __device__ __forceinline__ void bcast_entry(int4* buf, const int4* entry, int ro
 // Lanes walk their own set bits of m (inactive lanes multiply by one and emit nothing); the r-chain is uniform.
 // In the r-chain the multiplication of an iteration is computed BEFORE its squaring (cur stays in V), the
 // records keep the reference's order (sqr_i, then mul_i).
-template <class C>
-__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_witness(B28Dev K, WitDev Wd, WitIO A) {
+template <class C, int WENG>
+__global__ void __launch_bounds__(C::THREADS, WView<C, WENG>::PER_SM) k_witness(B28Dev K, WitDev Wd, WitIO A) {
     extern __shared__ int4 smem[];
-    Smem<C> S(smem);
+    typename WView<C, WENG>::type S(smem);
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    load_consts<C>(smem, K);
+    w_begin<C, WENG>(S, smem, K);
     size_t unit = (size_t)blockIdx.x * 32 + lane;
     const bool active = unit < A.count;
     if (!active) unit = A.count - 1;
@@ -806,7 +839,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_witness(B28Dev K
             }
             bcast_entry<C>(S.B, e, role, lane);
             WStep o; o.rec = (act && rec) ? rec + (size_t)t * recw : nullptr; o.rem_out = nullptr;
-            const u64 H = mulmod_w<C>(smem, S.B, 0, S.V, o, Wd.sh, wo, Wd.inv, Wd.cpow);
+            const u64 H = wmm<C, WENG>(smem, S, S.B, 0, S.V, o, Wd.sh, wo, Wd.inv, Wd.cpow);
             if (act) D = (D ^ H) * PB200_DIGEST_PRIME;
         }
     }
@@ -822,11 +855,11 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_witness(B28Dev K
         if (bit) {
             copy_from_global<C>(S.B, sc_acc, role, lane);
             WStep o; o.rec = rec ? rec + (idx + 1) * recw : nullptr; o.rem_out = nullptr;
-            Hm = mulmod_w<C>(smem, S.B, 0, S.B, o, Wd.sh, wo, Wd.inv, Wd.cpow);
+            Hm = wmm<C, WENG>(smem, S, S.B, 0, S.B, o, Wd.sh, wo, Wd.inv, Wd.cpow);
             copy_to_global<C>(sc_acc, S.B, role, lane);
         }
         WStep o; o.rec = rec ? rec + idx * recw : nullptr; o.rem_out = nullptr;
-        const u64 Hs = mulmod_w<C>(smem, nullptr, 1, S.V, o, Wd.sh, wo, Wd.inv, Wd.cpow);
+        const u64 Hs = wmm<C, WENG>(smem, S, nullptr, 1, S.V, o, Wd.sh, wo, Wd.inv, Wd.cpow);
         D = (D ^ Hs) * PB200_DIGEST_PRIME;
         if (bit) D = (D ^ Hm) * PB200_DIGEST_PRIME;
         idx += bit ? 2 : 1;
@@ -838,23 +871,24 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_witness(B28Dev K
     {
         WStep o; o.rec = rec ? rec + idx * recw : nullptr;
         o.rem_out = (A.c_out && active) ? A.c_out + unit * wo : nullptr;
-        const u64 H = mulmod_w<C>(smem, S.B, 0, nullptr, o, Wd.sh, wo, Wd.inv, Wd.cpow);
+        const u64 H = wmm<C, WENG>(smem, S, S.B, 0, nullptr, o, Wd.sh, wo, Wd.inv, Wd.cpow);
         D = (D ^ H) * PB200_DIGEST_PRIME;
     }
     if (role == 0 && active && A.digest) A.digest[unit] = D;
+    w_end<C, WENG>(S);
 }
 
 // paillier_add_native / PaillierChip::add (src/paillier.rs:62-85, :94-97) for `count` pairs on the witness engine:
 // one exact mul_mod per lane, rem (and optionally q) as 64-bit words.  Inputs are c_words words each (zero-extended,
 // src/paillier.rs:79-80) and need not be reduced; a quotient that does not fit words_out words raises the range flag.
-template <class C>
-__global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_add_w(B28Dev K, WitDev Wd, const u64* __restrict__ c1,
+template <class C, int WENG>
+__global__ void __launch_bounds__(C::THREADS, WView<C, WENG>::PER_SM) k_add_w(B28Dev K, WitDev Wd, const u64* __restrict__ c1,
                                                                       const u64* __restrict__ c2, int c_words, size_t count,
                                                                       u64* __restrict__ out, u64* __restrict__ q_out, int* flags) {
     extern __shared__ int4 smem[];
-    Smem<C> S(smem);
+    typename WView<C, WENG>::type S(smem);
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    load_consts<C>(smem, K);
+    w_begin<C, WENG>(S, smem, K);
     const int wo = K.words_out;
     for (size_t first = (size_t)blockIdx.x * 32; first < count; first += (size_t)gridDim.x * 32) {
         size_t unit = first + lane;
@@ -865,7 +899,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_add_w(B28Dev K, 
         // the record goes through a per-lane staging area only when q is wanted; rem alone is written directly
         WStep o; o.rec = nullptr; o.rem_out = active ? out + unit * wo : nullptr;
         o.q_out = (active && q_out) ? q_out + unit * wo : nullptr;
-        mulmod_w<C>(smem, S.B, 0, nullptr, o, Wd.sh, wo, Wd.inv, Wd.cpow);
+        wmm<C, WENG>(smem, S, S.B, 0, nullptr, o, Wd.sh, wo, Wd.inv, Wd.cpow);
         // q must fit words_out words (range check of assign_integer(q, 2*enc_bits)): canonical q digits are in T
         {
             const int* Qf = (const int*)S.T + C::L * 32;
@@ -883,6 +917,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS_PER_SM) k_add_w(B28Dev K, 
         }
         __syncthreads();
     }
+    w_end<C, WENG>(S);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -909,6 +944,7 @@ struct Block28Key {
     // witness engine (lazy: block28_witness_prepare)
     BigInt n; uint32_t n_bits = 0;
     bool wit_ready = false;
+    int4* d_wuconsts = nullptr; bool has_wu = false;     // witness engine on the tcgen05 phases
     int4* d_wconsts = nullptr; int4* d_gtab = nullptr; int4* d_one_s = nullptr; u64* d_cpow = nullptr; u64* d_nwords = nullptr;
     int4* d_wscratch = nullptr; size_t wscratch_ctas = 0;
     B28Dev wdev{}; WitDev wit{};
@@ -1229,13 +1265,37 @@ static cudaError_t witness_prepare_cfg(Block28Key* key, u64* d_gchain, bool gcha
     WitDev& Wd = key->wit;
     Wd.gtab = key->d_gtab; Wd.one_s = key->d_one_s; Wd.cpow = key->d_cpow; Wd.n_words = key->d_nwords;
     Wd.exp_bits = (int)n.bits(); Wd.sh = sh; Wd.inv = 1048576.0 / topd;
-    CUW(cudaFuncSetAttribute(k_witness<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES));
-    CUW(cudaFuncSetAttribute(k_gchain_w<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES));
-    CUW(cudaFuncSetAttribute(k_add_w<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES));
+    CUW((cudaFuncSetAttribute(k_witness<C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES)));
+    CUW((cudaFuncSetAttribute(k_gchain_w<C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES)));
+    CUW((cudaFuncSetAttribute(k_add_w<C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_W_BYTES)));
+    if constexpr (UL<C, 1, true>::SUPPORTED) {
+        // the same step on the tcgen05 phases: constants of the witness modulus + their Toeplitz core-matrix tables
+        typedef UL<C, 1, true> U;
+        std::vector<signed char> img(U::KEY_BYTES, 0);
+        memcpy(img.data(), all.data(), 3 * C::ENTRY4 * 16);
+        std::vector<signed char> k7(C::K7);
+        to_k7<C>(e_mu, k7);
+        umma_cm_table<C, 1>(k7.data(), true, img.data() + (U::OFF_CMH - U::OFF_CONST));
+        to_k7<C>(e_nt, k7);
+        umma_cm_table<C, 1>(k7.data(), false, img.data() + (U::OFF_CML - U::OFF_CONST));
+        CUW(cudaMalloc(&key->d_wuconsts, img.size()));
+        CUW(cudaMemcpyAsync(key->d_wuconsts, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+        CUW(cudaStreamSynchronize(st));
+        key->wdev.uconsts = key->d_wuconsts;
+        key->has_wu = !getenv("PB200_NO_UMMA_WITNESS");
+        CUW((cudaFuncSetAttribute(k_witness<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::SMEM_BYTES)));
+        CUW((cudaFuncSetAttribute(k_gchain_w<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::SMEM_BYTES)));
+        CUW((cudaFuncSetAttribute(k_add_w<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::SMEM_BYTES)));
+    }
     if (gchain_ready) {        // g-chain records already produced (simple64): only convert them into table entries
         k_wtab<C><<<(key->n_bits + 63) / 64, 64, 0, st>>>(key->d_gwords, wi, d_gchain, wo, (int)key->n_bits, sh / 2, key->d_gtab);
     } else {                   // produce records and table entries with the witness engine itself
-        k_gchain_w<C><<<1, C::THREADS, C::SMEM_W_BYTES, st>>>(key->wdev, key->wit, key->d_gwords, (int)key->n_bits, d_gchain, key->d_gtab);
+        bool done = false;
+        if constexpr (UL<C, 1, true>::SUPPORTED) if (key->has_wu && key->eng >= 2) {
+            k_gchain_w<C, 1><<<1, C::THREADS, UL<C, 1, true>::SMEM_BYTES, st>>>(key->wdev, key->wit, key->d_gwords, (int)key->n_bits, d_gchain, key->d_gtab);
+            done = true;
+        }
+        if (!done) k_gchain_w<C, 0><<<1, C::THREADS, C::SMEM_W_BYTES, st>>>(key->wdev, key->wit, key->d_gwords, (int)key->n_bits, d_gchain, key->d_gtab);
     }
     count_launch();
     CUW(cudaGetLastError());
@@ -1257,7 +1317,12 @@ static cudaError_t witness_cfg(Block28Key* key, const u64* d_m, const u64* d_r, 
     WitIO A;
     A.m = d_m; A.r = d_r; A.count = count; A.c_out = d_c; A.records = d_records; A.offsets = d_offsets; A.digest = d_digest;
     A.scratch = key->d_wscratch;
-    k_witness<C><<<(unsigned)ctas, C::THREADS, C::SMEM_W_BYTES, st>>>(key->wdev, key->wit, A);
+    bool done = false;
+    if constexpr (UL<C, 1, true>::SUPPORTED) if (key->has_wu && key->eng >= 2) {
+        k_witness<C, 1><<<(unsigned)ctas, C::THREADS, UL<C, 1, true>::SMEM_BYTES, st>>>(key->wdev, key->wit, A);
+        done = true;
+    }
+    if (!done) k_witness<C, 0><<<(unsigned)ctas, C::THREADS, C::SMEM_W_BYTES, st>>>(key->wdev, key->wit, A);
     count_launch();
     return cudaGetLastError();
 }
@@ -1298,6 +1363,7 @@ void block28_destroy(Block28Key* key) {
     for (int i = 0; i < TALLY_MAXW; i++) if (key->ipc_opened[i]) cudaIpcCloseMemHandle(key->ipc_opened[i]);
     if (key->d_mail) cudaFree(key->d_mail);
     if (key->d_wconsts) cudaFree(key->d_wconsts);
+    if (key->d_wuconsts) cudaFree(key->d_wuconsts);
     if (key->d_gtab) cudaFree(key->d_gtab);
     if (key->d_one_s) cudaFree(key->d_one_s);
     if (key->d_cpow) cudaFree(key->d_cpow);
@@ -1472,7 +1538,12 @@ static cudaError_t add_cfg(Block28Key* key, const u64* d_c1, const u64* d_c2, in
                            int* d_flags, cudaStream_t st) {
     size_t ctas = (count + 31) / 32, cap = (size_t)C::CTAS_PER_SM * key->sms;
     if (ctas > cap) ctas = cap;
-    k_add_w<C><<<(unsigned)ctas, C::THREADS, C::SMEM_W_BYTES, st>>>(key->wdev, key->wit, d_c1, d_c2, c_words, count, d_out, d_q, d_flags);
+    bool done = false;
+    if constexpr (UL<C, 1, true>::SUPPORTED) if (key->has_wu && key->eng >= 2) {
+        k_add_w<C, 1><<<(unsigned)ctas, C::THREADS, UL<C, 1, true>::SMEM_BYTES, st>>>(key->wdev, key->wit, d_c1, d_c2, c_words, count, d_out, d_q, d_flags);
+        done = true;
+    }
+    if (!done) k_add_w<C, 0><<<(unsigned)ctas, C::THREADS, C::SMEM_W_BYTES, st>>>(key->wdev, key->wit, d_c1, d_c2, c_words, count, d_out, d_q, d_flags);
     count_launch();
     return cudaGetLastError();
 }

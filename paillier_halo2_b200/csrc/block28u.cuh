@@ -36,7 +36,9 @@
 namespace pb200 {
 namespace b28 {
 
-template <class C, int LG>
+// WIT: layout of the witness engine — the q1 rows overlay B and a gap behind it instead of V | B, because the witness step must
+// preserve its first operand (block28.cuh, mulmod_w)
+template <class C, int LG, bool WIT = false>
 struct UL {
     static constexpr int L = C::L, K7 = C::K7, G = C::G;
     static constexpr int KCH = K7 / 16;                        // 16-byte K chunks per row
@@ -81,31 +83,34 @@ struct UL {
     static constexpr int Z0_H = z0(true), Z0_L = z0(false), NCM_H = ncm(true), NCM_L = ncm(false);
     // byte offsets in dynamic shared memory
     static constexpr int VALB = C::VAL4 * 16;
-    static constexpr int OFF_T = 2 * LG * VALB, OFF_ASC = OFF_T + LG * VALB;       // T low halves of all groups, then the high halves
+    static constexpr int ASB_OFF = WIT ? VALB : 0;                                  // where the q1 rows start
+    static constexpr int GAP = WIT ? ((A_BYTES > VALB ? A_BYTES - VALB : 0) + 127) / 128 * 128 : 0;
+    static constexpr int OFF_T = 2 * LG * VALB + GAP, OFF_ASC = OFF_T + LG * VALB;   // T low halves of all groups, then the high halves
     static constexpr int T_HI_JUMP = (LG - 1) * VALB;                                // block d >= G of a group lies this much further
     static constexpr int END_ASC = OFF_ASC + A_BYTES;
     static constexpr int OFF_CONST = ((END_ASC > OFF_T + 2 * LG * VALB ? END_ASC : OFF_T + 2 * LG * VALB) + 127) / 128 * 128;
     static constexpr int CONST_BYTES = (3 * C::ENTRY4 * 16 + 127) / 128 * 128;
     static constexpr int OFF_CMH = OFF_CONST + CONST_BYTES, OFF_CML = OFF_CMH + NCM_H * 128, OFF_BAR = OFF_CML + NCM_L * 128;
     static constexpr int KEY_BYTES = OFF_BAR - OFF_CONST;      // per-key image copied from global memory: constants, CM(mu), CM(Nt)
-    static constexpr size_t SMEM_BYTES = (size_t)OFF_BAR + 64;
+    static constexpr int OFF_EST = OFF_BAR + 64;               // witness engine: one int per lane (k estimate)
+    static constexpr size_t SMEM_BYTES = (size_t)OFF_BAR + 64 + (WIT ? 128 : 0);
     static constexpr int CTAS_PER_SM = (int)((233472 / (SMEM_BYTES + 1024)) < (512 / THREADS) ? (233472 / (SMEM_BYTES + 1024)) : (512 / THREADS));
     // compiled for configurations with whole k-steps per row, four tiles per phase (every mbarrier completes an even number of times
     // per multiplication, so the wait parities are compile-time constants), the q1 rows inside V | B and 8 warps per lane group
-    static constexpr bool SUPPORTED = (K7 % 32 == 0) && (NT_H == 4) && (NT_L == 4) && (A_BYTES <= 2 * LG * VALB) && (G == 8) &&
+    static constexpr bool SUPPORTED = (K7 % 32 == 0) && (NT_H == 4) && (NT_L == 4) && (WIT ? (LG == 1 && A_BYTES <= VALB + GAP && GAP >= G * 32 * 8) : (A_BYTES <= 2 * LG * VALB)) && (G == 8) &&
                                       (Z0_H % 8 == 7) && (Z0_L % 8 == 7) && (P_BASE_H % 8 == 0) && (TN <= 128 * LG + 32 * (LG - 1)) &&
                                       (2 * TN <= TMEM_COLS) && CTAS_PER_SM >= 1 && SMEM_BYTES <= 232448;
 };
 
 // Shared-memory view of one thread's lane group.  Member names follow Smem<C> so the kernels are written once.
-template <class C, int LG>
+template <class C, int LG, bool WIT = false>
 struct SmemU {
     int4* V; int4* B; int4* T; const int4* mu; const int4* Nt; const int4* two_sh;
     unsigned char* base;
     uint32_t tmem;          // TMEM base address of this CTA's columns
     int group;              // lane group of this thread in phase A and in the kernels' value handling: warp / G
     __device__ __forceinline__ SmemU(int4* b) {
-        typedef UL<C, LG> U;
+        typedef UL<C, LG, WIT> U;
         base = (unsigned char*)b;
         group = LG == 1 ? 0 : (int)(threadIdx.x >> 5) / C::G;
         V = b + group * 2 * C::VAL4; B = V + C::VAL4;
@@ -115,11 +120,11 @@ struct SmemU {
         tmem = 0;
     }
     // block d of this group's 2L-digit product
-    __device__ __forceinline__ int4* tblk(int d, int lane) const { return T + d * C::BLK4 + (d >= C::G ? UL<C, LG>::T_HI_JUMP / 16 : 0) + lane; }
-    __device__ __forceinline__ unsigned char* asb() const { return base; }
-    __device__ __forceinline__ unsigned char* asc() const { return base + UL<C, LG>::OFF_ASC; }
-    __device__ __forceinline__ uint64_t* bars() const { return (uint64_t*)(base + UL<C, LG>::OFF_BAR); }
-    __device__ __forceinline__ volatile uint32_t* slots() const { return (volatile uint32_t*)(base + UL<C, LG>::OFF_BAR + 32); }   // [0] TMEM base, [1] dead
+    __device__ __forceinline__ int4* tblk(int d, int lane) const { return T + d * C::BLK4 + (d >= C::G ? UL<C, LG, WIT>::T_HI_JUMP / 16 : 0) + lane; }
+    __device__ __forceinline__ unsigned char* asb() const { return base + UL<C, LG, WIT>::ASB_OFF; }
+    __device__ __forceinline__ unsigned char* asc() const { return base + UL<C, LG, WIT>::OFF_ASC; }
+    __device__ __forceinline__ uint64_t* bars() const { return (uint64_t*)(base + UL<C, LG, WIT>::OFF_BAR); }
+    __device__ __forceinline__ volatile uint32_t* slots() const { return (volatile uint32_t*)(base + UL<C, LG, WIT>::OFF_BAR + 32); }   // [0] TMEM base, [1] dead
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------------
@@ -192,9 +197,9 @@ __device__ __forceinline__ void group_sync(int group) {
 }
 
 // ---- per-CTA set-up / tear-down -----------------------------------------------------------------------------------------
-template <class C, int LG>
-__device__ __forceinline__ void umma_setup(SmemU<C, LG>& S) {
-    using U = UL<C, LG>;
+template <class C, int LG, bool WIT>
+__device__ __forceinline__ void umma_setup(SmemU<C, LG, WIT>& S) {
+    using U = UL<C, LG, WIT>;
     const int warp = threadIdx.x >> 5;
     // bars 0, 1: the MMAs of a TMEM buffer are complete (tcgen05.commit);  2, 3: every warp has read the buffer out (one arrival per warp)
     if (threadIdx.x == 0) {
@@ -215,13 +220,13 @@ __device__ __forceinline__ void umma_setup(SmemU<C, LG>& S) {
     tc_fence_after();
     S.tmem = S.slots()[0];
 }
-template <class C, int LG>
-__device__ __forceinline__ void umma_teardown(SmemU<C, LG>& S) {
+template <class C, int LG, bool WIT>
+__device__ __forceinline__ void umma_teardown(SmemU<C, LG, WIT>& S) {
     tc_fence_before();
     __syncthreads();
     if ((threadIdx.x >> 5) == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(S.tmem), "n"(UL<C, LG>::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(S.tmem), "n"(UL<C, LG, WIT>::TMEM_COLS) : "memory");
     }
     if (S.slots()[1]) {
         if (threadIdx.x == 0) printf("pb200 block28u: tcgen05 completion never arrived (CTA %d)\n", (int)blockIdx.x);
@@ -232,10 +237,10 @@ __device__ __forceinline__ void umma_teardown(SmemU<C, LG>& S) {
 // ---- phase A with the stash in TMEM --------------------------------------------------------------------------------------
 // phase_product of block28.cuh for this thread's lane group; the Hi digits of a warp's first anti-diagonal wait for the merge in
 // TMEM columns [32 (warp / 4), + CH * 4) of the warp's own lane quadrant instead of the Q buffer.
-template <class C, int LG>
+template <class C, int LG, bool WIT = false>
 __device__ __noinline__ void phase_product_u(int4* smem_base, const int4* Y, int sqr, uint32_t tmem) {
     constexpr int G = C::G, BL = C::BL;
-    SmemU<C, LG> S(smem_base);
+    SmemU<C, LG, WIT> S(smem_base);
     const int lane = threadIdx.x & 31, cwarp = threadIdx.x >> 5, warp = cwarp % G;      // warp: role within the lane group
     const unsigned v_addr = (unsigned)__cvta_generic_to_shared(S.V) + lane * 16;
     const unsigned y_addr = sqr ? v_addr : (unsigned)__cvta_generic_to_shared(Y) + lane * 16;
@@ -373,9 +378,9 @@ __device__ __forceinline__ void fold4(const int* v, int& lob, int& ca) {
 }
 
 // all MMAs of issue slot s (HIGH: tiles from the bottom up, LOW: from the top down — longest k range first) into TMEM buffer s & 1
-template <class C, int LG, bool HIGH>
-__device__ __forceinline__ void umma_issue(const SmemU<C, LG>& S, int s) {
-    using U = UL<C, LG>;
+template <class C, int LG, bool WIT, bool HIGH>
+__device__ __forceinline__ void umma_issue(const SmemU<C, LG, WIT>& S, int s) {
+    using U = UL<C, LG, WIT>;
     const int t = HIGH ? U::NT_H - 1 - s : s;
     const int ph = U::p_hi(HIGH, t), ks0 = U::k_start(ph), nks = U::n_ksteps(ph);
     const uint32_t a_base = smem_u32(HIGH ? S.asb() : S.asc()), cm_base = smem_u32(S.base + (HIGH ? U::OFF_CMH : U::OFF_CML));
@@ -436,11 +441,12 @@ __device__ __forceinline__ void umma_fold(const int* va, const int* vb, unsigned
 }
 
 // q1 = T digits [L-1, 2L-1) as s8 rows; Q = hi(q1 mu); V = ripple(lo(T) - lo(Q Nt)).
-template <class C, int LG>
+// WIT: stops after the low-part sums are in F (the exact tail of the witness step, w_tail_u, takes over from there)
+template <class C, int LG, bool WIT = false>
 __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
-    using U = UL<C, LG>;
+    using U = UL<C, LG, WIT>;
     constexpr int G = C::G, BL = C::BL;
-    SmemU<C, LG> S(smem_base);
+    SmemU<C, LG, WIT> S(smem_base);
     S.tmem = tmem;
     const int lane = threadIdx.x & 31, cwarp = threadIdx.x >> 5, warp = cwarp % G;
     volatile uint32_t* dead = S.slots() + 1;
@@ -464,7 +470,7 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
     }
     fence_async_smem();
     __syncthreads();
-    if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, LG, true>(S, 0); umma_issue<C, LG, true>(S, 1); }
+    if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, LG, WIT, true>(S, 0); umma_issue<C, LG, WIT, true>(S, 1); }
     // T's upper halves are dead now: zero chunks in front of the q-hat rows
     for (int i = threadIdx.x; i < U::FRONT * U::ROWS; i += U::THREADS) *(int4*)(S.asc() + i * 16) = make_int4(0, 0, 0, 0);
     // per-thread addressing of the folds.  TMEM quadrant q = warp % 4 holds MMA rows 32 q ..: ciphertext group ge, shift j; the
@@ -495,7 +501,7 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
                 if (threadIdx.x == 0) {
                     mbar_wait(&S.bars()[2 + (s & 1)], 0u, dead);
                     tc_fence_after();
-                    umma_issue<C, LG, true>(S, s + 2);
+                    umma_issue<C, LG, WIT, true>(S, s + 2);
                 }
                 __syncwarp();
             }
@@ -504,7 +510,7 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();                    // q-hat rows complete
-        if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, LG, false>(S, 0); umma_issue<C, LG, false>(S, 1); }
+        if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, LG, WIT, false>(S, 0); umma_issue<C, LG, WIT, false>(S, 1); }
     }
     {
         // LOW, issue slot s is tile t = s: d_top = 40 (NT_L - s) - 1 - 5 ri;  F of ciphertext group ge is that group's B buffer
@@ -524,7 +530,7 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
                 if (threadIdx.x == 0) {
                     mbar_wait(&S.bars()[2 + (s & 1)], 1u, dead);
                     tc_fence_after();
-                    umma_issue<C, LG, false>(S, s + 2);
+                    umma_issue<C, LG, WIT, false>(S, s + 2);
                 }
                 __syncwarp();
             }
@@ -533,6 +539,7 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
         tc_fence_before();
         __syncthreads();                    // F complete, TMEM free for the next phase A's stash
     }
+    if (WIT) return;
     // V block = ripple(T block - F), carry into digit 0 of the next block (all MMAs are complete: the q1 rows over V are dead)
     {
         int a[C::CH * 4];
@@ -558,6 +565,142 @@ template <class C, int LG, bool SQR>
 __device__ __forceinline__ void mulmod_u(SmemU<C, LG>& S, const int4* Y) {
     phase_product_u<C, LG>((int4*)S.base, Y, SQR ? 1 : 0, S.tmem);
     phases_bc_umma<C, LG>((int4*)S.base, S.tmem);
+}
+
+// ---- witness step on the tcgen05 phases --------------------------------------------------------------------------------------
+// w_tail of block28.cuh on this engine's buffers: the raw digits of V' are T_lo - F, q-hat is decoded from the rows of phase C,
+// the carry / comparison flags live in B (F is dead once every thread holds its digits), the per-block hash sums in the gap
+// behind B, the flat canonical digits over T as before.  Same arithmetic, same records.
+template <class C>
+__device__ __noinline__ u64w w_tail_u(int4* smem_base, int4* next_dst, WStep out, int sh, int words_out,
+                                      double inv, const u64w* __restrict__ cpow) {
+    typedef UL<C, 1, true> U;
+    constexpr int G = C::G, BL = C::BL, L = C::L, MSK = (1 << W) - 1;
+    SmemU<C, 1, true> S(smem_base);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* est = (int*)(S.base + U::OFF_EST);
+    int* scr = (int*)S.B;
+    int* cfR[2] = {scr, scr + G * 32};
+    int* cfQ[2] = {scr + 2 * G * 32, scr + 3 * G * 32};
+    int* cmpf = scr + 4 * G * 32;
+    u64w* hsum = (u64w*)(S.base + 2 * U::VALB);
+    const int* ntu = (const int*)S.two_sh + warp * C::CH * 4;      // unsigned digits of Nt_w, this block (broadcast reads)
+    int rd[BL], qd[BL];
+    {
+        int a[C::CH * 4];
+        load_block<C>(a, blk_ptr<C>(S.T, warp, lane), 32);
+        const int* F = (const int*)S.B + (warp * BL) * 32 + lane;
+        const unsigned char* row = S.asc() + U::FRONT * U::CHB + lane * 16;
+#pragma unroll
+        for (int k = 0; k < BL; k++) {
+            const int j = warp * BL + k;
+            rd[k] = a[k] - F[k * 32];
+            const unsigned v = *(const unsigned*)(row + (j >> 2) * U::CHB + (j & 3) * 4);
+            qd[k] = ((int)(v << 24) >> 24) + (((int)(v << 16) >> 24) << 7) + (((int)(v << 8) >> 24) << 14) + (((int)v >> 24) << 21);
+        }
+    }
+    if (warp == G - 1) {       // k estimate: strict top two digits of V' (computed mod 2^(28L), |V'| < 2^beta)
+        int carry = 0, d_hi = 0, d_lo = 0;
+#pragma unroll
+        for (int k = 0; k < BL; k++) {
+            int t = rd[k] + carry + (1 << (W - 1));
+            carry = t >> W;
+            int d = (t & MSK) - (1 << (W - 1));
+            if (k == BL - 2) d_lo = d;
+            if (k == BL - 1) d_hi = d;
+        }
+        double vt = (double)d_hi * 268435456.0 + (double)d_lo;
+        int ke = (int)floor(vt * inv);
+        est[lane] = ke < -3 ? -3 : (ke > 3 ? 3 : ke);
+    }
+    __syncthreads();
+    int adj = est[lane];
+    int rnd = 0;
+    bool first = true;
+    for (;;) {
+        int cR = 0, cQ = (warp == 0) ? adj : 0;
+        if (first || adj) {
+#pragma unroll
+            for (int k = 0; k < BL; k++) { int t = rd[k] - adj * ntu[k] + cR; rd[k] = t & MSK; cR = t >> W; }
+#pragma unroll
+            for (int k = 0; k < BL; k++) { int t = qd[k] + cQ; qd[k] = t & MSK; cQ = t >> W; }
+        } else cQ = 0;
+        first = false;
+        for (;;) {
+            if (warp == G - 1) { cR = 0; cQ = 0; }
+            cfR[rnd][warp * 32 + lane] = cR; cfQ[rnd][warp * 32 + lane] = cQ;
+            if (!__syncthreads_or((cR | cQ) != 0)) break;
+            const int iR = warp ? cfR[rnd][(warp - 1) * 32 + lane] : 0, iQ = warp ? cfQ[rnd][(warp - 1) * 32 + lane] : 0;
+            cR = add_carry_block<BL>(rd, iR);
+            cQ = add_carry_block<BL>(qd, iQ);
+            rnd ^= 1;
+        }
+        int cmp = 0;
+#pragma unroll
+        for (int k = 0; k < BL; k++) if (rd[k] != ntu[k]) cmp = rd[k] > ntu[k] ? 1 : -1;
+        if (warp == G - 1 && rd[BL - 1] >= (1 << (W - 1))) cmp = -2;
+        cmpf[warp * 32 + lane] = cmp;
+        __syncthreads();
+        int c = 0;
+#pragma unroll
+        for (int b = G - 1; b >= 0; b--) { const int f = cmpf[b * 32 + lane]; if (c == 0) c = f; }
+        adj = c == -2 ? -1 : (c >= 0 ? 1 : 0);
+        if (!__syncthreads_or(adj != 0)) break;
+        rnd ^= 1;
+    }
+    int* Rf = (int*)S.T;
+    int* Qf = Rf + L * 32;
+#pragma unroll
+    for (int k = 0; k < BL; k++) { Rf[(warp * BL + k) * 32 + lane] = rd[k]; Qf[(warp * BL + k) * 32 + lane] = qd[k]; }
+    __syncthreads();
+    u64w h = 0;
+    const int wpw = (words_out + G - 1) / G;
+    for (int i = 0; i < wpw; i++) {
+        const int j = warp * wpw + i;
+        if (j < words_out) {
+            const u64w wq = extract64<L>(Qf, 64 * j, lane), wr = extract64<L>(Rf, 64 * j + sh, lane);
+            h += wq * cpow[j] + wr * cpow[words_out + j];
+            if (out.rec) { out.rec[j] = wq; out.rec[words_out + j] = wr; }
+            if (out.rem_out) out.rem_out[j] = wr;
+            if (out.q_out) out.q_out[j] = wq;
+        }
+    }
+    hsum[warp * 32 + lane] = h;
+    int carry = 0;
+    if (next_dst) {            // strict digits of R >> s (= rem 2^s), this block
+        const int s = sh >> 1, pd = s / W, off = s - pd * W;
+        int a[C::CH * 4];
+#pragma unroll
+        for (int k = 0; k < BL; k++) {
+            const int p = warp * BL + k + pd;
+            const unsigned lo = p < L ? (unsigned)Rf[p * 32 + lane] : 0u, hi = p + 1 < L ? (unsigned)Rf[(p + 1) * 32 + lane] : 0u;
+            const int x = (int)(((lo >> off) | (off ? hi << (W - off) : 0u)) & MSK);
+            const int t = x + carry + (1 << (W - 1));
+            carry = t >> W;
+            a[k] = (t & MSK) - (1 << (W - 1));
+        }
+#pragma unroll
+        for (int k = BL; k < C::CH * 4; k++) a[k] = 0;
+        store_block<C>(blk_ptr<C>(next_dst, warp, lane), a);
+    }
+    __syncthreads();
+    if (next_dst && warp + 1 < G) *(int*)blk_ptr<C>(next_dst, warp + 1, lane) += carry;
+    u64w H = 0;
+    if (warp == 0) {
+#pragma unroll
+        for (int b = 0; b < G; b++) H += hsum[b * 32 + lane];
+    }
+    __syncthreads();
+    return H;
+}
+
+// one witnessed mul_mod on the tcgen05 phases; same contract as mulmod_w (block28.cuh): V is preserved, the hash is valid in warp 0
+template <class C>
+__device__ __forceinline__ u64w mulmod_wu(int4* smem_base, uint32_t tmem, const int4* Y, int sqr, int4* next_dst, WStep out,
+                                          int sh, int words_out, double inv, const u64w* cpow) {
+    phase_product_u<C, 1, true>(smem_base, Y, sqr, tmem);
+    phases_bc_umma<C, 1, true>(smem_base, tmem);
+    return w_tail_u<C>(smem_base, next_dst, out, sh, words_out, inv, cpow);
 }
 
 // host: CM[u][r][b] = K7c[z0 - (8u + r + b)] (zero outside the constant)
