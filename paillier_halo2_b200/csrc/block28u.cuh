@@ -49,13 +49,20 @@ struct UL {
     static constexpr int KOFF = 16 * FRONT;
     static constexpr int ACH = FRONT + KCH + BACK;
     static constexpr int A_BYTES = ACH * CHB;
-    static constexpr int TCOLS = 160, RCOLS = 20;
+    // a tile is G ranges per ciphertext (one per warp of the lane group); a range is RD digits: 5 with 8 warps, 3 with 16
+    static constexpr int RD = G == 16 ? 3 : 5, RCOLS = 4 * RD, TCOLS = G * RCOLS, DT = TCOLS / 4;
     static constexpr int TN = ((TCOLS - SHIFTC + 4) + 15) / 16 * 16;      // MMA N: the columns the unshifted rows must see
     static constexpr int NWARPS = C::G * LG, THREADS = 32 * NWARPS;
-    static constexpr int RPS = 8 / NSH;                        // ranges per (ciphertext group, shift) = warps per TMEM quadrant
+    static constexpr int RPS = G / NSH;                        // ranges per (ciphertext group, shift) = warps per TMEM quadrant
     static constexpr int P_BASE_H = 4 * (L - 2);               // phase B keeps two guard digits below q-hat
     static constexpr int NT_H = (4 * (L + 2) + TCOLS - 1) / TCOLS, NT_L = (4 * L + TCOLS - 1) / TCOLS;
-    static constexpr int TMEM_COLS = 256 * LG;
+    static constexpr int TMEM_COLS = 2 * TN <= 256 ? 256 : 512;
+    // mbarrier completions of buffer b per phase: "full" once per tile, "empty" once per tile that is followed by another tile in
+    // the same buffer; over one multiplication each must be even so that the wait parities are compile-time constants
+    __host__ __device__ static constexpr int n_full(bool high, int b) { return ((high ? NT_H : NT_L) + 1 - b) / 2; }
+    __host__ __device__ static constexpr int n_empty(bool high, int b) { return ((high ? NT_H : NT_L) - 2 + 1 - b) / 2 > 0 ? ((high ? NT_H : NT_L) - 2 + 1 - b) / 2 : 0; }
+    __host__ __device__ static constexpr unsigned par_full(bool high, int s) { return (unsigned)(((high ? 0 : n_full(true, s & 1)) + (s >> 1)) & 1); }
+    __host__ __device__ static constexpr unsigned par_empty(bool high, int s) { return (unsigned)(((high ? 0 : n_empty(true, s & 1)) + (s >> 1)) & 1); }
     __host__ __device__ static constexpr int p_top(bool high, int t) { return (high ? P_BASE_H + NT_H * TCOLS : NT_L * TCOLS) - 1 - TCOLS * t; }
     __host__ __device__ static constexpr int p_hi(bool high, int t) { return p_top(high, t) - SHIFTC; }
     // k range of a tile in the coordinates of the unshifted rows: the band of its TN columns, extended below zero for the shifted rows
@@ -84,7 +91,8 @@ struct UL {
     // byte offsets in dynamic shared memory
     static constexpr int VALB = C::VAL4 * 16;
     static constexpr int ASB_OFF = WIT ? VALB : 0;                                  // where the q1 rows start
-    static constexpr int GAP = WIT ? ((A_BYTES > VALB ? A_BYTES - VALB : 0) + 127) / 128 * 128 : 0;
+    // the gap also holds the witness tail's per-block hash sums (G * 32 u64)
+    static constexpr int GAP = WIT ? ((A_BYTES - VALB > G * 32 * 8 ? A_BYTES - VALB : G * 32 * 8) + 127) / 128 * 128 : 0;
     static constexpr int OFF_T = 2 * LG * VALB + GAP, OFF_ASC = OFF_T + LG * VALB;   // T low halves of all groups, then the high halves
     static constexpr int T_HI_JUMP = (LG - 1) * VALB;                                // block d >= G of a group lies this much further
     static constexpr int END_ASC = OFF_ASC + A_BYTES;
@@ -95,10 +103,14 @@ struct UL {
     static constexpr int OFF_EST = OFF_BAR + 64;               // witness engine: one int per lane (k estimate)
     static constexpr size_t SMEM_BYTES = (size_t)OFF_BAR + 64 + (WIT ? 128 : 0);
     static constexpr int CTAS_PER_SM = (int)((233472 / (SMEM_BYTES + 1024)) < (512 / THREADS) ? (233472 / (SMEM_BYTES + 1024)) : (512 / THREADS));
-    // compiled for configurations with whole k-steps per row, four tiles per phase (every mbarrier completes an even number of times
-    // per multiplication, so the wait parities are compile-time constants), the q1 rows inside V | B and 8 warps per lane group
-    static constexpr bool SUPPORTED = (K7 % 32 == 0) && (NT_H == 4) && (NT_L == 4) && (WIT ? (LG == 1 && A_BYTES <= VALB + GAP && GAP >= G * 32 * 8) : (A_BYTES <= 2 * LG * VALB)) && (G == 8) &&
-                                      (Z0_H % 8 == 7) && (Z0_L % 8 == 7) && (P_BASE_H % 8 == 0) && (TN <= 128 * LG + 32 * (LG - 1)) &&
+    // compiled for configurations with whole k-steps per row, tile counts for which every mbarrier completes an even number of times
+    // per multiplication (the wait parities are compile-time constants), the q1 rows inside V | B, and 8 or 16 warps per lane group
+    static constexpr bool SUPPORTED = (K7 % 32 == 0) && (NT_H >= 2) && (NT_L >= 2) &&
+                                      ((n_full(true, 0) + n_full(false, 0)) % 2 == 0) && ((n_full(true, 1) + n_full(false, 1)) % 2 == 0) &&
+                                      ((n_empty(true, 0) + n_empty(false, 0)) % 2 == 0) && ((n_empty(true, 1) + n_empty(false, 1)) % 2 == 0) &&
+                                      (WIT ? (LG == 1 && A_BYTES <= VALB + GAP && GAP >= G * 32 * 8) : (A_BYTES <= 2 * LG * VALB)) &&
+                                      ((G == 8) || (G == 16 && LG == 1)) && (TCOLS % 16 == 0) && (RCOLS + 4 <= 24) &&
+                                      (Z0_H % 8 == 7) && (Z0_L % 8 == 7) && (P_BASE_H % 8 == 0) && (TN <= 256) &&
                                       (2 * TN <= TMEM_COLS) && CTAS_PER_SM >= 1 && SMEM_BYTES <= 232448;
 };
 
@@ -402,27 +414,27 @@ __device__ __forceinline__ void umma_issue(const SmemU<C, LG, WIT>& S, int s) {
 // fold of one range of a tile: 5 digits (+ the digit below for its carry).  HIGH: packed q-hat words into the rows of phase C;
 // LOW: lo(q-hat Nt) digit sums into the flat array F[digit][lane] (the group's B buffer), subtracted from T by the ripple pass.
 // dst: the address of the range's top digit (HIGH: word 0 of its 16-byte chunk in this row; LOW: its F entry)
-template <class C, int CHB, bool HIGH>
-__device__ __forceinline__ void umma_fold(const int* va, const int* vb, unsigned char* dst, int d_top, int r /* HIGH: (d_top - 2) & 3, warp-uniform */) {
+template <class C, int CHB, int RD, bool HIGH>
+__device__ __forceinline__ void umma_fold(const int* v /* 4 (RD + 1) columns, top digit first */, unsigned char* dst, int d_top,
+                                          int r /* HIGH: (d_top - 2) & 3, warp-uniform */) {
     constexpr int L = C::L;
-    int lob[6], ca[6];
+    int lob[RD + 1], ca[RD + 1];
 #pragma unroll
-    for (int e = 0; e < 4; e++) fold4(va + 4 * e, lob[e], ca[e]);
-    fold4(vb, lob[4], ca[4]);
-    fold4(vb + 4, lob[5], ca[5]);
+    for (int e = 0; e <= RD; e++) fold4(v + 4 * e, lob[e], ca[e]);
     if (HIGH) {
-        // q-hat digit jj - 2 = LO[jj] + CA[jj], not rippled (block28.cuh, qhat_to_bytes); the two guard digits only feed a carry
+        // q-hat digit jj - 2 = LO[jj] + CA[jj], not rippled (block28.cuh, qhat_to_bytes); the two guard digits jj = 0, 1 (the last two
+        // digits of the phase's bottom range, d_top == RD - 1) only feed a carry into q-hat digit 0
         int carry_g = 0;
-        if (d_top == 4) { const int t1 = lob[3] + ca[4] - (1 << (W - 1)); carry_g = (t1 - sgxt28(t1)) >> W; }
-        unsigned w[5];
+        if (d_top == RD - 1) { const int t1 = lob[RD - 2] + ca[RD - 1] - (1 << (W - 1)); carry_g = (t1 - sgxt28(t1)) >> W; }
+        unsigned w[RD];
 #pragma unroll
-        for (int e = 0; e < 5; e++)
-            w[e] = split7_pack_biased((unsigned)(lob[e] + ca[e + 1] + (int)(SPLIT_BIAS - (1u << (W - 1))) + (e == 2 ? carry_g : 0)));
+        for (int e = 0; e < RD; e++)
+            w[e] = split7_pack_biased((unsigned)(lob[e] + ca[e + 1] + (int)(SPLIT_BIAS - (1u << (W - 1))) + (e == RD - 3 ? carry_g : 0)));
         const int qd0 = d_top - 2;
         auto put = [&](auto RC) {
             constexpr int R = decltype(RC)::value;
 #pragma unroll
-            for (int e = 0; e < 5; e++) {
+            for (int e = 0; e < RD; e++) {
                 const int wd = R - e, ch = wd >= 0 ? wd / 4 : -((3 - wd) / 4), word = wd - 4 * ch;
                 if ((unsigned)(qd0 - e) < (unsigned)L) *(unsigned*)(dst + ch * CHB + word * 4) = w[e];
             }
@@ -435,9 +447,17 @@ __device__ __forceinline__ void umma_fold(const int* va, const int* vb, unsigned
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < 5; e++)
+        for (int e = 0; e < RD; e++)
             if (d_top - e < L) *(int*)(dst - e * 128) = lob[e] + ca[e + 1] - (1 << (W - 1));
     }
+}
+
+// this warp's 4 (RD + 1) accumulator columns of a TMEM buffer
+template <int RD>
+__device__ __forceinline__ void umma_load(uint32_t ta, int* v) {
+    tmem_ld16(ta, v);
+    if (RD == 5) tmem_ld8(ta + 16, v + 16);
+    tmem_wait_ld();
 }
 
 // q1 = T digits [L-1, 2L-1) as s8 rows; Q = hi(q1 mu); V = ripple(lo(T) - lo(Q Nt)).
@@ -483,29 +503,27 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
     // then folds its own columns.  Every mbarrier completes an even number of times per multiplication (four tiles per phase), so
     // all wait parities are constants.
     {
-        // HIGH, issue slot s is tile t = NT_H - 1 - s: top digit of this warp's range d_top = 40 (s + 1) - 1 - 5 ri
-        const int d_top0 = 39 - 5 * ri;
+        // HIGH, issue slot s is tile t = NT_H - 1 - s: top digit of this warp's range d_top = DT (s + 1) - 1 - RD ri
+        const int d_top0 = U::DT - 1 - U::RD * ri;
         const int r = (d_top0 - 2) & 3;
         unsigned char* dst0 = S.asc() + U::FRONT * U::CHB + (ge * 32 + lane) * 16 + (((d_top0 - 2) >> 2) * U::CHB);      // (d_top0 - 2) >> 2 may be -1: floor
 #pragma unroll
         for (int s = 0; s < U::NT_H; s++) {
-            mbar_wait(&S.bars()[s & 1], (uint32_t)((s >> 1) & 1), dead);
+            mbar_wait(&S.bars()[s & 1], U::par_full(true, s), dead);
             tc_fence_after();
-            int va[16], vb[8];
-            tmem_ld16(ta0 + (uint32_t)((s & 1) * U::TN), va);
-            tmem_ld8(ta0 + (uint32_t)((s & 1) * U::TN) + 16, vb);
-            tmem_wait_ld();
+            int va[4 * (U::RD + 1)];
+            umma_load<U::RD>(ta0 + (uint32_t)((s & 1) * U::TN), va);
             if (s + 2 < U::NT_H) {
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&S.bars()[2 + (s & 1)]);
                 if (threadIdx.x == 0) {
-                    mbar_wait(&S.bars()[2 + (s & 1)], 0u, dead);
+                    mbar_wait(&S.bars()[2 + (s & 1)], U::par_empty(true, s), dead);
                     tc_fence_after();
                     umma_issue<C, LG, WIT, true>(S, s + 2);
                 }
                 __syncwarp();
             }
-            umma_fold<C, U::CHB, true>(va, vb, dst0 + s * (10 * U::CHB), d_top0 + 40 * s, r);
+            umma_fold<C, U::CHB, U::RD, true>(va, dst0 + s * ((U::DT / 4) * U::CHB), d_top0 + U::DT * s, r);
         }
         fence_async_smem();
         tc_fence_before();
@@ -513,28 +531,26 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
         if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, LG, WIT, false>(S, 0); umma_issue<C, LG, WIT, false>(S, 1); }
     }
     {
-        // LOW, issue slot s is tile t = s: d_top = 40 (NT_L - s) - 1 - 5 ri;  F of ciphertext group ge is that group's B buffer
-        const int d_top0 = 40 * U::NT_L - 1 - 5 * ri;
+        // LOW, issue slot s is tile t = s: d_top = DT (NT_L - s) - 1 - RD ri;  F of ciphertext group ge is that group's B buffer
+        const int d_top0 = U::DT * U::NT_L - 1 - U::RD * ri;
         unsigned char* dst0 = S.base + (2 * ge + 1) * U::VALB + lane * 4 + d_top0 * 128;
 #pragma unroll
         for (int s = 0; s < U::NT_L; s++) {
-            mbar_wait(&S.bars()[s & 1], (uint32_t)((U::NT_H / 2 + (s >> 1)) & 1), dead);
+            mbar_wait(&S.bars()[s & 1], U::par_full(false, s), dead);
             tc_fence_after();
-            int va[16], vb[8];
-            tmem_ld16(ta0 + (uint32_t)((s & 1) * U::TN), va);
-            tmem_ld8(ta0 + (uint32_t)((s & 1) * U::TN) + 16, vb);
-            tmem_wait_ld();
+            int va[4 * (U::RD + 1)];
+            umma_load<U::RD>(ta0 + (uint32_t)((s & 1) * U::TN), va);
             if (s + 2 < U::NT_L) {
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&S.bars()[2 + (s & 1)]);
                 if (threadIdx.x == 0) {
-                    mbar_wait(&S.bars()[2 + (s & 1)], 1u, dead);
+                    mbar_wait(&S.bars()[2 + (s & 1)], U::par_empty(false, s), dead);
                     tc_fence_after();
                     umma_issue<C, LG, WIT, false>(S, s + 2);
                 }
                 __syncwarp();
             }
-            umma_fold<C, U::CHB, false>(va, vb, dst0 - s * (40 * 128), d_top0 - 40 * s, 0);
+            umma_fold<C, U::CHB, U::RD, false>(va, dst0 - s * (U::DT * 128), d_top0 - U::DT * s, 0);
         }
         tc_fence_before();
         __syncthreads();                    // F complete, TMEM free for the next phase A's stash

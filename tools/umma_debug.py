@@ -77,6 +77,8 @@ def main():
         for eng in (3, 4, 5):
             t = np.zeros((2 * G, CH, 32, 4), dtype=np.int32)
             rc = lib.pb200_debug_mulmod(key.handle, eng, v.ctypes.data, y.ctypes.data if y is not None else None, 1, None, t.ctypes.data, None)
+            if rc == _lib.PB200_ERR_UNSUPPORTED:       # this key size has no such variant
+                continue
             if rc:
                 res[f"{mode}_phaseA_rc_eng{eng}"] = rc
                 bad = True
@@ -127,6 +129,8 @@ def main():
             key.set_engine(eng)
             cs[eng] = key.encrypt_words(m, r)
         except Exception as e:  # noqa: BLE001
+            if getattr(e, "status", None) == _lib.PB200_ERR_UNSUPPORTED:
+                continue
             res[f"encrypt_eng{eng}_error"] = str(e)[:200]
             bad = True
     for other in (4, 5):
