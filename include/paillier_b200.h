@@ -110,6 +110,13 @@ int pb200_key_take_flags(pb200_key* key, uint32_t* flags_out);
  * v_out receives the lazy result and qhat_rows (nullable, 32 * G * BL words) the quotient estimate's packed s8 digits.  The
  * engines are specified to agree digit for digit; the parity tests check exactly that. */
 int pb200_key_shape(const pb200_key* key, int* g_out, int* bl_out);
+/* layout constants of the block28u variant for values of G blocks x BL digits with `lane_groups` (1 or 2) groups of 32 ciphertexts
+ * per CTA (witness != 0: the witness engine's layout): out20 = {supported, digits per range, columns per tile, MMA N, tiles of
+ * phase B, tiles of phase C, zero chunks in front, behind, k offset, chunk bytes, operand-row bytes, z0 of the two Toeplitz tables,
+ * their entry counts, shared-memory bytes, CTAs per SM, TMEM columns, gap bytes, first column of phase B}.  Host only (no device
+ * needed): tests/test_umma_layout.py checks its CPU model of the tcgen05 data path against them.  PB200_ERR_UNSUPPORTED for shapes
+ * that are not compiled. */
+int pb200_umma_layout(int g, int bl, int lane_groups, int witness, int32_t* out20);
 int pb200_debug_mulmod(pb200_key* key, int engine, const int32_t* v_in, const int32_t* y_in, int reps, int32_t* v_out, int32_t* t_out,
                        uint32_t* qhat_rows);
 /* `reps` lazy squarings on each of `ctas` CTAs (engine 3, 4 or 5, |n| = 2048 configuration); cycles_out[3 cta + {0, 1, 2}] = SM cycles

@@ -58,6 +58,7 @@ SYMBOLS = {
     "pb200_key_n2": (C.c_int, [C.c_void_p, u64p]),
     "pb200_key_engine": (C.c_char_p, [C.c_void_p]),
     "pb200_key_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
+    "pb200_umma_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pb200_key_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pb200_debug_mulmod_cycles": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pb200_debug_mulmod": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

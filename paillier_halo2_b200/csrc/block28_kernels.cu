@@ -1336,6 +1336,31 @@ typedef Cfg<16, 19> Cfg4096;   // L = 304: n^2 up to 8486 bits (|n| <= 4096)
 template <class C>
 static bool covers(uint32_t n_bits) { return 2 * (size_t)n_bits <= (size_t)C::KN - 2 && n_bits % 8 == 0; }
 
+// layout constants of a block28u variant (host only, no device needed): the CPU model of the tcgen05 data path in
+// tests/test_umma_layout.py checks its own derivation against these
+template <class C, int LG, bool WIT>
+static void ul_fill(int* out) {
+    typedef UL<C, LG, WIT> U;
+    const int v[20] = {(int)U::SUPPORTED, U::RD, U::TCOLS, U::TN, U::NT_H, U::NT_L, U::FRONT, U::BACK, U::KOFF, U::CHB, U::A_BYTES, U::Z0_H, U::Z0_L,
+                       U::NCM_H, U::NCM_L, (int)U::SMEM_BYTES, U::CTAS_PER_SM, U::TMEM_COLS, U::GAP, U::P_BASE_H};
+    for (int i = 0; i < 20; i++) out[i] = v[i];
+}
+template <class C>
+static bool ul_cfg(int lg, int wit, int* out) {
+    if (lg == 1 && !wit) ul_fill<C, 1, false>(out);
+    else if (lg == 1 && wit) ul_fill<C, 1, true>(out);
+    else if (lg == 2 && !wit) ul_fill<C, 2, false>(out);
+    else return false;
+    return true;
+}
+bool block28_umma_layout(int G, int BL, int lg, int wit, int* out) {
+    if (G == 4 && BL == 19) return ul_cfg<Cfg1024>(lg, wit, out);
+    if (G == 8 && BL == 19) return ul_cfg<Cfg2048>(lg, wit, out);
+    if (G == 16 && BL == 14) return ul_cfg<Cfg3072>(lg, wit, out);
+    if (G == 16 && BL == 19) return ul_cfg<Cfg4096>(lg, wit, out);
+    return false;
+}
+
 Block28Key* block28_create(const BigInt& n, const BigInt& g, uint32_t n_bits, int device, cudaStream_t st,
                            std::string* why, cudaError_t* cuda_err) {
     *cuda_err = cudaSuccess;

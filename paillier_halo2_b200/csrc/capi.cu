@@ -289,6 +289,10 @@ int pb200_debug_mulmod_cycles(pb200_key* k, int engine, const int32_t* v_in, int
     CU(block28_debug_time(k->fast, engine - 2, v_in, ctas, reps, stagger_cycles, (long long*)cycles_out, k->stream));
     return PB200_OK;
 } PB200_CATCH
+int pb200_umma_layout(int g, int bl, int lane_groups, int witness, int32_t* out20) try {
+    if (!out20) return PB200_ERR_INVALID_ARG;
+    return block28_umma_layout(g, bl, lane_groups, witness, out20) ? PB200_OK : PB200_ERR_UNSUPPORTED;
+} PB200_CATCH
 int pb200_key_shape(const pb200_key* k, int* g_out, int* bl_out) {
     if (!k || !g_out || !bl_out) return PB200_ERR_INVALID_ARG;
     if (!k->fast) return PB200_ERR_UNSUPPORTED;

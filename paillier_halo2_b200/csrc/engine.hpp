@@ -75,6 +75,8 @@ cudaError_t block28_add(Block28Key*, const u64* d_c1, const u64* d_c2, int c_wor
 cudaError_t block28_debug_mulmod(Block28Key*, int eng, const int* h_v, const int* h_y, int reps, int* h_vout, int* h_t, unsigned* h_rows,
                                  cudaStream_t st);
 void block28_shape(const Block28Key*, int* G, int* BL);
+// 20 layout constants of the block28u variant <G, BL> with lg lane groups per CTA (wit: witness layout); false for unknown shapes
+bool block28_umma_layout(int G, int BL, int lg, int wit, int* out);
 // diagnostic: cycles of phase A / phases B + C / the whole loop per CTA over `reps` squarings on `ctas` CTAs (|n| = 2048 configuration)
 cudaError_t block28_debug_time(Block28Key*, int eng, const int* h_v, int ctas, int reps, int stagger, long long* h_cyc, cudaStream_t st);
 

@@ -80,6 +80,7 @@ extern "C" {
     pub fn pb200_key_n2(key: *const pb200_key, n2_out: *mut u64) -> c_int;
     pub fn pb200_key_engine(key: *const pb200_key) -> *const c_char;
     pub fn pb200_key_set_engine(key: *mut pb200_key, engine: c_int) -> c_int;
+    pub fn pb200_umma_layout(g: c_int, bl: c_int, lane_groups: c_int, witness: c_int, out20: *mut i32) -> c_int;
     pub fn pb200_key_shape(key: *const pb200_key, g_out: *mut c_int, bl_out: *mut c_int) -> c_int;
     pub fn pb200_debug_mulmod_cycles(key: *mut pb200_key, engine: c_int, v_in: *const i32, ctas: c_int, reps: c_int, stagger_cycles: c_int, cycles_out: *mut i64) -> c_int;
     pub fn pb200_debug_mulmod(key: *mut pb200_key, engine: c_int, v_in: *const i32, y_in: *const i32, reps: c_int, v_out: *mut i32, t_out: *mut i32, qhat_rows: *mut u32) -> c_int;
