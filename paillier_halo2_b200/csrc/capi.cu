@@ -285,6 +285,7 @@ int pb200_debug_mulmod_cycles(pb200_key* k, int engine, const int32_t* v_in, int
     if (!k->fast) return PB200_ERR_UNSUPPORTED;
     if (engine == 4 && !block28_has_umma(k->fast)) return PB200_ERR_UNSUPPORTED;
     if (engine == 5 && !block28_has_umma2(k->fast)) return PB200_ERR_UNSUPPORTED;
+    { int g = 0, bl = 0; block28_shape(k->fast, &g, &bl); if (g != 8) return PB200_ERR_UNSUPPORTED; }      // the |n| = 2048 configuration only
     USE_DEVICE(k);
     CU(block28_debug_time(k->fast, engine - 2, v_in, ctas, reps, stagger_cycles, (long long*)cycles_out, k->stream));
     return PB200_OK;
