@@ -19,12 +19,14 @@
 // j) of any (tile, k-step) is entry u0 + g + 2j of one per-key table CM[u][r][b] = Rev[8u + r + b] (descriptor strides 128 B along
 // N, 256 B along K) — csrc/microbench/umma_toeplitz.cu measured and verified this form.
 //
-// Tiles: 160 output columns (40 digits) each, 8 ranges of 20 columns per ciphertext; a warp folds one range from its TMEM quadrant
-// and reads the 4 columns below its range itself for the incoming carry, so tiles and ranges are independent of each other.
+// Tiles: G ranges per ciphertext, one per warp of its lane group — 8 ranges of 5 digits (160 columns) with 8 warps, 16 ranges of 3
+// digits (192 columns) with 16; a warp folds one range from its TMEM quadrant and reads the 4 columns below its range itself for
+// the incoming carry, so tiles and ranges are independent of each other.
 // Two TMEM buffers per CTA; a warp that has read its columns out arrives on the buffer's "empty" mbarrier, thread 0 waits for the
 // arrivals and issues the MMAs of the tile after next — no CTA barrier between tiles.
 //
-// Shared memory, LG = 1 (112 KB, two CTAs per SM): V | B | T(2L) | tail of the q-hat rows | constants | CM(mu) | CM(Nt).
+// Shared memory, LG = 1 (|n| = 2048: 111 KB, two CTAs per SM; 3072 / 4096: 166 / 211 KB, one): V | B | T(2L) | tail of the q-hat
+// rows | constants | CM(mu) | CM(Nt).
 // LG = 2 (190 KB, one CTA of 16 warps per SM): V0 B0 V1 B1 | T0lo T1lo T0hi T1hi | tail | constants | CM | CM.  The q1 rows overlay
 // V, B (dead after phase A), the q-hat rows overlay the upper halves of T (dead once q1 has been cut out); phase A's stash of Hi
 // digits, which block28t keeps in the Q buffer, lives in TMEM columns (tcgen05.st / ld); the low-part sums of phase C go to a flat
@@ -359,7 +361,6 @@ static __constant__ int c_opq[8] = {0, 1, 2, 3, 7, 9, 14, 28};
 #define OPQ_2 (c_opq[2])
 #define OPQ_3 (c_opq[3])
 #define OPQ_7 (c_opq[4])
-#define OPQ_9 (c_opq[5])
 #define OPQ_14 (c_opq[6])
 #define OPQ_28 (c_opq[7])
 __device__ __forceinline__ unsigned lop3_sel(unsigned a, unsigned b, unsigned m) {          // (a & ~m) | (b & m)
