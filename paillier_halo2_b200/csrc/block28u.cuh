@@ -163,6 +163,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(smem_u32(bar)) : "memory");
 }
+// one lane of a fully active warp (elect.sync): code under it is single-threaded to ptxas, which then issues tcgen05.mma without the
+// per-thread serialisation loop it wraps around a warp-level instruction in merely divergent code
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -491,7 +498,10 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
     }
     fence_async_smem();
     __syncthreads();
-    if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, LG, WIT, true>(S, 0); umma_issue<C, LG, WIT, true>(S, 1); }
+    if (cwarp == 0) {
+        if (elect_one()) { tc_fence_after(); umma_issue<C, LG, WIT, true>(S, 0); umma_issue<C, LG, WIT, true>(S, 1); }
+        __syncwarp();
+    }
     // T's upper halves are dead now: zero chunks in front of the q-hat rows
     for (int i = threadIdx.x; i < U::FRONT * U::ROWS; i += U::THREADS) *(int4*)(S.asc() + i * 16) = make_int4(0, 0, 0, 0);
     // per-thread addressing of the folds.  TMEM quadrant q = warp % 4 holds MMA rows 32 q ..: ciphertext group ge, shift j; the
@@ -517,19 +527,25 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
             if (s + 2 < U::NT_H) {
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&S.bars()[2 + (s & 1)]);
-                if (threadIdx.x == 0) {
-                    mbar_wait(&S.bars()[2 + (s & 1)], U::par_empty(true, s), dead);
-                    tc_fence_after();
-                    umma_issue<C, LG, WIT, true>(S, s + 2);
-                }
                 __syncwarp();
+                if (cwarp == 0) {
+                    if (elect_one()) {
+                        mbar_wait(&S.bars()[2 + (s & 1)], U::par_empty(true, s), dead);
+                        tc_fence_after();
+                        umma_issue<C, LG, WIT, true>(S, s + 2);
+                    }
+                    __syncwarp();
+                }
             }
             umma_fold<C, U::CHB, U::RD, true>(va, dst0 + s * ((U::DT / 4) * U::CHB), d_top0 + U::DT * s, r);
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();                    // q-hat rows complete
-        if (threadIdx.x == 0) { tc_fence_after(); umma_issue<C, LG, WIT, false>(S, 0); umma_issue<C, LG, WIT, false>(S, 1); }
+        if (cwarp == 0) {
+            if (elect_one()) { tc_fence_after(); umma_issue<C, LG, WIT, false>(S, 0); umma_issue<C, LG, WIT, false>(S, 1); }
+            __syncwarp();
+        }
     }
     {
         // LOW, issue slot s is tile t = s: d_top = DT (NT_L - s) - 1 - RD ri;  F of ciphertext group ge is that group's B buffer
@@ -544,12 +560,15 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
             if (s + 2 < U::NT_L) {
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&S.bars()[2 + (s & 1)]);
-                if (threadIdx.x == 0) {
-                    mbar_wait(&S.bars()[2 + (s & 1)], U::par_empty(false, s), dead);
-                    tc_fence_after();
-                    umma_issue<C, LG, WIT, false>(S, s + 2);
-                }
                 __syncwarp();
+                if (cwarp == 0) {
+                    if (elect_one()) {
+                        mbar_wait(&S.bars()[2 + (s & 1)], U::par_empty(false, s), dead);
+                        tc_fence_after();
+                        umma_issue<C, LG, WIT, false>(S, s + 2);
+                    }
+                    __syncwarp();
+                }
             }
             umma_fold<C, U::CHB, U::RD, false>(va, dst0 - s * (U::DT * 128), d_top0 - U::DT * s, 0);
         }
