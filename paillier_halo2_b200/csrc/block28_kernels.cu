@@ -163,6 +163,7 @@ template <class C> struct View<C, 2> {            // block28u, one lane group pe
     static constexpr int PER_SM = UL<C, 1>::CTAS_PER_SM;
     static constexpr int LG = 1, THREADS = C::THREADS;
 };
+template <class C> struct View<C, 4> : View<C, 2> {};      // block28u as the tally runs it: MMAs issued by thread 0 (see phases_bc_umma)
 template <class C> struct View<C, 3> {            // block28u, two lane groups (64 ciphertexts) per CTA
     typedef SmemU<C, 2> type;
     static constexpr size_t BYTES = UL<C, 2>::SMEM_BYTES;
@@ -171,7 +172,7 @@ template <class C> struct View<C, 3> {            // block28u, two lane groups (
 };
 template <class C, bool SQR, int ENG, class SV>
 __device__ __forceinline__ void mm(SV& S, const int4* Y, int role, int lane) {
-    if constexpr (ENG >= 2) mulmod_u<C, View<C, ENG>::LG, SQR>(S, Y);
+    if constexpr (ENG >= 2) mulmod_u<C, View<C, ENG>::LG, SQR, ENG != 4>(S, Y);
     else mulmod<C, SQR, ENG == 1>(S, Y, role, lane);
 }
 // per-key constants into shared memory (+ TMEM and mbarriers for block28u)
@@ -180,7 +181,7 @@ __device__ __forceinline__ void cta_begin(SV& S, int4* smem_base, const B28Dev& 
     if constexpr (ENG >= 2) {
         typedef UL<C, View<C, ENG>::LG> U;
         int4* dst = (int4*)((unsigned char*)smem_base + U::OFF_CONST);
-        const int4* src = ENG == 2 ? K.uconsts : K.uconsts2;
+        const int4* src = ENG == 3 ? K.uconsts2 : K.uconsts;
         for (int i = threadIdx.x; i < U::KEY_BYTES / 16; i += U::THREADS) dst[i] = src[i];
         umma_setup<C, View<C, ENG>::LG>(S);
     } else load_consts<C>(smem_base, K);
@@ -1056,7 +1057,7 @@ static Block28Key* create_cfg(const BigInt& n, const BigInt& g, uint32_t n_bits,
         CUK(u_image(std::integral_constant<int, 1>{}, &key->d_uconsts));
         key->has_u = true;
         CUK((cudaFuncSetAttribute(k_encrypt<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C, 1>::SMEM_BYTES)));
-        CUK((cudaFuncSetAttribute(k_tally<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C, 1>::SMEM_BYTES)));
+        CUK((cudaFuncSetAttribute(k_tally<C, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C, 1>::SMEM_BYTES)));
         CUK((cudaFuncSetAttribute(k_pow<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UL<C, 1>::SMEM_BYTES)));
     }
     if constexpr (UL<C, 1>::SUPPORTED && UL<C, 2>::SUPPORTED) {
@@ -1213,7 +1214,7 @@ static cudaError_t tally_cfg(Block28Key* key, const u64* d_c, size_t count, u64*
     else { key->peer.epoch += 1; P.epoch = key->peer.epoch; }
     bool done = false;
     if constexpr (UL<C, 1>::SUPPORTED) if (key->eng >= 2 && key->has_u) {
-        k_tally<C, 2><<<(unsigned)ctas, C::THREADS, UL<C, 1>::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
+        k_tally<C, 4><<<(unsigned)ctas, C::THREADS, UL<C, 1>::SMEM_BYTES, st>>>(key->dev, d_c, count, d_out, key->d_nodes, key->d_node_cnt, P);
         done = true;
     }
     if (done) {}

@@ -470,7 +470,9 @@ __device__ __forceinline__ void umma_load(uint32_t ta, int* v) {
 
 // q1 = T digits [L-1, 2L-1) as s8 rows; Q = hi(q1 mu); V = ripple(lo(T) - lo(Q Nt)).
 // WIT: stops after the low-part sums are in F (the exact tail of the witness step, w_tail_u, takes over from there)
-template <class C, int LG, bool WIT = false>
+// EL: the MMAs are issued by the lane elect.sync picks (3 instructions per MMA) instead of by thread 0 in divergent code (9, with
+// ptxas' per-thread serialisation loop).  Faster everywhere except in k_tally (5.27 against 5.09 ms), which keeps the old form.
+template <class C, int LG, bool WIT = false, bool EL = true>
 __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
     using U = UL<C, LG, WIT>;
     constexpr int G = C::G, BL = C::BL;
@@ -499,7 +501,7 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
     fence_async_smem();
     __syncthreads();
     if (cwarp == 0) {
-        if (elect_one()) { tc_fence_after(); umma_issue<C, LG, WIT, true>(S, 0); umma_issue<C, LG, WIT, true>(S, 1); }
+        if (EL ? elect_one() : lane == 0) { tc_fence_after(); umma_issue<C, LG, WIT, true>(S, 0); umma_issue<C, LG, WIT, true>(S, 1); }
         __syncwarp();
     }
     // T's upper halves are dead now: zero chunks in front of the q-hat rows
@@ -529,7 +531,7 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
                 if (lane == 0) mbar_arrive(&S.bars()[2 + (s & 1)]);
                 __syncwarp();
                 if (cwarp == 0) {
-                    if (elect_one()) {
+                    if (EL ? elect_one() : lane == 0) {
                         mbar_wait(&S.bars()[2 + (s & 1)], U::par_empty(true, s), dead);
                         tc_fence_after();
                         umma_issue<C, LG, WIT, true>(S, s + 2);
@@ -543,7 +545,7 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
         tc_fence_before();
         __syncthreads();                    // q-hat rows complete
         if (cwarp == 0) {
-            if (elect_one()) { tc_fence_after(); umma_issue<C, LG, WIT, false>(S, 0); umma_issue<C, LG, WIT, false>(S, 1); }
+            if (EL ? elect_one() : lane == 0) { tc_fence_after(); umma_issue<C, LG, WIT, false>(S, 0); umma_issue<C, LG, WIT, false>(S, 1); }
             __syncwarp();
         }
     }
@@ -562,7 +564,7 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
                 if (lane == 0) mbar_arrive(&S.bars()[2 + (s & 1)]);
                 __syncwarp();
                 if (cwarp == 0) {
-                    if (elect_one()) {
+                    if (EL ? elect_one() : lane == 0) {
                         mbar_wait(&S.bars()[2 + (s & 1)], U::par_empty(false, s), dead);
                         tc_fence_after();
                         umma_issue<C, LG, WIT, false>(S, s + 2);
@@ -597,10 +599,10 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
     }
 }
 
-template <class C, int LG, bool SQR>
+template <class C, int LG, bool SQR, bool EL = true>
 __device__ __forceinline__ void mulmod_u(SmemU<C, LG>& S, const int4* Y) {
     phase_product_u<C, LG>((int4*)S.base, Y, SQR ? 1 : 0, S.tmem);
-    phases_bc_umma<C, LG>((int4*)S.base, S.tmem);
+    phases_bc_umma<C, LG, false, EL>((int4*)S.base, S.tmem);
 }
 
 // ---- witness step on the tcgen05 phases --------------------------------------------------------------------------------------
