@@ -149,6 +149,16 @@ impl Key {
     pub fn words_in(&self) -> usize { unsafe { pb200_key_words_in(self.raw) as usize } }
     pub fn words_out(&self) -> usize { unsafe { pb200_key_words_out(self.raw) as usize } }
     pub fn as_ptr(&mut self) -> *mut pb200_key { self.raw }
+    /// name of the arithmetic engine in effect ("block28u<8,19>" = tcgen05 + TMEM phases at |n| = 2048, "block28t<..>", "simple64")
+    pub fn engine(&self) -> String {
+        unsafe { std::ffi::CStr::from_ptr(pb200_key_engine(self.raw)).to_string_lossy().into_owned() }
+    }
+    /// 0 = automatic (fastest), 1 = simple64, 2 = block28, 3 = block28t (mma.sync), 4 = block28u (tcgen05), 5 = block28u2; every engine
+    /// returns the same canonical words, so a host only calls this for A/B measurements
+    pub fn set_engine(&mut self, engine: i32) -> Result<(), i32> {
+        let rc = unsafe { pb200_key_set_engine(self.raw, engine as c_int) };
+        if rc == PB200_OK { Ok(()) } else { Err(rc) }
+    }
 
     /// batched `paillier_enc_native` (src/paillier.rs:87-92): `m`, `r` hold `count * words_in` words, the result `count * words_out`
     pub fn encrypt_batch(&mut self, m: &[u64], r: &[u64]) -> Result<Vec<u64>, i32> {
