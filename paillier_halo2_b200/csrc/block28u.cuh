@@ -22,7 +22,7 @@
 // Tiles: G ranges per ciphertext, one per warp of its lane group — 8 ranges of 5 digits (160 columns) with 8 warps, 16 ranges of 3
 // digits (192 columns) with 16; a warp folds one range from its TMEM quadrant and reads the 4 columns below its range itself for
 // the incoming carry, so tiles and ranges are independent of each other.
-// Two TMEM buffers per CTA; a warp that has read its columns out arrives on the buffer's "empty" mbarrier, thread 0 waits for the
+// Two TMEM buffers per CTA; a warp that has read its columns out arrives on the buffer's "empty" mbarrier, one thread of warp 0 waits for the
 // arrivals and issues the MMAs of the tile after next — no CTA barrier between tiles.
 //
 // Shared memory, LG = 1 (|n| = 2048: 111 KB, two CTAs per SM; 3072 / 4096: 166 / 211 KB, one): V | B | T(2L) | tail of the q-hat
@@ -512,7 +512,7 @@ __device__ __noinline__ void phases_bc_umma(int4* smem_base, uint32_t tmem) {
     const int ri = (U::NSH - 1 - j) * U::RPS + (cwarp >> 2);
     const uint32_t ta0 = S.tmem + (uint32_t)(U::RCOLS * ri - U::SHIFTC + 16 * j) + ((uint32_t)(32 * q) << 16);
     // Tiles are not separated by CTA barriers: a warp that has read its columns out of a TMEM buffer arrives on the buffer's "empty"
-    // mbarrier and goes on folding; thread 0 alone waits for the arrivals, issues the MMAs of the tile after next into the buffer,
+    // mbarrier and goes on folding; one thread of warp 0 alone waits for the arrivals, issues the MMAs of the tile after next into the buffer,
     // then folds its own columns.  Every mbarrier completes an even number of times per multiplication (four tiles per phase), so
     // all wait parities are constants.
     {
